@@ -1,0 +1,254 @@
+/*
+ * oimgpu.h — C ABI of liboimgpu.so, the B200-native block-I/O data path that replaces the
+ * SPDK vhost daemon behind intel/oim.
+ *
+ * Plain C: fixed-width integers, plain pointers and sizes, no callbacks, every function
+ * returns 0 / a non-negative count on success or -errno.  That makes it directly bindable
+ * from cgo, ctypes (oim_b200/_abi.py) and C++ (the JSON-RPC daemon).
+ *
+ * What each group replaces in the reference (paths relative to /root/reference,
+ * S/ = vendor/github.com/spdk/spdk/):
+ *
+ *   bdev control      construct_malloc_bdev   S/lib/bdev/malloc/bdev_malloc_rpc.c:63-106
+ *                                             S/lib/bdev/malloc/bdev_malloc.c:378-443
+ *                     construct_rbd_bdev      S/lib/bdev/rbd/bdev_rbd_rpc.c:102-148 (RPC shape only)
+ *                     delete_bdev / get_bdevs S/lib/bdev/rpc/bdev_rpc.c:216-300,396-433
+ *   vhost-scsi ctrl   construct_vhost_scsi_controller / add_vhost_scsi_lun /
+ *                     remove_vhost_scsi_target / remove_vhost_controller / get_vhost_controllers
+ *                                             S/lib/vhost/vhost_rpc.c:65-478, vhost_scsi.c:951-1103
+ *                     (called by pkg/spdk/spdk.go:47-286 and pkg/oim-controller/controller.go:55-212)
+ *   data path         one virtio-scsi request = what task_data_setup() hands to the SCSI layer
+ *                                             S/lib/vhost/vhost_scsi.c:490-653 (request build)
+ *                                             S/lib/scsi/scsi_bdev.c:1456-1802  (CDB decode, limits)
+ *                                             S/lib/bdev/malloc/bdev_malloc.c:153-233 (iovec copy / fill)
+ *                                             S/lib/copy/copy_engine.c:114-140 (the memcpy/memset)
+ *                                             S/lib/vhost/vhost_scsi.c:311-331 (response fields)
+ *   copy engine       struct spdk_copy_engine {copy, fill}   S/include/spdk_internal/copy_engine.h:47-53
+ */
+#ifndef OIMGPU_H
+#define OIMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OIMGPU_ABI_VERSION		1
+
+/* ---- limits taken from the reference ---------------------------------------------------- */
+#define OIMGPU_CDB_SIZE			32	/* VIRTIO_SCSI_CDB_SIZE */
+#define OIMGPU_SENSE_SIZE		18	/* fixed-format sense, S/lib/scsi/task.c:198-236 */
+#define OIMGPU_IOVS_MAX			129	/* SPDK_VHOST_IOVS_MAX, S/lib/vhost/vhost_internal.h:68 */
+#define OIMGPU_CTRLR_MAX_DEVS		8	/* SPDK_VHOST_SCSI_CTRLR_MAX_DEVS, vhost_internal.h:66 */
+#define OIMGPU_MAX_VQ_SIZE		1024	/* SPDK_VHOST_MAX_VQ_SIZE, vhost_internal.h:64 */
+#define OIMGPU_REQS_PER_PASS		32	/* reqs[32] in process_requestq, vhost_scsi.c:695 */
+#define OIMGPU_MAX_XFER_BYTES		(4u * 1024u * 1024u)	/* SPDK_WORK_BLOCK_SIZE, scsi_bdev.c:50 */
+#define OIMGPU_MAX_UNMAP_DESC		256	/* DEFAULT_MAX_UNMAP_BLOCK_DESCRIPTOR_COUNT, scsi_bdev.c:58 */
+#define OIMGPU_RESP_SIZE		108	/* sizeof(struct virtio_scsi_cmd_resp) */
+
+/* data direction, numerically equal to enum spdk_scsi_data_dir (S/include/spdk/scsi.h:66-70) */
+#define OIMGPU_DIR_NONE			0
+#define OIMGPU_DIR_TO_DEV		1	/* guest -> device  (WRITE, UNMAP parameter list) */
+#define OIMGPU_DIR_FROM_DEV		2	/* device -> guest  (READ, READ CAPACITY ...)     */
+
+/* virtio-scsi response codes (linux/virtio_scsi.h) */
+#define OIMGPU_S_OK			0
+#define OIMGPU_S_BAD_TARGET		3
+
+/* SCSI status */
+#define OIMGPU_STATUS_GOOD		0x00
+#define OIMGPU_STATUS_CHECK_CONDITION	0x02
+
+/* where the addresses in an SG list point */
+#define OIMGPU_MEM_DEVICE		0	/* device (HBM) pointers valid on the LUN's GPU */
+#define OIMGPU_MEM_HOST			1	/* host pointers; pinned + mapped by oimgpu_mem_register() */
+
+/* ---- wire structures (shared, bit for bit, by host code, the kernels and the oracle) ---- */
+
+/* One scatter-gather element: the iovec spdk_vhost_vring_desc_to_iov() produces
+ * (S/lib/vhost/vhost.c:461-509).  16 bytes so 32 of them load as one 512-byte bulk copy. */
+struct oimgpu_iov {
+	uint64_t addr;		/* byte-granular; no alignment requirement */
+	uint32_t len;
+	uint32_t flags;		/* reserved, must be 0 */
+};
+
+/* One request slot (64 bytes).  Bytes 0..50 are exactly struct virtio_scsi_cmd_req
+ * (lun[8], tag, task_attr, prio, crn, cdb[32]; packed) so a vhost front end can copy the guest's
+ * request header straight in; the tail carries what task_data_setup() derives from the
+ * descriptor chain (direction and the SG list). */
+struct oimgpu_req {
+	uint8_t  lun[8];	/* lun[0]==1, lun[1]=target, (lun[2]<<8|lun[3])&0x3FFF = LUN id */
+	uint64_t tag;
+	uint8_t  task_attr;
+	uint8_t  prio;
+	uint8_t  crn;
+	uint8_t  cdb[OIMGPU_CDB_SIZE];
+	uint8_t  dir;		/* OIMGPU_DIR_* */
+	uint16_t iovcnt;	/* number of SG elements (0..129; more => invalid request) */
+	uint16_t flags;		/* reserved, must be 0 */
+	uint32_t iov_start;	/* index of the first element in the SG table passed with the batch */
+	uint32_t reserved;
+};
+
+/* One completion (48 bytes).  Bytes 8..37 are the first 30 bytes of struct virtio_scsi_cmd_resp
+ * (sense_len, resid, status_qualifier, status, response, sense[0..17]) as written by
+ * spdk_vhost_scsi_task_cpl() (vhost_scsi.c:311-331); used_len is the length published in the
+ * used ring (vhost_scsi.c:296, 583, 612). */
+struct oimgpu_cpl {
+	uint64_t tag;
+	uint32_t sense_len;
+	uint32_t resid;
+	uint16_t status_qualifier;
+	uint8_t  status;
+	uint8_t  response;
+	uint8_t  sense[OIMGPU_SENSE_SIZE];
+	uint8_t  resp_valid;	/* 1 = response fields above were written; 0 = invalid_request()
+				 * (vhost_scsi.c:347-358): only the used-ring element is produced */
+	uint8_t  pad;
+	uint32_t used_len;
+	uint32_t data_transferred;	/* task->data_transferred, for debugging/iostat */
+};
+
+/* get_bdevs entry (S/lib/bdev/rpc/bdev_rpc.c:216-300) */
+struct oimgpu_bdev_info {
+	char     name[64];
+	char     product_name[32];	/* "Malloc disk" | "Ceph Rbd Disk" */
+	char     uuid[40];
+	uint64_t num_blocks;
+	uint32_t block_size;
+	int32_t  claimed;
+	int32_t  device;	/* CUDA device ordinal holding the backing store */
+	uint32_t replicas;	/* 1, or R for a mirrored bdev */
+	uint64_t device_ptr;	/* backing store base (device address; tests/digest only) */
+};
+
+/* get_vhost_controllers target entry (S/lib/vhost/vhost_scsi.c:1410-1456) */
+struct oimgpu_target_info {
+	int32_t  scsi_dev_num;
+	int32_t  id;
+	char     target_name[16];	/* "Target N" */
+	int32_t  lun_id;		/* always 0 */
+	char     bdev_name[64];
+};
+
+struct oimgpu_ctrlr_info {
+	char     ctrlr[64];
+	char     cpumask[20];		/* "0x1" */
+	uint32_t delay_base_us;
+	uint32_t iops_threshold;
+	char     socket[192];
+	uint32_t ntargets;
+	struct oimgpu_target_info targets[OIMGPU_CTRLR_MAX_DEVS];
+};
+
+/* per-LUN counters (the part of get_bdevs_iostat the path feeds, bdev_rpc.c:213) */
+struct oimgpu_iostat {
+	uint64_t num_read_ops, num_write_ops, num_unmap_ops, num_other_ops;
+	uint64_t bytes_read, bytes_written, bytes_unmapped;
+	uint64_t num_errors;
+	uint64_t kernel_launches;	/* launches of our kernels on this LUN's stream */
+};
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+
+int  oimgpu_abi_version(void);
+/* Initialise on the given CUDA device ordinals (devices==NULL: current device only).
+ * Fails with -ENODEV when no CUDA device is usable: there is no CPU fallback. */
+int  oimgpu_init(const int *devices, int ndevices);
+void oimgpu_fini(void);
+int  oimgpu_device_count(void);
+const char *oimgpu_version_string(void);
+
+/* ---- bdev control ----------------------------------------------------------------------- */
+
+/* construct_malloc_bdev: zero-filled backing store of num_blocks*block_size bytes in HBM.
+ * name==NULL -> "Malloc%d"; uuid==NULL -> random.  device<0 -> least-loaded initialised GPU.
+ * Returns 0 and the final name in name_out, -EINVAL (num_blocks==0, bad uuid, bad block size),
+ * -EEXIST, -ENOMEM. */
+int oimgpu_bdev_create_malloc(const char *name, const char *uuid, uint64_t num_blocks,
+			      uint32_t block_size, int device, char *name_out, size_t name_cap);
+/* construct_rbd_bdev: same HBM store, product "Ceph Rbd Disk"; size comes from size_bytes
+ * (the RBD image size the reference would learn from librbd). */
+int oimgpu_bdev_create_rbd(const char *name, const char *pool_name, const char *rbd_name,
+			   const char *user_id, uint32_t block_size, uint64_t size_bytes,
+			   int device, char *name_out, size_t name_cap);
+/* R-way mirrored malloc bdev: replica r lives on devices[r]; writes fan out over NVLink. */
+int oimgpu_bdev_create_mirror(const char *name, uint64_t num_blocks, uint32_t block_size,
+			      const int *devices, int nreplicas, char *name_out, size_t name_cap);
+int oimgpu_bdev_delete(const char *name);			/* -ENODEV if unknown, -EBUSY if attached */
+int oimgpu_bdev_get(const char *name, struct oimgpu_bdev_info *out);	/* -ENODEV if unknown */
+int oimgpu_bdev_list(struct oimgpu_bdev_info *out, int max);	/* returns count */
+/* test/digest helpers: raw access to the backing store of replica r (synchronous) */
+int oimgpu_bdev_read_raw(const char *name, int replica, uint64_t offset, void *dst, uint64_t len);
+int oimgpu_bdev_write_raw(const char *name, int replica, uint64_t offset, const void *src, uint64_t len);
+
+/* ---- vhost-scsi control ----------------------------------------------------------------- */
+
+int oimgpu_vhost_scsi_ctrlr_create(const char *ctrlr, const char *cpumask);	/* -EEXIST, -EINVAL */
+/* returns the target number used (>=0) or -ENODEV (no ctrlr), -EEXIST (occupied),
+ * -EINVAL (num >= 8 or no such bdev), -ENOSPC (num == -1 and all 8 used) */
+int oimgpu_vhost_scsi_add_lun(const char *ctrlr, int scsi_target_num, const char *bdev_name);
+int oimgpu_vhost_scsi_remove_target(const char *ctrlr, int scsi_target_num);	/* -ENODEV */
+int oimgpu_vhost_ctrlr_remove(const char *ctrlr);	/* -ENODEV, -EBUSY (has targets) */
+int oimgpu_vhost_ctrlr_get(const char *ctrlr, struct oimgpu_ctrlr_info *out);
+int oimgpu_vhost_ctrlr_list(struct oimgpu_ctrlr_info *out, int max);
+
+/* ---- data path -------------------------------------------------------------------------- */
+
+typedef struct oimgpu_lun oimgpu_lun;	/* one attached SCSI target: backing store + queues + stream */
+
+/* Open the data path of target `scsi_target_num` of `ctrlr` with `num_queues` request queues of
+ * `queue_size` slots (power of two, <= OIMGPU_MAX_VQ_SIZE) each.  The LUN gets its own CUDA
+ * stream on the GPU that holds the bdev. */
+int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t num_queues,
+		    uint32_t queue_size, oimgpu_lun **out);
+int oimgpu_lun_close(oimgpu_lun *lun);
+int oimgpu_lun_device(const oimgpu_lun *lun);
+
+/* Pin + map a host buffer so SG elements may point into it (OIMGPU_MEM_HOST).  The analogue of
+ * spdk_mem_register() on the guest's memory table (S/lib/vhost/vhost.c:1044-1100). */
+int oimgpu_mem_register(void *addr, size_t len);
+int oimgpu_mem_unregister(void *addr);
+
+/* Submit `nreqs` requests to queue `q` of the LUN.  reqs[i].iov_start indexes into `iovs`
+ * (niovs entries).  `mem` says where SG addresses AND the reqs/iovs/cpls arrays of this call live:
+ *   OIMGPU_MEM_HOST   : reqs/iovs are host arrays, copied to the device inside the call
+ *   OIMGPU_MEM_DEVICE : reqs/iovs are device arrays already resident in HBM (zero host work)
+ * Requests of one queue are executed in order in passes of <= 32 (process_requestq); requests of
+ * different queues have no mutual order.  Asynchronous: returns once the work is enqueued on the
+ * LUN's stream.  -EAGAIN when the queue has fewer than nreqs free slots. */
+int oimgpu_submit(oimgpu_lun *lun, uint32_t q, const struct oimgpu_req *reqs, uint32_t nreqs,
+		  const struct oimgpu_iov *iovs, uint32_t niovs, int mem);
+
+/* Run every queue's outstanding requests to completion on the LUN's stream ("kick").  With
+ * OIMGPU_MEM_DEVICE completions stay in HBM at the address returned by oimgpu_queue_cpl_ptr(). */
+int oimgpu_kick(oimgpu_lun *lun);
+/* Reap up to `max` completions of queue q in submission order into host memory; blocks until the
+ * kicked work is finished if wait != 0.  Returns the number reaped. */
+int oimgpu_poll(oimgpu_lun *lun, uint32_t q, struct oimgpu_cpl *cpls, uint32_t max, int wait);
+int oimgpu_lun_sync(oimgpu_lun *lun);	/* wait for everything kicked so far */
+
+/* One-call convenience for callers that own a whole batch: submit to `nq` queues
+ * (queue i gets reqs[i*per_q .. (i+1)*per_q) ), kick, wait, reap into cpls. */
+int oimgpu_submit_and_wait(oimgpu_lun *lun, uint32_t nq, uint32_t per_q,
+			   const struct oimgpu_req *reqs, const struct oimgpu_iov *iovs,
+			   uint32_t niovs, struct oimgpu_cpl *cpls, int mem);
+
+int oimgpu_lun_iostat(oimgpu_lun *lun, struct oimgpu_iostat *out);
+/* raw CUDA stream handle (cudaStream_t) of the LUN, for callers that time with CUDA events */
+void *oimgpu_lun_stream(oimgpu_lun *lun);
+
+/* ---- copy-engine level (B2): the operator SPDK's bdev_malloc calls ----------------------- */
+
+/* struct spdk_copy_engine.copy / .fill for device-resident buffers, enqueued on the LUN's
+ * stream; completion is observed with oimgpu_lun_sync(). */
+int oimgpu_copy_submit(oimgpu_lun *lun, void *dst, const void *src, uint64_t nbytes);
+int oimgpu_fill_submit(oimgpu_lun *lun, void *dst, uint8_t fill, uint64_t nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OIMGPU_H */

@@ -1,0 +1,100 @@
+"""ctypes bindings of the two CPU checkers (TEST INFRASTRUCTURE — never imported by oim_b200).
+
+  RefOracle   oracle/_ref/liboim_ref.so — the reference's own SPDK C sources compiled from
+              /root/reference (see oracle/Makefile, oracle/ref_driver.c)
+  PortOracle  oracle/liboim_oracle.so   — plain-C restatement (oracle/oim_oracle.c)
+
+Both expose: create(num_blocks, block_size, target) / store (numpy view of the backing store) /
+submit(reqs, iovs) -> cpls, with SG addresses being host pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oim_b200.abi import cpl_dtype, iov_dtype, req_dtype
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "liboim_ref.so")
+PORT_SO = os.path.join(_HERE, "liboim_oracle.so")
+
+
+def build(verbose: bool = False) -> None:
+    """(Re)build whichever checker can be built here (the reference needs /root/reference)."""
+    out = subprocess.run(["make", "-C", _HERE, "-j8", "all"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout[-3000:] + out.stderr[-3000:])
+    if verbose:
+        print(out.stdout[-2000:])
+
+
+class _Oracle:
+    prefix = ""
+    path = ""
+
+    def __init__(self, num_blocks: int, block_size: int = 512, target: int = 0):
+        if not os.path.exists(self.path):
+            raise FileNotFoundError(self.path)
+        self.lib = C.CDLL(self.path)
+        p = self.prefix
+        self._create = getattr(self.lib, p + "_create")
+        self._create.restype = C.c_void_p
+        self._create.argtypes = [C.c_uint64, C.c_uint32, C.c_int]
+        self._destroy = getattr(self.lib, p + "_destroy")
+        self._destroy.argtypes = [C.c_void_p]
+        self._store = getattr(self.lib, p + "_store")
+        self._store.restype = C.c_void_p
+        self._store.argtypes = [C.c_void_p]
+        self._submit = getattr(self.lib, p + "_submit")
+        self._submit.restype = C.c_int
+        self._submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        self._set_removed = getattr(self.lib, p + "_set_removed")
+        self._set_removed.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.h = self._create(num_blocks, block_size, target)
+        if not self.h:
+            raise RuntimeError(f"{p}_create failed")
+        self.num_blocks, self.block_size, self.target = num_blocks, block_size, target
+        addr = self._store(self.h)
+        buf = (C.c_uint8 * (num_blocks * block_size)).from_address(addr)
+        self.store = np.frombuffer(buf, dtype=np.uint8)
+
+    def submit(self, reqs: np.ndarray, iovs: np.ndarray) -> np.ndarray:
+        assert reqs.dtype == req_dtype and iovs.dtype == iov_dtype
+        reqs = np.ascontiguousarray(reqs)
+        iovs = np.ascontiguousarray(iovs)
+        cpls = np.zeros(len(reqs), dtype=cpl_dtype)
+        rc = self._submit(self.h, reqs.ctypes.data, len(reqs), iovs.ctypes.data, len(iovs),
+                          cpls.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_submit rc={rc}")
+        return cpls
+
+    def set_removed(self, target: int, removed: bool = True) -> None:
+        self._set_removed(self.h, target, int(removed))
+
+    def close(self) -> None:
+        if self.h:
+            self.store = None
+            self._destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class RefOracle(_Oracle):
+    prefix, path = "oimref", REF_SO
+
+
+class PortOracle(_Oracle):
+    prefix, path = "oimorc", PORT_SO
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_SO)

@@ -1,0 +1,637 @@
+/*
+ * oim_oracle.c — TEST INFRASTRUCTURE: plain-C restatement of the reference's block-I/O hot path.
+ *
+ * Parity status: PINNED.  This file is checked (tests/test_oracle_vs_ref.py) against
+ * oracle/_ref/liboim_ref.so, which is the reference's own SPDK sources compiled from
+ * /root/reference and driven through process_requestq() (oracle/ref_driver.c), on the golden
+ * cases of SPDK's unit tests (scsi_bdev_ut.c:639-897, vhost_ut.c:153-235), the bdevio data-integrity
+ * suite (S/test/bdev/bdevio/bdevio.c:388-800) and seeded random request traces; the resulting
+ * vectors are committed under tests/golden/ so the check also runs where /root/reference is absent.
+ *
+ * One function per reference function, each citing the file:line it follows
+ * (S/ = /root/reference/vendor/github.com/spdk/spdk/).  Requests are executed strictly in
+ * submission order, as the single reactor thread does.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may load this library; the product
+ * (oim_b200/, liboimgpu.so) never does.
+ */
+#include <errno.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdbool.h>
+
+#include "oimgpu.h"
+
+_Static_assert(sizeof(struct oimgpu_req) == 64, "oimgpu_req must be 64 bytes");
+_Static_assert(sizeof(struct oimgpu_iov) == 16, "oimgpu_iov must be 16 bytes");
+_Static_assert(sizeof(struct oimgpu_cpl) == 48, "oimgpu_cpl must be 48 bytes");
+_Static_assert(offsetof(struct oimgpu_req, cdb) == 19, "cdb offset = virtio_scsi_cmd_req.cdb");
+_Static_assert(offsetof(struct oimgpu_req, dir) == 51, "tail starts after the 51-byte virtio header");
+_Static_assert(offsetof(struct oimgpu_cpl, sense) == 20, "sense offset");
+
+/* SCSI constants (S/include/spdk/scsi_spec.h) */
+enum {
+	SC_GOOD = 0x00, SC_CHECK_CONDITION = 0x02,
+	SK_NO_SENSE = 0x0, SK_ILLEGAL_REQUEST = 0x5, SK_ABORTED_COMMAND = 0xb,
+	ASC_NONE = 0x00, ASC_INVALID_OPCODE = 0x20, ASC_LBA_OOR = 0x21, ASC_INVALID_FIELD = 0x24,
+	ASC_LUN_NOT_SUPPORTED = 0x25,
+	ASCQ_NONE = 0x00,
+};
+enum { TASK_COMPLETE = 0, TASK_PENDING = 1, TASK_UNKNOWN = 2 };
+
+/* struct malloc_disk (S/lib/bdev/malloc/bdev_malloc.c:50-54) + the bits of struct spdk_bdev used */
+struct orc_bdev {
+	uint8_t  *buf;		/* malloc_buf: num_blocks*block_size zero-filled bytes */
+	uint64_t blockcnt;
+	uint32_t blocklen;
+};
+
+/* per-session target state (struct spdk_scsi_dev_vhost_state, vhost_scsi.c:66-71) */
+struct orc_tgt {
+	struct orc_bdev *bdev;	/* LUN 0's bdev, NULL = no device in this slot */
+	bool removed;		/* session saw a hot-remove (vhost_scsi.c:1093-1100) */
+	bool lun_removed;	/* spdk_scsi_lun.removed: LUN being torn down (lun.c:171-176) */
+};
+
+struct oimorc {
+	struct orc_bdev bdev;
+	struct orc_tgt  tgt[OIMGPU_CTRLR_MAX_DEVS];
+};
+
+/* struct spdk_scsi_task, the fields the path touches (S/include/spdk/scsi.h:97-146) */
+struct orc_task {
+	uint8_t  status;
+	uint32_t transfer_len, length, dxfer_dir, data_transferred;
+	const uint8_t *cdb;
+	struct { uint8_t *base; uint32_t len; } iovs[OIMGPU_IOVS_MAX];
+	uint16_t iovcnt;
+	uint8_t  sense_data[32];
+	uint32_t sense_data_len;
+};
+
+static inline uint16_t be16(const uint8_t *p) { return (uint16_t)(p[0] << 8 | p[1]); }
+static inline uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+static inline uint64_t be64(const uint8_t *p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
+static inline void to_be32(uint8_t *p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
+static inline void to_be64(uint8_t *p, uint64_t v) { to_be32(p, v >> 32); to_be32(p + 4, (uint32_t)v); }
+
+/* spdk_scsi_task_build_sense_data + spdk_scsi_task_set_status (S/lib/scsi/task.c:198-247) */
+static void task_set_status(struct orc_task *t, int sc, int sk, int asc, int ascq)
+{
+	if (sc == SC_CHECK_CONDITION) {
+		uint8_t *cp = t->sense_data;
+		memset(cp, 0, 18);
+		cp[0] = 0x80 | 0x70;	/* VALID | current, fixed format */
+		cp[2] = sk & 0xf;
+		cp[7] = 10;		/* additional sense length */
+		cp[12] = asc;
+		cp[13] = ascq;
+		t->sense_data_len = 18;
+	}
+	t->status = sc;
+}
+
+/* spdk_scsi_task_scatter_data (S/lib/scsi/task.c:111-152); the internal-buffer branch
+ * (iovcnt==1 && iov_base==NULL) cannot be reached with mapped SG elements and is left out */
+static int task_scatter_data(struct orc_task *t, const uint8_t *src, size_t buf_len)
+{
+	size_t len = 0, buf_left = buf_len;
+	int i;
+
+	if (buf_len == 0) return 0;
+	for (i = 0; i < t->iovcnt; i++) len += t->iovs[i].len;
+	if (len < buf_len) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD, ASCQ_NONE);
+		return -1;
+	}
+	for (i = 0; i < t->iovcnt; i++) {
+		len = t->iovs[i].len < buf_left ? t->iovs[i].len : buf_left;
+		buf_left -= len;
+		if (len) memcpy(t->iovs[i].base, src, len);
+		src += len;
+	}
+	return (int)buf_len;
+}
+
+/* spdk_bdev_bytes_to_blocks + spdk_bdev_io_valid_blocks (S/lib/bdev/bdev.c:2474-2509) */
+static int bdev_bytes_to_blocks(const struct orc_bdev *b, uint64_t off, uint64_t *off_blk,
+				uint64_t n, uint64_t *n_blk)
+{
+	*off_blk = off / b->blocklen;
+	*n_blk = n / b->blocklen;
+	return (off % b->blocklen) | (n % b->blocklen) ? -1 : 0;
+}
+static bool bdev_valid_blocks(const struct orc_bdev *b, uint64_t off_blk, uint64_t n_blk)
+{
+	if (off_blk + n_blk < off_blk) return false;
+	if (off_blk + n_blk > b->blockcnt) return false;
+	return true;
+}
+
+/* bdev_malloc_check_iov_len (S/lib/bdev/malloc/bdev_malloc.c:137-150): fails only when the
+ * iovecs are SHORTER than nbytes */
+static int malloc_check_iov_len(const struct orc_task *t, size_t nbytes)
+{
+	int i;
+	for (i = 0; i < t->iovcnt; i++) {
+		if (nbytes < t->iovs[i].len) return 0;
+		nbytes -= t->iovs[i].len;
+	}
+	return nbytes != 0;
+}
+
+/* spdk_bdev_readv -> bdev_malloc_readv -> mem_copy_submit
+ * (bdev.c:2559-2602, bdev_malloc.c:153-185, S/lib/copy/copy_engine.c:114-126).
+ * Returns 0, -EINVAL, or 1 when the bdev_io itself completes FAILED. */
+static int bdev_readv(struct orc_bdev *b, struct orc_task *t, uint64_t offset, uint64_t nbytes)
+{
+	uint64_t ob, nb;
+	const uint8_t *src;
+	int i;
+
+	if (bdev_bytes_to_blocks(b, offset, &ob, nbytes, &nb) != 0) return -EINVAL;
+	if (!bdev_valid_blocks(b, ob, nb)) return -EINVAL;
+	if (malloc_check_iov_len(t, nb * b->blocklen)) return 1;
+	src = b->buf + ob * b->blocklen;
+	for (i = 0; i < t->iovcnt; i++) {
+		if (t->iovs[i].len) memcpy(t->iovs[i].base, src, t->iovs[i].len);
+		src += t->iovs[i].len;
+	}
+	return 0;
+}
+
+/* spdk_bdev_writev -> bdev_malloc_writev -> mem_copy_submit (bdev.c:2656-2703, bdev_malloc.c:188-219) */
+static int bdev_writev(struct orc_bdev *b, struct orc_task *t, uint64_t offset, uint64_t nbytes)
+{
+	uint64_t ob, nb;
+	uint8_t *dst;
+	int i;
+
+	if (bdev_bytes_to_blocks(b, offset, &ob, nbytes, &nb) != 0) return -EINVAL;
+	if (!bdev_valid_blocks(b, ob, nb)) return -EINVAL;
+	if (malloc_check_iov_len(t, nb * b->blocklen)) return 1;
+	dst = b->buf + ob * b->blocklen;
+	for (i = 0; i < t->iovcnt; i++) {
+		if (t->iovs[i].len) memcpy(dst, t->iovs[i].base, t->iovs[i].len);
+		dst += t->iovs[i].len;
+	}
+	return 0;
+}
+
+/* spdk_bdev_unmap_blocks -> bdev_malloc_unmap -> mem_copy_fill
+ * (bdev.c:2780-2821, bdev_malloc.c:222-233, copy_engine.c:128-140) */
+static int bdev_unmap_blocks(struct orc_bdev *b, uint64_t ob, uint64_t nb)
+{
+	if (!bdev_valid_blocks(b, ob, nb)) return -EINVAL;
+	if (nb == 0) return -EINVAL;
+	memset(b->buf + ob * b->blocklen, 0, nb * b->blocklen);
+	return 0;
+}
+
+/* bdev_io FAILED -> spdk_bdev_io_get_scsi_status default branch (bdev.c:3391-3423) */
+static void task_set_bdev_failed(struct orc_task *t)
+{
+	task_set_status(t, SC_CHECK_CONDITION, SK_ABORTED_COMMAND, ASC_NONE, ASCQ_NONE);
+}
+
+/* spdk_bdev_scsi_read (S/lib/scsi/scsi_bdev.c:1318-1357) */
+static int scsi_read(struct orc_bdev *b, struct orc_task *t, uint64_t lba)
+{
+	uint64_t nbytes = t->length;	/* NOT xfer_len*blocklen: the payload length rules */
+	int rc = bdev_readv(b, t, lba * b->blocklen, nbytes);
+
+	if (rc < 0) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, ASC_NONE, ASCQ_NONE);
+		return TASK_COMPLETE;
+	}
+	t->data_transferred = (uint32_t)nbytes;
+	if (rc > 0) task_set_bdev_failed(t);
+	return TASK_PENDING;
+}
+
+/* spdk_bdev_scsi_write (scsi_bdev.c:1360-1411) */
+static int scsi_write(struct orc_bdev *b, struct orc_task *t, uint64_t lba, uint32_t len)
+{
+	uint64_t nbytes = (uint64_t)len * b->blocklen;
+	int rc;
+
+	if (nbytes > t->transfer_len) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, ASC_NONE, ASCQ_NONE);
+		return TASK_COMPLETE;
+	}
+	rc = bdev_writev(b, t, lba * b->blocklen, t->length);
+	if (rc < 0) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, ASC_NONE, ASCQ_NONE);
+		return TASK_COMPLETE;
+	}
+	t->data_transferred = t->length;
+	if (rc > 0) task_set_bdev_failed(t);
+	return TASK_PENDING;
+}
+
+/* spdk_bdev_scsi_readwrite (scsi_bdev.c:1456-1511) */
+static int scsi_readwrite(struct orc_bdev *b, struct orc_task *t, uint64_t lba, uint32_t xfer_len,
+			  bool is_read)
+{
+	uint32_t max_xfer_len;
+
+	t->data_transferred = 0;
+	if (t->dxfer_dir != OIMGPU_DIR_NONE &&
+	    t->dxfer_dir != (is_read ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV)) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, ASC_NONE, ASCQ_NONE);
+		return TASK_COMPLETE;
+	}
+	if (b->blockcnt <= lba || b->blockcnt - lba < xfer_len) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_LBA_OOR, ASCQ_NONE);
+		return TASK_COMPLETE;
+	}
+	if (xfer_len == 0) {
+		t->status = SC_GOOD;
+		return TASK_COMPLETE;
+	}
+	max_xfer_len = OIMGPU_MAX_XFER_BYTES / b->blocklen;
+	if (xfer_len > max_xfer_len) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD, ASCQ_NONE);
+		return TASK_COMPLETE;
+	}
+	return is_read ? scsi_read(b, t, lba) : scsi_write(b, t, lba, xfer_len);
+}
+
+/* spdk_bdev_scsi_sync (scsi_bdev.c:1414-1454); Malloc FLUSH is a no-op success (bdev_malloc.c:235-241) */
+static int scsi_sync(struct orc_bdev *b, struct orc_task *t, uint64_t lba, uint32_t num_blocks)
+{
+	if (num_blocks == 0) return TASK_COMPLETE;
+	if (lba >= b->blockcnt || num_blocks > b->blockcnt || lba > b->blockcnt - num_blocks) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, ASC_NONE, ASCQ_NONE);
+		return TASK_COMPLETE;
+	}
+	t->data_transferred = 0;
+	return TASK_PENDING;
+}
+
+/* __copy_desc + spdk_bdev_scsi_unmap (scsi_bdev.c:1545-1679) */
+static int scsi_unmap(struct orc_bdev *b, struct orc_task *t)
+{
+	uint8_t *data = NULL, *gathered = NULL;
+	size_t data_len = 0;
+	int desc_count = -1, i, submitted = 0;
+
+	if (t->iovcnt == 1) {
+		data = t->iovs[0].base;
+		data_len = t->iovs[0].len;
+	} else {
+		/* spdk_scsi_task_gather_data (task.c:154-186) */
+		for (i = 0; i < t->iovcnt; i++) data_len += t->iovs[i].len;
+		if (data_len != 0) {
+			uint8_t *pos = gathered = malloc(data_len);
+			for (i = 0; i < t->iovcnt; i++) {
+				memcpy(pos, t->iovs[i].base, t->iovs[i].len);
+				pos += t->iovs[i].len;
+			}
+			data = gathered;
+		}
+	}
+	if (data && data_len >= 8) {
+		uint16_t desc_data_len = be16(&data[2]);
+		if (desc_data_len <= data_len - 8 && desc_data_len / 16 <= OIMGPU_MAX_UNMAP_DESC) {
+			desc_count = desc_data_len / 16;
+		}
+	}
+	if (desc_count < 0) {
+		free(gathered);
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD, ASCQ_NONE);
+		return TASK_COMPLETE;
+	}
+	for (i = 0; i < desc_count; i++) {
+		const uint8_t *d = &data[8 + 16 * i];
+		uint64_t ob = be64(d);
+		uint32_t nb = be32(d + 8);
+
+		if (nb == 0) continue;
+		if (bdev_unmap_blocks(b, ob, nb) != 0) {
+			/* descriptors before this one stay applied; the rest are skipped */
+			task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, ASC_NONE, ASCQ_NONE);
+			break;
+		}
+		submitted++;
+	}
+	free(gathered);
+	return submitted == 0 ? TASK_COMPLETE : TASK_PENDING;
+}
+
+/* spdk_bdev_scsi_process_block (scsi_bdev.c:1681-1802) */
+static int scsi_process_block(struct orc_bdev *b, struct orc_task *t)
+{
+	const uint8_t *cdb = t->cdb;
+	uint64_t lba;
+	uint32_t xfer_len, len;
+
+	switch (cdb[0]) {
+	case 0x08: case 0x0a:	/* READ_6 / WRITE_6 */
+		lba = (uint64_t)cdb[1] << 16 | (uint64_t)cdb[2] << 8 | cdb[3];
+		xfer_len = cdb[4];
+		if (xfer_len == 0) xfer_len = 256;
+		return scsi_readwrite(b, t, lba, xfer_len, cdb[0] == 0x08);
+	case 0x28: case 0x2a:	/* READ_10 / WRITE_10 */
+		return scsi_readwrite(b, t, be32(&cdb[2]), be16(&cdb[7]), cdb[0] == 0x28);
+	case 0xa8: case 0xaa:	/* READ_12 / WRITE_12 */
+		return scsi_readwrite(b, t, be32(&cdb[2]), be32(&cdb[6]), cdb[0] == 0xa8);
+	case 0x88: case 0x8a:	/* READ_16 / WRITE_16 */
+		return scsi_readwrite(b, t, be64(&cdb[2]), be32(&cdb[10]), cdb[0] == 0x88);
+
+	case 0x25: {		/* READ CAPACITY (10) */
+		uint8_t buffer[8];
+		if (b->blockcnt - 1 > 0xffffffffULL) memset(buffer, 0xff, 4);
+		else to_be32(buffer, (uint32_t)(b->blockcnt - 1));
+		to_be32(&buffer[4], b->blocklen);
+		len = t->length < sizeof(buffer) ? t->length : sizeof(buffer);
+		if (task_scatter_data(t, buffer, len) < 0) break;
+		t->data_transferred = len;
+		t->status = SC_GOOD;
+		break;
+	}
+	case 0x9e:		/* SERVICE ACTION IN (16) */
+		if ((cdb[1] & 0x1f) != 0x10) return TASK_UNKNOWN;
+		{		/* READ CAPACITY (16) */
+			uint8_t buffer[32] = {0};
+			to_be64(&buffer[0], b->blockcnt - 1);
+			to_be32(&buffer[8], b->blocklen);
+			buffer[14] |= 1 << 7;	/* TPE: Malloc supports UNMAP (bdev_malloc.c:326-340) */
+			len = be32(&cdb[10]) < sizeof(buffer) ? be32(&cdb[10]) : sizeof(buffer);
+			if (task_scatter_data(t, buffer, len) < 0) break;
+			t->data_transferred = len;
+			t->status = SC_GOOD;
+		}
+		break;
+
+	case 0x35: case 0x91:	/* SYNCHRONIZE CACHE (10) / (16) */
+		if (cdb[0] == 0x35) { lba = be32(&cdb[2]); len = be16(&cdb[7]); }
+		else { lba = be64(&cdb[2]); len = be32(&cdb[10]); }
+		if (len == 0) len = (uint32_t)(b->blockcnt - lba);	/* u64 -> u32 truncation as in the reference */
+		return scsi_sync(b, t, lba, len);
+
+	case 0x42:		/* UNMAP */
+		return scsi_unmap(b, t);
+
+	default:
+		return TASK_UNKNOWN;
+	}
+	return TASK_COMPLETE;
+}
+
+/* spdk_bdev_scsi_process_primary (scsi_bdev.c:1827-2077): the commands that need no page tables.
+ * INQUIRY / MODE SENSE / MODE SELECT / REPORT LUNS are SURVEY.md §8(f) rank 1 ("next"). */
+static int scsi_process_primary(struct orc_bdev *b, struct orc_task *t)
+{
+	const uint8_t *cdb = t->cdb;
+	int rc = 0, data_len = -1, alloc_len = -1;
+	uint8_t data[32];
+
+	(void)b;
+	switch (cdb[0]) {
+	case 0x03:		/* REQUEST SENSE */
+		if (cdb[1] & 0x1) {
+			task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD, ASCQ_NONE);
+			break;
+		}
+		alloc_len = cdb[4];
+		task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, 0, 0);	/* build_sense_data only... */
+		t->status = SC_GOOD;						/* ...status is set below */
+		data_len = (int)t->sense_data_len;
+		memcpy(data, t->sense_data, data_len);
+		break;
+	case 0x4c: case 0x4d:	/* LOG SELECT / LOG SENSE */
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE, ASCQ_NONE);
+		rc = -1;
+		break;
+	case 0x00: case 0x1b:	/* TEST UNIT READY / START STOP UNIT */
+		rc = 0;
+		break;
+	default:
+		return TASK_UNKNOWN;
+	}
+	if (rc >= 0 && data_len > 0) {
+		task_scatter_data(t, data, alloc_len < data_len ? alloc_len : data_len);
+		rc = data_len < alloc_len ? data_len : alloc_len;
+	}
+	if (rc >= 0) {
+		t->data_transferred = rc;
+		t->status = SC_GOOD;
+	}
+	return TASK_COMPLETE;
+}
+
+/* spdk_bdev_scsi_execute (scsi_bdev.c:2079-2097) */
+static void scsi_execute(struct orc_bdev *b, struct orc_task *t)
+{
+	int rc = scsi_process_block(b, t);
+	if (rc == TASK_UNKNOWN) rc = scsi_process_primary(b, t);
+	if (rc == TASK_UNKNOWN) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE, ASCQ_NONE);
+	}
+}
+
+/* spdk_scsi_task_process_null_lun (S/lib/scsi/task.c:258-293) */
+static void task_process_null_lun(struct orc_task *t)
+{
+	t->length = t->transfer_len;
+	if (t->cdb[0] == 0x12) {	/* INQUIRY */
+		uint8_t buffer[36];
+		uint32_t alloc_len = be16(&t->cdb[3]);
+		memset(buffer, 0, sizeof(buffer));
+		buffer[0] = 0x03 << 5 | 0x1f;
+		buffer[4] = sizeof(buffer) - 5;
+		if (task_scatter_data(t, buffer, alloc_len < sizeof(buffer) ? alloc_len : sizeof(buffer)) >= 0) {
+			t->data_transferred = sizeof(buffer);
+			t->status = SC_GOOD;
+		}
+	} else {
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_LUN_NOT_SUPPORTED, ASCQ_NONE);
+		t->data_transferred = 0;
+	}
+}
+
+/* One request through process_requestq's loop body (vhost_scsi.c:702-739):
+ * task_data_setup (490-624) -> spdk_vhost_scsi_task_init_target (361-387) -> process_request
+ * (626-653) -> task_submit / early completion / invalid_request -> spdk_vhost_scsi_task_cpl (311-331) */
+static void process_one(struct oimorc *o, const struct oimgpu_req *q, const struct oimgpu_iov *iovs,
+			struct oimgpu_cpl *c)
+{
+	struct orc_task t;
+	uint32_t cnt = q->iovcnt, len = 0, i, used_len;
+	bool from_dev = (q->dir == OIMGPU_DIR_FROM_DEV) || cnt == 0;
+	struct orc_tgt *tgt;
+	struct orc_bdev *lun_bdev = NULL;
+	uint16_t lun_id;
+
+	memset(&t, 0, sizeof(t));
+	memset(c, 0, sizeof(*c));
+	c->tag = q->tag;
+	t.cdb = q->cdb;
+	t.dxfer_dir = from_dev ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV;
+
+	/* ---- task_data_setup ---- */
+	if (cnt == 0) {
+		/* "TEST UNIT READY command and some others might not contain any payload" (548-560) */
+		used_len = OIMGPU_RESP_SIZE;
+		t.iovcnt = 1;
+		t.iovs[0].base = NULL;
+		t.iovs[0].len = 0;
+	} else {
+		for (i = 0; i < cnt; i++) {
+			const struct oimgpu_iov *v = &iovs[q->iov_start + i];
+			/* spdk_vhost_vring_desc_to_iov (vhost.c:461-509) with GPA == VA: one iovec per
+			 * descriptor; fails at the 130th element or on an untranslatable (0) address */
+			if (i >= OIMGPU_IOVS_MAX || v->addr == 0) {
+				c->used_len = 0;	/* invalid_request(): used elem only */
+				c->resp_valid = 0;
+				return;
+			}
+			t.iovs[i].base = (uint8_t *)(uintptr_t)v->addr;
+			t.iovs[i].len = v->len;
+			len += v->len;
+		}
+		t.iovcnt = cnt;
+		used_len = from_dev ? OIMGPU_RESP_SIZE + len : OIMGPU_RESP_SIZE;
+	}
+	t.length = t.transfer_len = len;
+	c->used_len = used_len;
+	c->resp_valid = 1;
+
+	/* ---- spdk_vhost_scsi_task_init_target ---- */
+	lun_id = (((uint16_t)q->lun[2] << 8) | q->lun[3]) & 0x3FFF;
+	if (q->lun[0] != 1 || q->lun[1] >= OIMGPU_CTRLR_MAX_DEVS) {
+		c->response = OIMGPU_S_BAD_TARGET;
+		return;
+	}
+	tgt = &o->tgt[q->lun[1]];
+	if (tgt->bdev == NULL || tgt->removed) {
+		if (!tgt->removed) {
+			c->response = OIMGPU_S_BAD_TARGET;
+			return;
+		}
+		/* hot-detached: LUN stays NULL so the guest gets a sense code */
+	} else if (lun_id == 0) {
+		lun_bdev = tgt->bdev;	/* spdk_scsi_dev_get_lun(dev, 0) */
+	}
+
+	c->response = OIMGPU_S_OK;
+	if (lun_bdev == NULL) {
+		task_process_null_lun(&t);
+	} else {
+		/* _spdk_scsi_lun_execute_task (S/lib/scsi/lun.c:163-189) */
+		t.status = SC_GOOD;
+		if (tgt->lun_removed) {
+			/* spdk_scsi_task_process_abort (task.c:295-302) */
+			task_set_status(&t, SC_CHECK_CONDITION, SK_ABORTED_COMMAND, ASC_NONE, ASCQ_NONE);
+		} else {
+			scsi_execute(lun_bdev, &t);
+		}
+	}
+
+	/* ---- spdk_vhost_scsi_task_cpl ---- */
+	c->status = t.status;
+	if (t.status != SC_GOOD) {
+		memcpy(c->sense, t.sense_data, t.sense_data_len);
+		c->sense_len = t.sense_data_len;
+	}
+	c->resid = t.length - t.data_transferred;
+	c->data_transferred = t.data_transferred;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+
+void *oimorc_create(uint64_t num_blocks, uint32_t block_size, int target_num)
+{
+	struct oimorc *o;
+
+	/* create_malloc_disk (bdev_malloc.c:378-443): zero blocks refused, 2 MiB-aligned zeroed buffer */
+	if (num_blocks == 0 || block_size == 0 || target_num < 0 || target_num >= OIMGPU_CTRLR_MAX_DEVS) return NULL;
+	o = calloc(1, sizeof(*o));
+	if (!o) return NULL;
+	if (posix_memalign((void **)&o->bdev.buf, 2 * 1024 * 1024, num_blocks * block_size) != 0) {
+		free(o);
+		return NULL;
+	}
+	memset(o->bdev.buf, 0, num_blocks * block_size);
+	o->bdev.blockcnt = num_blocks;
+	o->bdev.blocklen = block_size;
+	o->tgt[target_num].bdev = &o->bdev;
+	return o;
+}
+
+void oimorc_destroy(void *h)
+{
+	struct oimorc *o = h;
+	if (!o) return;
+	free(o->bdev.buf);
+	free(o);
+}
+
+uint8_t *oimorc_store(void *h) { return ((struct oimorc *)h)->bdev.buf; }
+uint64_t oimorc_num_blocks(void *h) { return ((struct oimorc *)h)->bdev.blockcnt; }
+
+void oimorc_set_removed(void *h, int target_num, int removed)
+{
+	((struct oimorc *)h)->tgt[target_num].removed = removed != 0;
+}
+
+int oimorc_submit(void *h, const struct oimgpu_req *reqs, uint32_t nreqs,
+		  const struct oimgpu_iov *iovs, uint32_t niovs, struct oimgpu_cpl *cpls)
+{
+	uint32_t i;
+	(void)niovs;
+	for (i = 0; i < nreqs; i++) process_one(h, &reqs[i], iovs, &cpls[i]);
+	return 0;
+}
+
+/* spdk_vhost_vring_desc_to_iov (S/lib/vhost/vhost.c:461-509) over a region table
+ * {gpa, size, hva} x nregions (rte_vhost_gpa_to_vva, rte_vhost.h:133-150). */
+static uint64_t gpa_to_vva(const uint64_t *reg, uint32_t n, uint64_t gpa)
+{
+	uint32_t i;
+	for (i = 0; i < n; i++) {
+		if (gpa >= reg[3 * i] && gpa < reg[3 * i] + reg[3 * i + 1]) return gpa - reg[3 * i] + reg[3 * i + 2];
+	}
+	return 0;
+}
+
+int oimorc_desc_to_iov(const uint64_t *regions, uint32_t nregions, uint64_t addr, uint32_t len,
+		       struct oimgpu_iov *out, uint32_t start_index)
+{
+	const uint64_t MB2 = 2ull * 1024 * 1024;
+	uint32_t remaining = len, idx = start_index;
+	uint64_t payload = addr;
+
+	do {
+		uint64_t vva;
+		uint32_t to_boundary, l;
+		if (idx >= OIMGPU_IOVS_MAX) return -1;
+		vva = gpa_to_vva(regions, nregions, payload);
+		if (vva == 0) return -1;
+		to_boundary = (uint32_t)(MB2 - (payload & (MB2 - 1)));
+		if (remaining <= to_boundary) {
+			l = remaining;
+		} else {
+			/* split only where the two sides of a 2 MiB boundary are not VA-contiguous */
+			l = to_boundary;
+			while (l < remaining) {
+				if (vva + l != gpa_to_vva(regions, nregions, payload + l)) break;
+				l += (remaining - l) < MB2 ? (remaining - l) : (uint32_t)MB2;
+			}
+		}
+		out[idx - start_index].addr = vva;
+		out[idx - start_index].len = l;
+		out[idx - start_index].flags = 0;
+		remaining -= l;
+		payload += l;
+		idx++;
+	} while (remaining);
+	return (int)(idx - start_index);
+}
+
+const char *oimorc_describe(void)
+{
+	return "port: plain-C restatement of SPDK v19.04-pre vhost-scsi/scsi/bdev/malloc path (oracle/oim_oracle.c)";
+}
