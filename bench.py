@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on its configs[1]: 4 KiB random-read IOPS on one 8 GiB
+HBM-resident Malloc bdev per GPU (qd=32 per request queue, Q queues), plus 128 KiB sequential GB/s.
+
+  python bench.py [--gpus N --steps K --warmup W]            our CUDA path  (one rank per GPU under torchrun)
+  python bench.py --impl reference [...]                      the reference's CPU path on the host cores
+
+One "step" = one pass of the hot path over one batch: every queue of the LUN gets `per_queue`
+requests and the LUN is kicked once.  `value` is measured with requests, SG lists, client buffers
+and completions resident in HBM (CUDA events on the LUN's stream); `e2e` goes through the C ABI
+with host arrays and pinned host client buffers, PCIe traffic inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from oim_b200 import abi, traces  # noqa: E402
+
+NUM_BLOCKS = 16777216          # 8 GiB / 512 B  (BASELINE.json configs[1])
+BLOCK = 512
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--queues", type=int, default=int(os.environ.get("OIM_BENCH_QUEUES", 1184)))
+    p.add_argument("--per-queue", type=int, default=int(os.environ.get("OIM_BENCH_PER_QUEUE", 512)))
+    p.add_argument("--e2e-queues", type=int, default=256)
+    p.add_argument("--e2e-per-queue", type=int, default=512)
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--no-seq", action="store_true", help="skip the 128 KiB sequential leg")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own C on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_leg(seconds: float, io_blocks: int, pattern: str):
+    """Replay the workload through oracle/_ref (the compiled reference) or, where that did not
+    travel, the C restatement.  One thread: SPDK polls one vhost controller - hence one LUN - on
+    one reactor core (S/lib/vhost/vhost_scsi.c:1314-1318).  Returns (iops, info)."""
+    from oracle import bindings
+    try:
+        bindings.build()
+    except Exception:
+        pass
+    cls, kind = (bindings.RefOracle, "reference") if bindings.ref_available() else (bindings.PortOracle, "port")
+    o = cls(NUM_BLOCKS, BLOCK)
+    io_bytes = io_blocks * BLOCK
+    chunk = (1 << 18) if io_blocks <= 8 else (1 << 13)
+    t = traces.uniform_trace(chunk, NUM_BLOCKS, io_blocks=io_blocks, pattern=pattern, seed=0xB2000000)
+    arena = np.zeros(t.arena_bytes, dtype=np.uint8)
+    if "write" in pattern:
+        arena[:] = traces.pattern_bytes(0xC3, 0, arena.size)
+    iovs = t.bind(arena.ctypes.data)
+    o.submit(t.reqs[:4096], iovs)                       # warm-up pass
+    done, t0, busy = 0, time.perf_counter(), 0.0
+    while time.perf_counter() - t0 < seconds:
+        a = time.perf_counter()
+        o.submit(t.reqs, iovs)
+        busy += time.perf_counter() - a
+        done += chunk
+    o.close()
+    iops = done / busy
+    return iops, {"kind": kind, "cores": 1, "unit": "IOPS",
+                  "sample": f"{done} x {io_bytes} B {pattern} requests over the 8 GiB bdev in {busy:.1f} s, "
+                            f"{chunk}-request trace replayed; client buffers {arena.size >> 20} MiB host memory; "
+                            f"1 reactor thread (SPDK: one core per vhost controller)"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        iops, info = cpu_leg(per_step, 8, "randread")
+        if i >= args.warmup:
+            vals.append(iops)
+    v = statistics.mean(vals)
+    line = {"impl": "reference", "metric": "4KiB rand-read IOPS", "value": v, "unit": "IOPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C2: one 8 GiB Malloc bdev, 4 KiB random read, reference CPU poller"},
+            "cpu_baseline": {**info, "value": v},
+            "e2e": {"value": v, "unit": "IOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+def device_pattern_fill(lun, store_ptr: int, nbytes: int, seed: int, torch):
+    """prefill the backing store with the position-keyed pattern, generated on the GPU in 256 MiB
+    chunks (same function as traces.pattern_words, in int64 two's-complement arithmetic)."""
+    chunk_words = (256 << 20) // 8
+    gamma = -7046029254386353131          # 0x9E3779B97F4A7C15 as int64
+    m1, m2 = -4658895280553007687, -7723592293110705685
+
+    def lsr(x, k):
+        return (x >> k) & ((1 << (64 - k)) - 1)
+    done = 0
+    while done < nbytes // 8:
+        n = min(chunk_words, nbytes // 8 - done)
+        idx = torch.arange(done, done + n, dtype=torch.int64, device="cuda")
+        z = (idx ^ seed) * gamma + gamma
+        z = (z ^ lsr(z, 30)) * m1
+        z = (z ^ lsr(z, 27)) * m2
+        z = z ^ lsr(z, 31)
+        torch.cuda.synchronize()
+        lun.copy(store_ptr + done * 8, z.data_ptr(), n * 8)
+        lun.sync()
+        done += n
+
+
+def queue_major(t: traces.Trace, nq: int, per_q: int):
+    """per-queue views of a queue-major trace: request q*per_q.. belong to queue q"""
+    k = len(t.iovs) // (nq * per_q)
+    return k
+
+
+def run_ours(args, rank, world, local):
+    import torch
+    torch.cuda.set_device(local)
+    torch.zeros(1, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from oim_b200 import build, lib
+    build.build()
+    lib.init([local])
+    peak, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    bname = lib.construct_malloc_bdev(NUM_BLOCKS, BLOCK, name=f"Malloc{rank}", device=local)
+    lib.construct_vhost_scsi_controller(f"vhost.{rank}")
+    lib.add_vhost_scsi_lun(f"vhost.{rank}", 0, bname)
+    store_ptr = lib.get_bdevs(bname)[0]["device_ptr"]
+    nq, per_q = args.queues, args.per_queue
+    lun = lib.Lun(f"vhost.{rank}", 0, num_queues=max(nq, args.e2e_queues), queue_size=1024)
+    device_pattern_fill(lun, store_ptr, NUM_BLOCKS * BLOCK, 0xB2000000 + rank, torch)
+    timer = lib.Timer()
+    out = {}
+
+    def resident_leg(io_blocks, pattern, sg, nq, per_q, steps, warmup, check):
+        n = nq * per_q
+        t = traces.uniform_trace(n, NUM_BLOCKS, io_blocks=io_blocks, pattern=pattern, sg=sg, seed=0xB2000000 + rank)
+        arena = torch.empty(t.arena_bytes, dtype=torch.uint8, device="cuda")
+        if "write" in pattern:
+            arena.view(torch.int64)[:] = 0x0123456789ABCDEF
+        else:
+            arena.zero_()
+        d_reqs = torch.from_numpy(t.reqs.view(np.uint8)).cuda()
+        d_iovs = torch.from_numpy(t.bind(arena.data_ptr()).view(np.uint8)).cuda()
+        d_cpls = torch.zeros(n * 48, dtype=torch.uint8, device="cuda")
+        k = len(t.iovs) // n
+
+        def step():
+            # one C call: queue q <- requests [q*per_q, (q+1)*per_q); everything already in HBM
+            lun.submit_batch(nq, per_q, d_reqs.data_ptr(), d_iovs.data_ptr(), len(t.iovs), d_cpls.data_ptr(),
+                             abi.MEM_DEVICE)
+        for _ in range(warmup):
+            step()
+        lun.sync()
+        barrier()
+        l0 = lun.iostat()["kernel_launches"]
+        timer.start(lun)
+        for _ in range(steps):
+            step()
+        timer.stop(lun)
+        lun.sync()
+        barrier()
+        ms = max_over_ranks(timer.elapsed_ms())
+        launches = lun.iostat()["kernel_launches"] - l0
+        c = np.frombuffer(d_cpls.cpu().numpy().tobytes(), dtype=abi.cpl_dtype)
+        assert (c["status"] == 0).all() and (c["resid"] == 0).all() and (c["used_len"] > 0).all(), "bad completions"
+        if check:
+            check(t, arena)
+        del arena, d_reqs, d_iovs, d_cpls
+        torch.cuda.empty_cache()
+        return n, ms, launches, t
+
+    def check_randread(t, arena):
+        # spot parity against the position-keyed pattern: 256 random requests, full 4 KiB compare
+        rng = np.random.default_rng(1)
+        for i in rng.integers(0, len(t.reqs), 256):
+            lba = int.from_bytes(bytes(t.reqs["cdb"][i][2:6]), "big")
+            got = arena[i * 4096:(i + 1) * 4096].cpu().numpy()
+            want = traces.pattern_bytes(0xB2000000 + rank, lba * BLOCK, 4096)
+            assert (got == want).all(), f"request {i} lba {lba}: payload differs from the store pattern"
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n, ms, launches, _ = resident_leg(8, "randread", "single", nq, per_q, args.steps, args.warmup, check_randread)
+    clocks = sampler.stop() if rank == 0 else {}
+    iops = n * args.steps * world / (ms / 1e3)
+    per_launch_ms = ms / max(1, launches)
+    achieved = 2 * 4096 * n / (per_launch_ms / 1e3) / 1e9
+    out["rand4k"] = (iops, ms / args.steps, launches)
+
+    seq = None
+    if not args.no_seq:
+        sq, sp = max(1, nq // 8), 128
+        n2, ms2, l2, _ = resident_leg(256, "seqwrite", "pages", sq, sp, args.steps, args.warmup, None)
+        seq_gbs = n2 * args.steps * world * 131072 / (ms2 / 1e3) / 1e9
+        seq = {"metric": "128KiB seq-write GB/s (32 x 4 KiB SG pages)", "value": seq_gbs, "unit": "GB/s",
+               "ms_per_step": ms2 / args.steps, "hbm_frac": 2 * seq_gbs / world / peak,
+               "requests_per_step": n2, "queues": sq}
+
+    # ---- e2e: host request arrays through the C ABI, client buffers in pinned host memory ----
+    e2e = None
+    if not args.no_e2e:
+        eq, ep = args.e2e_queues, args.e2e_per_queue
+        en = eq * ep
+        t = traces.uniform_trace(en, NUM_BLOCKS, io_blocks=8, pattern="randread", seed=0xE2E00000 + rank)
+        host = torch.empty(t.arena_bytes, dtype=torch.uint8).pin_memory()
+        iovs = t.bind(host.data_ptr())
+        cpls = np.zeros(en, dtype=abi.cpl_dtype)
+        L = lib.load()
+
+        def e2e_step():
+            rc = L.oimgpu_submit_and_wait(lun.h, eq, ep, t.reqs.ctypes.data, iovs.ctypes.data, len(iovs),
+                                          cpls.ctypes.data, abi.MEM_HOST)
+            assert rc == 0, rc
+            return int(cpls["status"].sum())       # device->host read of the step's result
+        for _ in range(max(1, args.warmup)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            assert e2e_step() == 0
+        barrier()
+        wall = max_over_ranks(time.perf_counter() - t0)
+        got = host[:4096].numpy()
+        lba0 = int.from_bytes(bytes(t.reqs["cdb"][0][2:6]), "big")
+        assert (got == traces.pattern_bytes(0xB2000000 + rank, lba0 * BLOCK, 4096)).all()
+        e2e = {"value": en * args.steps * world / wall, "unit": "IOPS",
+               "h2d_bytes_per_step": int(en * 64 + len(iovs) * 16),
+               "d2h_bytes_per_step": int(en * 4096 + en * 48),
+               "ms_per_step": wall / args.steps * 1e3, "requests_per_step": en, "queues": eq,
+               "note": "request/SG/completion rings in mapped pinned host memory, read/written by the kernel "
+                       "over PCIe; payload stored by the kernel straight into pinned client buffers"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, info = cpu_leg(args.cpu_seconds, 8, "randread")
+        cpu = {**info, "value": v}
+
+    lun.close()
+    if rank == 0:
+        line = {
+            "metric": "4KiB rand-read IOPS", "value": iops, "unit": "IOPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"C2: one 8 GiB HBM Malloc bdev per GPU, 4 KiB random read, qd=32 per request "
+                                   f"queue x {nq} queues, {per_q} requests/queue/step",
+                       "queues": nq, "per_queue": per_q, "requests_per_step_per_gpu": n,
+                       "l2": "inputs larger than L2: 8 GiB store + unique 4 KiB client buffer per request "
+                             f"({n * 4096 >> 20} MiB) per step"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
+            "seq128k": seq, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_setup(args)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

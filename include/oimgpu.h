@@ -223,6 +223,10 @@ int oimgpu_mem_unregister(void *addr);
 int oimgpu_submit(oimgpu_lun *lun, uint32_t q, const struct oimgpu_req *reqs, uint32_t nreqs,
 		  const struct oimgpu_iov *iovs, uint32_t niovs, int mem);
 
+/* OIMGPU_MEM_DEVICE submission with the completion array also in HBM (nothing touches the host). */
+int oimgpu_submit_device(oimgpu_lun *lun, uint32_t q, const struct oimgpu_req *d_reqs, uint32_t nreqs,
+			 const struct oimgpu_iov *d_iovs, struct oimgpu_cpl *d_cpls);
+
 /* Run every queue's outstanding requests to completion on the LUN's stream ("kick").  With
  * OIMGPU_MEM_DEVICE completions stay in HBM at the address returned by oimgpu_queue_cpl_ptr(). */
 int oimgpu_kick(oimgpu_lun *lun);
@@ -231,8 +235,12 @@ int oimgpu_kick(oimgpu_lun *lun);
 int oimgpu_poll(oimgpu_lun *lun, uint32_t q, struct oimgpu_cpl *cpls, uint32_t max, int wait);
 int oimgpu_lun_sync(oimgpu_lun *lun);	/* wait for everything kicked so far */
 
-/* One-call convenience for callers that own a whole batch: submit to `nq` queues
- * (queue i gets reqs[i*per_q .. (i+1)*per_q) ), kick, wait, reap into cpls. */
+/* Batch forms for callers that own a whole batch: queue i (0..nq-1) gets reqs[i*per_q .. (i+1)*per_q),
+ * all indexing the one SG table `iovs`.  oimgpu_submit_batch = submit + kick (asynchronous; with
+ * OIMGPU_MEM_DEVICE `cpls` is the device completion array); oimgpu_submit_and_wait adds wait + reap. */
+int oimgpu_submit_batch(oimgpu_lun *lun, uint32_t nq, uint32_t per_q,
+			const struct oimgpu_req *reqs, const struct oimgpu_iov *iovs,
+			uint32_t niovs, struct oimgpu_cpl *cpls, int mem);
 int oimgpu_submit_and_wait(oimgpu_lun *lun, uint32_t nq, uint32_t per_q,
 			   const struct oimgpu_req *reqs, const struct oimgpu_iov *iovs,
 			   uint32_t niovs, struct oimgpu_cpl *cpls, int mem);
@@ -240,6 +248,16 @@ int oimgpu_submit_and_wait(oimgpu_lun *lun, uint32_t nq, uint32_t per_q,
 int oimgpu_lun_iostat(oimgpu_lun *lun, struct oimgpu_iostat *out);
 /* raw CUDA stream handle (cudaStream_t) of the LUN, for callers that time with CUDA events */
 void *oimgpu_lun_stream(oimgpu_lun *lun);
+
+/* Session-visible hot-remove state of the target (S/lib/vhost/vhost_scsi.c:1093-1100: `removed`;
+ * S/lib/scsi/lun.c:171-176: `lun_removed`). */
+int oimgpu_lun_set_removed(oimgpu_lun *lun, int removed, int lun_removed);
+
+/* CUDA-event timing on the LUN's stream (torch.cuda.Event only sees torch's streams). */
+int  oimgpu_timer_create(void **start, void **stop);
+int  oimgpu_timer_record(oimgpu_lun *lun, void *event);
+int  oimgpu_timer_elapsed_ms(void *start, void *stop, float *ms);
+void oimgpu_timer_destroy(void *start, void *stop);
 
 /* ---- copy-engine level (B2): the operator SPDK's bdev_malloc calls ----------------------- */
 

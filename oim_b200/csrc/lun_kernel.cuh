@@ -1,0 +1,245 @@
+/*
+ * lun_kernel.cuh — the per-LUN request-queue kernel (sm_100a).
+ *
+ * This one kernel is the GPU-side replacement of everything SPDK's vhost reactor does per request
+ * between "a head appears in the avail ring" and "the used element is published"
+ * (S/ = /root/reference/vendor/github.com/spdk/spdk/):
+ *
+ *   vdev_worker / process_requestq        S/lib/vhost/vhost_scsi.c:758-772, 690-741
+ *       one CTA per request queue, <= 32 requests per pass, one parser lane per request
+ *   task_data_setup                       vhost_scsi.c:490-624   -> parse_sg()
+ *   spdk_vhost_scsi_task_init_target      vhost_scsi.c:361-387   -> parse_request()
+ *   spdk_scsi_task_process_null_lun       S/lib/scsi/task.c:258-293
+ *   spdk_bdev_scsi_process_block          S/lib/scsi/scsi_bdev.c:1681-1802 (CDB decode)
+ *   spdk_bdev_scsi_readwrite/_read/_write scsi_bdev.c:1456-1511, 1318-1411
+ *   spdk_bdev_scsi_unmap / __copy_desc    scsi_bdev.c:1545-1679
+ *   spdk_bdev_readv/writev, valid_blocks  S/lib/bdev/bdev.c:2474-2509, 2559-2703
+ *   bdev_malloc_readv/writev/unmap        S/lib/bdev/malloc/bdev_malloc.c:153-233
+ *   mem_copy_submit / mem_copy_fill       S/lib/copy/copy_engine.c:114-140  -> move_unit()
+ *   spdk_vhost_scsi_task_cpl              vhost_scsi.c:311-331   -> completion record
+ *
+ * Data layout in HBM: the backing store is one flat byte array (LBA n at byte n*block_size,
+ * bdev_malloc.c:401); request slots (64 B), SG elements (16 B) and completion slots (48 B) are
+ * flat arrays per queue (include/oimgpu.h).  Payload moves HBM->HBM (or HBM<->mapped host memory)
+ * in 16-byte vectors, 8 outstanding per lane.
+ *
+ * Ordering: the reference executes a queue's requests one after the other, so within a queue the
+ * result is sequentially consistent in ring order.  Here a queue is owned by one CTA; inside a
+ * pass, requests whose LBA ranges conflict (RAW/WAW/WAR) are put in successive "waves" separated by
+ * a CTA barrier; passes follow each other in order.  Different queues are unordered, as they are
+ * for any multi-queue block device.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "oimgpu.h"
+
+namespace oimgpu {
+
+constexpr int kPass = OIMGPU_REQS_PER_PASS;	/* 32 = one warp of parser lanes */
+constexpr int kThreads = 256;			/* CTA size: parser warp + 7 more mover warps */
+constexpr int kWarps = kThreads / 32;
+constexpr int kSegCap = 768;			/* SG segments staged in shared memory per round */
+constexpr uint32_t kUnitBytes = 4096;		/* bytes one warp moves per step: 8 x 16 B per lane */
+constexpr int kMaxReplicas = 4;
+
+enum : uint8_t { SC_GOOD = 0x00, SC_CHECK = 0x02 };
+enum : uint8_t { SK_NO_SENSE = 0x0, SK_ILLEGAL_REQUEST = 0x5, SK_ABORTED_COMMAND = 0xb };
+enum : uint8_t { ASC_NONE = 0x00, ASC_INVALID_OPCODE = 0x20, ASC_LBA_OOR = 0x21, ASC_INVALID_FIELD = 0x24,
+		 ASC_LUN_NOT_SUPPORTED = 0x25 };
+
+/* per-LUN state, resident in HBM: the device-side struct malloc_disk + session target state */
+struct LunCtx {
+	uint8_t  *store[kMaxReplicas];	/* replica 0 is local; others are peer (NVLink) mappings */
+	uint32_t nreplicas;
+	uint64_t num_blocks;
+	uint32_t block_size;
+	uint32_t block_shift;		/* log2(block_size), or 0xffffffff when not a power of two */
+	uint8_t  target;		/* SCSI target number of this LUN inside its controller */
+	uint8_t  present[OIMGPU_CTRLR_MAX_DEVS];	/* which target slots of the controller are occupied */
+	uint8_t  removed;		/* session saw a hot-remove of this target */
+	uint8_t  lun_removed;
+	unsigned long long stats[8];	/* read ops, write ops, unmap ops, other, bytes r/w/unmapped, errors */
+};
+
+/* one request queue as the kernel sees it for one launch */
+struct QueueDesc {
+	const oimgpu_req *reqs;
+	const oimgpu_iov *iovs;
+	oimgpu_cpl       *cpls;
+	uint32_t ring_mask;		/* slot index mask (0xffffffff: linear array) */
+	uint32_t iov_mask;
+	uint32_t head;			/* first slot to process */
+	uint32_t count;			/* number of slots to process */
+};
+
+/* one contiguous piece of payload to move (or to zero when src == nullptr) */
+struct Segment {
+	const uint8_t *src;
+	uint8_t *dst;
+	uint64_t len;
+	uint32_t first_unit;		/* exclusive prefix sum of units over the round's segments */
+	uint16_t wave;
+	uint16_t mirror;		/* 1: dst is in the backing store -> replicate to peers */
+};
+
+struct __align__(16) PassShared {
+	oimgpu_req req[kPass];
+	oimgpu_cpl cpl[kPass];
+	Segment seg[kSegCap];
+	uint32_t nseg;
+	uint32_t nunits;
+	uint32_t nwaves;
+	uint32_t wave_first_unit[kPass + 2];
+	uint32_t round_reqs;		/* how many of the pass's requests this round covers */
+	uint32_t scan_tmp[kWarps];
+};
+
+/* ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ int4 ld_cg16(const void *p)
+{
+	int4 r;
+	asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];"
+		     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+	return r;
+}
+__device__ __forceinline__ void st_cg16(void *p, const int4 &v)
+{
+	asm volatile("st.global.cg.v4.s32 [%0], {%1,%2,%3,%4};"
+		     :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint8_t ld_cg8(const uint8_t *p)
+{
+	uint32_t r;
+	asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+	return (uint8_t)r;
+}
+__device__ __forceinline__ uint32_t ld_cg32(const void *p)
+{
+	uint32_t r;
+	asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+	return r;
+}
+
+__device__ __forceinline__ uint16_t be16(const uint8_t *p) { return (uint16_t)(p[0] << 8 | p[1]); }
+__device__ __forceinline__ uint32_t be32(const uint8_t *p)
+{
+	return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+}
+__device__ __forceinline__ uint64_t be64(const uint8_t *p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
+
+/* spdk_scsi_task_set_status + build_sense_data (S/lib/scsi/task.c:198-247) into the completion */
+struct TaskStatus {
+	uint8_t status, sk, asc, has_sense;
+	__device__ __forceinline__ void good() { status = SC_GOOD; }
+	__device__ __forceinline__ void check(uint8_t k, uint8_t a) { status = SC_CHECK; sk = k; asc = a; has_sense = 1; }
+};
+
+/* Move `n` (<= kUnitBytes) bytes with one warp.  Fast path: both sides 16-byte aligned. */
+__device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
+{
+	if ((((uintptr_t)dst | (uintptr_t)src | n) & 15) == 0) {
+		int4 r[kUnitBytes / 512];
+		const uint32_t nv = n >> 4;
+#pragma unroll
+		for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
+			uint32_t v = lane + 32 * k;
+			if (v < nv) r[k] = ld_cg16(src + (size_t)v * 16);
+		}
+#pragma unroll
+		for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
+			uint32_t v = lane + 32 * k;
+			if (v < nv) st_cg16(dst + (size_t)v * 16, r[k]);
+		}
+		return;
+	}
+	/* byte-granular SG element (SURVEY.md §7 "unaligned SG elements"): peel to a 16-byte aligned
+	 * destination, then aligned 16-byte stores fed by the widest loads the source allows */
+	uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+	if (head > n) head = n;
+	if ((uint32_t)lane < head) dst[lane] = ld_cg8(src + lane);
+	dst += head; src += head; n -= head;
+	const uint32_t nv = n >> 4;
+	if (((uintptr_t)src & 15) == 0) {
+		for (uint32_t v = lane; v < nv; v += 32) st_cg16(dst + (size_t)v * 16, ld_cg16(src + (size_t)v * 16));
+	} else if (((uintptr_t)src & 3) == 0) {
+		for (uint32_t v = lane; v < nv; v += 32) {
+			const uint8_t *s = src + (size_t)v * 16;
+			int4 r;
+			r.x = ld_cg32(s); r.y = ld_cg32(s + 4); r.z = ld_cg32(s + 8); r.w = ld_cg32(s + 12);
+			st_cg16(dst + (size_t)v * 16, r);
+		}
+	} else {
+		for (uint32_t v = lane; v < nv; v += 32) {
+			const uint8_t *s = src + (size_t)v * 16;
+			uint32_t w[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				w[j] = (uint32_t)ld_cg8(s + 4 * j) | (uint32_t)ld_cg8(s + 4 * j + 1) << 8 |
+				       (uint32_t)ld_cg8(s + 4 * j + 2) << 16 | (uint32_t)ld_cg8(s + 4 * j + 3) << 24;
+			}
+			st_cg16(dst + (size_t)v * 16, make_int4(w[0], w[1], w[2], w[3]));
+		}
+	}
+	const uint32_t tail = n & 15;
+	if ((uint32_t)lane < tail) dst[(size_t)nv * 16 + lane] = ld_cg8(src + (size_t)nv * 16 + lane);
+}
+
+/* mem_copy_fill with fill == 0 (copy_engine.c:128-140): zero `n` bytes; block-aligned by construction */
+__device__ __forceinline__ void zero_unit(uint8_t *dst, uint32_t n, int lane)
+{
+	const int4 z = make_int4(0, 0, 0, 0);
+	if ((((uintptr_t)dst | n) & 15) == 0) {
+		for (uint32_t v = lane; v < (n >> 4); v += 32) st_cg16(dst + (size_t)v * 16, z);
+	} else {
+		for (uint32_t i = lane; i < n; i += 32) dst[i] = 0;
+	}
+}
+
+/* What a parser lane knows about its request after decode */
+struct Parsed {
+	uint64_t off;		/* byte offset in the backing store */
+	uint64_t store_lo, store_hi;	/* block range touched, for hazard detection */
+	uint32_t length;	/* task->length: sum of SG element lengths */
+	uint32_t nseg;		/* segments this request emits */
+	uint8_t  op;		/* 0 none, 1 read (store->sg), 2 write (sg->store), 3 unmap, 4 small scatter */
+	uint8_t  valid;		/* 0: invalid_request() */
+};
+
+enum : uint8_t { OP_NONE = 0, OP_READ = 1, OP_WRITE = 2, OP_UNMAP = 3 };
+
+/* spdk_scsi_task_scatter_data (task.c:111-152) of a <=36-byte control payload into the SG list */
+__device__ inline int scatter_small(const QueueDesc &q, const oimgpu_req &r, uint32_t iovcnt, uint32_t total_len,
+				    const uint8_t *buf, uint32_t buf_len, TaskStatus &st)
+{
+	if (buf_len == 0) return 0;
+	if (total_len < buf_len) {
+		st.check(SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD);
+		return -1;
+	}
+	uint32_t left = buf_len;
+	for (uint32_t j = 0; j < iovcnt && left; j++) {
+		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
+		uint32_t l = v.len < left ? v.len : left;
+		uint8_t *d = (uint8_t *)(uintptr_t)v.addr;
+		for (uint32_t k = 0; k < l; k++) d[k] = buf[buf_len - left + k];
+		left -= l;
+	}
+	return (int)buf_len;
+}
+
+/* byte `pos` of the request's gathered TO_DEV payload (spdk_scsi_task_gather_data, task.c:154-186) */
+__device__ inline uint8_t gather_byte(const QueueDesc &q, const oimgpu_req &r, uint32_t iovcnt, uint32_t pos)
+{
+	for (uint32_t j = 0; j < iovcnt; j++) {
+		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
+		if (pos < v.len) return ld_cg8((const uint8_t *)(uintptr_t)v.addr + pos);
+		pos -= v.len;
+	}
+	return 0;
+}
+
+}  // namespace oimgpu

@@ -1,0 +1,943 @@
+/*
+ * oimgpu.cu — host side of liboimgpu.so: the C ABI declared in include/oimgpu.h.
+ *
+ * Control plane state mirrors what the SPDK daemon keeps for OIM's twelve RPCs
+ * (bdev list: S/lib/bdev/bdev.c + bdev_malloc.c:378-443; vhost controllers and their 8 target
+ * slots: S/lib/vhost/vhost_scsi.c:951-1103), the data plane launches oim_lun_queue_kernel on the
+ * LUN's own CUDA stream.  There is deliberately no CPU implementation of the data path in this
+ * library: without a usable CUDA device oimgpu_init() fails and every other call returns -ENODEV.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "lun_kernel.cuh"
+
+namespace oimgpu {
+__global__ void oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues);
+__global__ void oim_copy_kernel(uint8_t *dst, const uint8_t *src, uint64_t nbytes);
+__global__ void oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes);
+size_t lun_kernel_smem_bytes();
+}  // namespace oimgpu
+
+using namespace oimgpu;
+
+static_assert(sizeof(oimgpu_req) == 64, "oimgpu_req layout");
+static_assert(sizeof(oimgpu_iov) == 16, "oimgpu_iov layout");
+static_assert(sizeof(oimgpu_cpl) == 48, "oimgpu_cpl layout");
+static_assert(offsetof(oimgpu_req, cdb) == 19 && offsetof(oimgpu_req, dir) == 51, "virtio header prefix");
+static_assert(sizeof(Segment) == 32, "Segment layout");
+
+#define CU_OK(expr)                                                                          \
+	do {                                                                                 \
+		cudaError_t e__ = (expr);                                                    \
+		if (e__ != cudaSuccess) {                                                    \
+			fprintf(stderr, "oimgpu: %s failed: %s (%s:%d)\n", #expr,             \
+				cudaGetErrorString(e__), __FILE__, __LINE__);                 \
+			return e__ == cudaErrorMemoryAllocation ? -ENOMEM : -EIO;            \
+		}                                                                            \
+	} while (0)
+
+namespace {
+
+struct Device {
+	int ordinal = -1;
+	int sm_count = 0;
+	uint64_t bytes_allocated = 0;
+};
+
+struct Bdev {
+	std::string name, product, uuid;
+	uint64_t num_blocks = 0;
+	uint32_t block_size = 0;
+	int claimed = 0;	/* number of SCSI targets built on it */
+	std::vector<int> devices;	/* replica r lives on devices[r] */
+	std::vector<uint8_t *> stores;
+};
+
+struct Ctrlr {
+	std::string name, cpumask;
+	std::string targets[OIMGPU_CTRLR_MAX_DEVS];	/* bdev name or "" */
+};
+
+struct Registry {
+	std::mutex mu;
+	bool inited = false;
+	std::vector<Device> devices;
+	std::map<std::string, std::unique_ptr<Bdev>> bdevs;
+	std::map<std::string, std::unique_ptr<Ctrlr>> ctrlrs;
+	int malloc_disk_count = 0;	/* bdev_malloc.c:93 */
+	int rbd_count = 0;
+	std::map<void *, size_t> registered;
+	int open_luns = 0;
+};
+
+Registry g;
+
+struct Queue {
+	/* library-owned ring in mapped pinned host memory (OIMGPU_MEM_HOST submissions) */
+	oimgpu_req *h_reqs = nullptr;
+	oimgpu_iov *h_iovs = nullptr;
+	oimgpu_cpl *h_cpls = nullptr;
+	oimgpu_req *d_reqs = nullptr;	/* device view of the same memory */
+	oimgpu_iov *d_iovs = nullptr;
+	oimgpu_cpl *d_cpls = nullptr;
+	uint32_t tail = 0;		/* next free slot (absolute index) */
+	uint32_t kicked = 0;		/* slots [reaped, kicked) handed to the GPU */
+	uint32_t reaped = 0;
+	uint32_t iov_tail = 0;
+	/* pending OIMGPU_MEM_DEVICE submission (caller-owned device arrays), consumed by next kick */
+	const oimgpu_req *dev_reqs = nullptr;
+	const oimgpu_iov *dev_iovs = nullptr;
+	oimgpu_cpl *dev_cpls = nullptr;
+	uint32_t dev_count = 0;
+};
+
+}  // namespace
+
+struct oimgpu_lun {
+	std::string ctrlr, bdev;
+	int target = 0;
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;
+	LunCtx *d_ctx = nullptr;
+	LunCtx h_ctx{};
+	uint32_t num_queues = 0, queue_size = 0, iov_cap = 0;
+	std::vector<Queue> queues;
+	QueueDesc *h_desc = nullptr;	/* pinned */
+	QueueDesc *d_desc = nullptr;
+	uint64_t launches = 0;
+	int grid_cap = 0;
+};
+
+/* ---------------------------------------------------------------------------------------------- */
+
+static int find_device_slot(int ordinal)
+{
+	for (size_t i = 0; i < g.devices.size(); i++) {
+		if (g.devices[i].ordinal == ordinal) return (int)i;
+	}
+	return -1;
+}
+
+static std::string random_uuid()
+{
+	std::random_device rd;
+	uint8_t u[16];
+	for (int i = 0; i < 16; i++) u[i] = (uint8_t)rd();
+	u[6] = (u[6] & 0x0f) | 0x40;
+	u[8] = (u[8] & 0x3f) | 0x80;
+	char out[40];
+	snprintf(out, sizeof(out), "%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x",
+		 u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7], u[8], u[9], u[10], u[11], u[12], u[13], u[14], u[15]);
+	return out;
+}
+
+/* spdk_uuid_parse -> uuid_parse: exactly 36 chars, hex with dashes at 8/13/18/23 */
+static bool uuid_valid(const char *s)
+{
+	if (strlen(s) != 36) return false;
+	for (int i = 0; i < 36; i++) {
+		if (i == 8 || i == 13 || i == 18 || i == 23) {
+			if (s[i] != '-') return false;
+		} else if (!isxdigit((unsigned char)s[i])) {
+			return false;
+		}
+	}
+	return true;
+}
+
+static void copy_str(char *dst, size_t cap, const std::string &s)
+{
+	if (!dst || !cap) return;
+	snprintf(dst, cap, "%s", s.c_str());
+}
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+
+extern "C" int oimgpu_abi_version(void) { return OIMGPU_ABI_VERSION; }
+
+extern "C" const char *oimgpu_version_string(void)
+{
+	return "oimgpu 0.1 (sm_100a; replaces SPDK v19.04-pre vhost-scsi/Malloc data path behind intel/oim)";
+}
+
+extern "C" int oimgpu_init(const int *devices, int ndevices)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (g.inited) return 0;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+		fprintf(stderr, "oimgpu: no CUDA device; the data path has no CPU fallback\n");
+		return -ENODEV;
+	}
+	std::vector<int> ords;
+	if (devices && ndevices > 0) {
+		ords.assign(devices, devices + ndevices);
+	} else {
+		int cur = 0;
+		CU_OK(cudaGetDevice(&cur));
+		ords.push_back(cur);
+	}
+	for (int o : ords) {
+		if (o < 0 || o >= count) return -EINVAL;
+		cudaDeviceProp prop;
+		CU_OK(cudaGetDeviceProperties(&prop, o));
+		Device d;
+		d.ordinal = o;
+		d.sm_count = prop.multiProcessorCount;
+		g.devices.push_back(d);
+	}
+	/* mirrored bdevs store to peer HBM directly: enable P2P between every pair we manage */
+	for (size_t i = 0; i < g.devices.size(); i++) {
+		for (size_t j = 0; j < g.devices.size(); j++) {
+			if (i == j) continue;
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, g.devices[i].ordinal, g.devices[j].ordinal);
+			if (can) {
+				cudaSetDevice(g.devices[i].ordinal);
+				cudaError_t e = cudaDeviceEnablePeerAccess(g.devices[j].ordinal, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+				(void)cudaGetLastError();
+			}
+		}
+	}
+	cudaSetDevice(g.devices[0].ordinal);
+	g.inited = true;
+	return 0;
+}
+
+extern "C" void oimgpu_fini(void)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return;
+	for (auto &kv : g.bdevs) {
+		for (size_t r = 0; r < kv.second->stores.size(); r++) {
+			cudaSetDevice(kv.second->devices[r]);
+			cudaFree(kv.second->stores[r]);
+		}
+	}
+	g.bdevs.clear();
+	g.ctrlrs.clear();
+	g.devices.clear();
+	g.malloc_disk_count = g.rbd_count = 0;
+	g.inited = false;
+}
+
+extern "C" int oimgpu_device_count(void) { return (int)g.devices.size(); }
+
+/* ---- bdev control ---------------------------------------------------------------------------- */
+
+static int pick_device(int device)
+{
+	if (device >= 0) return find_device_slot(device) >= 0 ? device : -1;
+	size_t best = 0;
+	for (size_t i = 1; i < g.devices.size(); i++) {
+		if (g.devices[i].bytes_allocated < g.devices[best].bytes_allocated) best = i;
+	}
+	return g.devices[best].ordinal;
+}
+
+static int alloc_store(int ordinal, uint64_t bytes, uint8_t **out)
+{
+	CU_OK(cudaSetDevice(ordinal));
+	cudaError_t e = cudaMalloc((void **)out, bytes);
+	if (e != cudaSuccess) {
+		(void)cudaGetLastError();
+		return -ENOMEM;
+	}
+	/* spdk_dma_zmalloc: the disk starts zero-filled (bdev_malloc.c:401) */
+	CU_OK(cudaMemset(*out, 0, bytes));
+	CU_OK(cudaDeviceSynchronize());
+	g.devices[find_device_slot(ordinal)].bytes_allocated += bytes;
+	return 0;
+}
+
+static int create_bdev_locked(const char *name, const char *uuid, uint64_t num_blocks, uint32_t block_size,
+			      const std::vector<int> &devs, const char *product, const std::string &auto_name,
+			      char *name_out, size_t name_cap)
+{
+	if (!g.inited) return -ENODEV;
+	/* create_malloc_disk: "Disk must be more than 0 blocks" (bdev_malloc.c:384-387); block size must
+	 * be a positive multiple the SCSI layer can divide 4 MiB by */
+	if (num_blocks == 0 || block_size == 0 || block_size > OIMGPU_MAX_XFER_BYTES) return -EINVAL;
+	if (uuid && !uuid_valid(uuid)) return -EINVAL;
+	std::string nm = name && name[0] ? name : auto_name;
+	if (g.bdevs.count(nm)) return -EEXIST;	/* spdk_bdev_register: name already in use */
+	auto b = std::make_unique<Bdev>();
+	b->name = nm;
+	b->product = product;
+	b->uuid = uuid ? uuid : random_uuid();
+	b->num_blocks = num_blocks;
+	b->block_size = block_size;
+	for (int d : devs) {
+		uint8_t *p = nullptr;
+		int rc = alloc_store(d, num_blocks * (uint64_t)block_size, &p);
+		if (rc != 0) {
+			for (size_t r = 0; r < b->stores.size(); r++) {
+				cudaSetDevice(b->devices[r]);
+				cudaFree(b->stores[r]);
+			}
+			return rc;
+		}
+		b->devices.push_back(d);
+		b->stores.push_back(p);
+	}
+	copy_str(name_out, name_cap, nm);
+	g.bdevs[nm] = std::move(b);
+	return 0;
+}
+
+extern "C" int oimgpu_bdev_create_malloc(const char *name, const char *uuid, uint64_t num_blocks,
+					 uint32_t block_size, int device, char *name_out, size_t name_cap)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	int d = pick_device(device);
+	if (d < 0) return -EINVAL;
+	std::string auto_name;
+	if (!(name && name[0])) auto_name = "Malloc" + std::to_string(g.malloc_disk_count);
+	int rc = create_bdev_locked(name, uuid, num_blocks, block_size, {d}, "Malloc disk", auto_name, name_out, name_cap);
+	if (rc == 0 && !(name && name[0])) g.malloc_disk_count++;
+	return rc;
+}
+
+extern "C" int oimgpu_bdev_create_rbd(const char *name, const char *pool_name, const char *rbd_name,
+				      const char *user_id, uint32_t block_size, uint64_t size_bytes,
+				      int device, char *name_out, size_t name_cap)
+{
+	(void)user_id;
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	/* spdk_rpc_construct_rbd_bdev requires pool_name, rbd_name and block_size (bdev_rbd_rpc.c:81-96) */
+	if (!pool_name || !pool_name[0] || !rbd_name || !rbd_name[0] || block_size == 0) return -EINVAL;
+	if (size_bytes == 0 || size_bytes % block_size) return -EINVAL;
+	int d = pick_device(device);
+	if (d < 0) return -EINVAL;
+	std::string auto_name;
+	if (!(name && name[0])) auto_name = "Ceph" + std::to_string(g.rbd_count);	/* bdev_rbd.c:732 */
+	int rc = create_bdev_locked(name, nullptr, size_bytes / block_size, block_size, {d}, "Ceph Rbd Disk",
+				    auto_name, name_out, name_cap);
+	if (rc == 0 && !(name && name[0])) g.rbd_count++;
+	return rc;
+}
+
+extern "C" int oimgpu_bdev_create_mirror(const char *name, uint64_t num_blocks, uint32_t block_size,
+					 const int *devices, int nreplicas, char *name_out, size_t name_cap)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	if (!devices || nreplicas < 1 || nreplicas > kMaxReplicas) return -EINVAL;
+	std::vector<int> devs(devices, devices + nreplicas);
+	for (int d : devs) {
+		if (find_device_slot(d) < 0) return -EINVAL;
+	}
+	for (int r = 1; r < nreplicas; r++) {
+		int can = 0;
+		cudaDeviceCanAccessPeer(&can, devs[0], devs[r]);
+		if (!can && devs[0] != devs[r]) return -ENOTSUP;
+	}
+	std::string auto_name;
+	if (!(name && name[0])) auto_name = "Mirror" + std::to_string(g.malloc_disk_count);
+	int rc = create_bdev_locked(name, nullptr, num_blocks, block_size, devs, "Malloc disk", auto_name, name_out, name_cap);
+	if (rc == 0 && !(name && name[0])) g.malloc_disk_count++;
+	return rc;
+}
+
+extern "C" int oimgpu_bdev_delete(const char *name)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.bdevs.find(name ? name : "");
+	if (it == g.bdevs.end()) return -ENODEV;
+	if (it->second->claimed) return -EBUSY;
+	for (size_t r = 0; r < it->second->stores.size(); r++) {
+		cudaSetDevice(it->second->devices[r]);
+		cudaFree(it->second->stores[r]);
+		g.devices[find_device_slot(it->second->devices[r])].bytes_allocated -=
+			it->second->num_blocks * (uint64_t)it->second->block_size;
+	}
+	g.bdevs.erase(it);
+	return 0;
+}
+
+static void fill_bdev_info(const Bdev &b, oimgpu_bdev_info *o)
+{
+	memset(o, 0, sizeof(*o));
+	copy_str(o->name, sizeof(o->name), b.name);
+	copy_str(o->product_name, sizeof(o->product_name), b.product);
+	copy_str(o->uuid, sizeof(o->uuid), b.uuid);
+	o->num_blocks = b.num_blocks;
+	o->block_size = b.block_size;
+	o->claimed = b.claimed != 0;
+	o->device = b.devices[0];
+	o->replicas = (uint32_t)b.stores.size();
+	o->device_ptr = (uint64_t)(uintptr_t)b.stores[0];
+}
+
+extern "C" int oimgpu_bdev_get(const char *name, oimgpu_bdev_info *out)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.bdevs.find(name ? name : "");
+	if (it == g.bdevs.end()) return -ENODEV;
+	if (out) fill_bdev_info(*it->second, out);
+	return 0;
+}
+
+extern "C" int oimgpu_bdev_list(oimgpu_bdev_info *out, int max)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	int n = 0;
+	for (auto &kv : g.bdevs) {
+		if (out && n < max) fill_bdev_info(*kv.second, &out[n]);
+		n++;
+	}
+	return n;
+}
+
+static int raw_access(const char *name, int replica, uint64_t offset, void *host, uint64_t len, bool write)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.bdevs.find(name ? name : "");
+	if (it == g.bdevs.end()) return -ENODEV;
+	Bdev &b = *it->second;
+	if (replica < 0 || replica >= (int)b.stores.size()) return -EINVAL;
+	uint64_t size = b.num_blocks * (uint64_t)b.block_size;
+	if (offset > size || len > size - offset) return -EINVAL;
+	CU_OK(cudaSetDevice(b.devices[replica]));
+	CU_OK(cudaDeviceSynchronize());
+	if (write) CU_OK(cudaMemcpy(b.stores[replica] + offset, host, len, cudaMemcpyHostToDevice));
+	else CU_OK(cudaMemcpy(host, b.stores[replica] + offset, len, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int oimgpu_bdev_read_raw(const char *name, int replica, uint64_t offset, void *dst, uint64_t len)
+{
+	return raw_access(name, replica, offset, dst, len, false);
+}
+
+extern "C" int oimgpu_bdev_write_raw(const char *name, int replica, uint64_t offset, const void *src, uint64_t len)
+{
+	return raw_access(name, replica, offset, const_cast<void *>(src), len, true);
+}
+
+/* ---- vhost-scsi control ------------------------------------------------------------------------ */
+
+/* spdk_vhost_dev_register strips the socket directory prefix from the name (vhost.c:611-628);
+ * callers may pass a path, we keep the last component */
+static std::string ctrlr_key(const char *ctrlr)
+{
+	std::string s = ctrlr ? ctrlr : "";
+	size_t p = s.find_last_of('/');
+	return p == std::string::npos ? s : s.substr(p + 1);
+}
+
+extern "C" int oimgpu_vhost_scsi_ctrlr_create(const char *ctrlr, const char *cpumask)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	std::string key = ctrlr_key(ctrlr);
+	if (key.empty()) return -EINVAL;
+	if (g.ctrlrs.count(key)) return -EEXIST;
+	std::string mask = "0x1";
+	if (cpumask && cpumask[0]) {
+		/* spdk_vhost_parse_core_mask: a hex mask that must select at least one core (vhost.c:560-590) */
+		char *end = nullptr;
+		unsigned long long v = strtoull(cpumask, &end, 16);
+		if (end == cpumask || *end != 0 || v == 0) return -EINVAL;
+		char buf[24];
+		snprintf(buf, sizeof(buf), "0x%llx", v);
+		mask = buf;
+	}
+	auto c = std::make_unique<Ctrlr>();
+	c->name = key;
+	c->cpumask = mask;
+	g.ctrlrs[key] = std::move(c);
+	return 0;
+}
+
+extern "C" int oimgpu_vhost_scsi_add_lun(const char *ctrlr, int scsi_target_num, const char *bdev_name)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.ctrlrs.find(ctrlr_key(ctrlr));
+	if (it == g.ctrlrs.end()) return -ENODEV;
+	Ctrlr &c = *it->second;
+	/* spdk_vhost_scsi_dev_add_tgt (vhost_scsi.c:951-1021) */
+	if (scsi_target_num < 0) {
+		for (scsi_target_num = 0; scsi_target_num < OIMGPU_CTRLR_MAX_DEVS; scsi_target_num++) {
+			if (c.targets[scsi_target_num].empty()) break;
+		}
+		if (scsi_target_num == OIMGPU_CTRLR_MAX_DEVS) return -ENOSPC;
+	} else {
+		if (scsi_target_num >= OIMGPU_CTRLR_MAX_DEVS) return -EINVAL;
+	}
+	if (!bdev_name) return -EINVAL;
+	if (!c.targets[scsi_target_num].empty()) return -EEXIST;
+	auto b = g.bdevs.find(bdev_name);
+	if (b == g.bdevs.end()) return -EINVAL;	/* spdk_scsi_dev_construct failed */
+	c.targets[scsi_target_num] = bdev_name;
+	b->second->claimed++;
+	return scsi_target_num;
+}
+
+extern "C" int oimgpu_vhost_scsi_remove_target(const char *ctrlr, int scsi_target_num)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.ctrlrs.find(ctrlr_key(ctrlr));
+	if (it == g.ctrlrs.end()) return -ENODEV;
+	if (scsi_target_num < 0 || scsi_target_num >= OIMGPU_CTRLR_MAX_DEVS) return -EINVAL;
+	Ctrlr &c = *it->second;
+	if (c.targets[scsi_target_num].empty()) return -ENODEV;
+	auto b = g.bdevs.find(c.targets[scsi_target_num]);
+	if (b != g.bdevs.end() && b->second->claimed > 0) b->second->claimed--;
+	c.targets[scsi_target_num].clear();
+	return 0;
+}
+
+extern "C" int oimgpu_vhost_ctrlr_remove(const char *ctrlr)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.ctrlrs.find(ctrlr_key(ctrlr));
+	if (it == g.ctrlrs.end()) return -ENODEV;
+	for (auto &t : it->second->targets) {
+		if (!t.empty()) return -EBUSY;	/* vhost_scsi.c:837-842 */
+	}
+	g.ctrlrs.erase(it);
+	return 0;
+}
+
+static void fill_ctrlr_info(const Ctrlr &c, oimgpu_ctrlr_info *o)
+{
+	memset(o, 0, sizeof(*o));
+	copy_str(o->ctrlr, sizeof(o->ctrlr), c.name);
+	copy_str(o->cpumask, sizeof(o->cpumask), c.cpumask);
+	o->delay_base_us = 0;
+	o->iops_threshold = 60000;	/* SPDK_VHOST_VQ_IOPS_COALESCING_THRESHOLD */
+	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		if (c.targets[t].empty()) continue;
+		oimgpu_target_info &ti = o->targets[o->ntargets++];
+		ti.scsi_dev_num = t;
+		ti.id = t;
+		snprintf(ti.target_name, sizeof(ti.target_name), "Target %d", t);
+		ti.lun_id = 0;
+		copy_str(ti.bdev_name, sizeof(ti.bdev_name), c.targets[t]);
+	}
+}
+
+extern "C" int oimgpu_vhost_ctrlr_get(const char *ctrlr, oimgpu_ctrlr_info *out)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.ctrlrs.find(ctrlr_key(ctrlr));
+	if (it == g.ctrlrs.end()) return -ENODEV;
+	if (out) fill_ctrlr_info(*it->second, out);
+	return 0;
+}
+
+extern "C" int oimgpu_vhost_ctrlr_list(oimgpu_ctrlr_info *out, int max)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	int n = 0;
+	for (auto &kv : g.ctrlrs) {
+		if (out && n < max) fill_ctrlr_info(*kv.second, &out[n]);
+		n++;
+	}
+	return n;
+}
+
+/* ---- data path ----------------------------------------------------------------------------------- */
+
+extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t num_queues,
+			       uint32_t queue_size, oimgpu_lun **out)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	if (!out || num_queues == 0 || queue_size == 0 || (queue_size & (queue_size - 1)) ||
+	    queue_size > OIMGPU_MAX_VQ_SIZE) return -EINVAL;
+	auto it = g.ctrlrs.find(ctrlr_key(ctrlr));
+	if (it == g.ctrlrs.end()) return -ENODEV;
+	if (scsi_target_num < 0 || scsi_target_num >= OIMGPU_CTRLR_MAX_DEVS) return -EINVAL;
+	const std::string &bn = it->second->targets[scsi_target_num];
+	if (bn.empty()) return -ENODEV;
+	Bdev &b = *g.bdevs[bn];
+
+	auto L = std::make_unique<oimgpu_lun>();
+	L->ctrlr = it->second->name;
+	L->bdev = bn;
+	L->target = scsi_target_num;
+	L->device = b.devices[0];
+	L->sm_count = g.devices[find_device_slot(L->device)].sm_count;
+	L->num_queues = num_queues;
+	L->queue_size = queue_size;
+	L->iov_cap = queue_size * 4 < 1024 ? 1024 : queue_size * 4;	/* power of two >= 8 x 129 */
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+	CU_OK(cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming));
+
+	memset(&L->h_ctx, 0, sizeof(L->h_ctx));
+	for (size_t r = 0; r < b.stores.size(); r++) L->h_ctx.store[r] = b.stores[r];
+	L->h_ctx.nreplicas = (uint32_t)b.stores.size();
+	L->h_ctx.num_blocks = b.num_blocks;
+	L->h_ctx.block_size = b.block_size;
+	L->h_ctx.block_shift = (b.block_size & (b.block_size - 1)) ? 0xffffffffu : (uint32_t)__builtin_ctz(b.block_size);
+	L->h_ctx.target = (uint8_t)scsi_target_num;
+	CU_OK(cudaMalloc((void **)&L->d_ctx, sizeof(LunCtx)));
+	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, sizeof(LunCtx), cudaMemcpyHostToDevice));
+
+	CU_OK(cudaHostAlloc((void **)&L->h_desc, sizeof(QueueDesc) * num_queues, cudaHostAllocDefault));
+	CU_OK(cudaMalloc((void **)&L->d_desc, sizeof(QueueDesc) * num_queues));
+	L->queues.resize(num_queues);
+	/* one mapped pinned slab per LUN, carved into per-queue rings: the "virtqueues" */
+	const size_t per_q = sizeof(oimgpu_req) * queue_size + sizeof(oimgpu_iov) * L->iov_cap + sizeof(oimgpu_cpl) * queue_size;
+	uint8_t *slab = nullptr, *dslab = nullptr;
+	CU_OK(cudaHostAlloc((void **)&slab, per_q * num_queues, cudaHostAllocMapped));
+	CU_OK(cudaHostGetDevicePointer((void **)&dslab, slab, 0));
+	memset(slab, 0, per_q * num_queues);
+	for (uint32_t q = 0; q < num_queues; q++) {
+		Queue &Q = L->queues[q];
+		uint8_t *h = slab + per_q * q, *d = dslab + per_q * q;
+		Q.h_reqs = (oimgpu_req *)h;
+		Q.d_reqs = (oimgpu_req *)d;
+		h += sizeof(oimgpu_req) * queue_size; d += sizeof(oimgpu_req) * queue_size;
+		Q.h_iovs = (oimgpu_iov *)h;
+		Q.d_iovs = (oimgpu_iov *)d;
+		h += sizeof(oimgpu_iov) * L->iov_cap; d += sizeof(oimgpu_iov) * L->iov_cap;
+		Q.h_cpls = (oimgpu_cpl *)h;
+		Q.d_cpls = (oimgpu_cpl *)d;
+	}
+	int per_sm = 0;
+	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes()));
+	if (per_sm < 1) per_sm = 1;
+	L->grid_cap = L->sm_count * per_sm;
+	g.open_luns++;
+	*out = L.release();
+	return 0;
+}
+
+extern "C" int oimgpu_lun_close(oimgpu_lun *L)
+{
+	if (!L) return -EINVAL;
+	std::lock_guard<std::mutex> lk(g.mu);
+	cudaSetDevice(L->device);
+	cudaStreamSynchronize(L->stream);
+	if (!L->queues.empty()) cudaFreeHost(L->queues[0].h_reqs);
+	cudaFreeHost(L->h_desc);
+	cudaFree(L->d_desc);
+	cudaFree(L->d_ctx);
+	cudaEventDestroy(L->done);
+	cudaStreamDestroy(L->stream);
+	g.open_luns--;
+	delete L;
+	return 0;
+}
+
+extern "C" int oimgpu_lun_device(const oimgpu_lun *L) { return L ? L->device : -EINVAL; }
+extern "C" void *oimgpu_lun_stream(oimgpu_lun *L) { return L ? (void *)L->stream : nullptr; }
+
+extern "C" int oimgpu_mem_register(void *addr, size_t len)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	if (!addr || !len) return -EINVAL;
+	cudaError_t e = cudaHostRegister(addr, len, cudaHostRegisterMapped | cudaHostRegisterPortable);
+	if (e != cudaSuccess) {
+		(void)cudaGetLastError();
+		return e == cudaErrorHostMemoryAlreadyRegistered ? -EEXIST : -EFAULT;
+	}
+	g.registered[addr] = len;
+	return 0;
+}
+
+extern "C" int oimgpu_mem_unregister(void *addr)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	auto it = g.registered.find(addr);
+	if (it == g.registered.end()) return -ENOENT;
+	cudaHostUnregister(addr);
+	g.registered.erase(it);
+	return 0;
+}
+
+extern "C" int oimgpu_submit(oimgpu_lun *L, uint32_t q, const oimgpu_req *reqs, uint32_t nreqs,
+			     const oimgpu_iov *iovs, uint32_t niovs, int mem)
+{
+	if (!L || q >= L->num_queues || (!reqs && nreqs)) return -EINVAL;
+	Queue &Q = L->queues[q];
+	if (nreqs == 0) return 0;
+	if (mem == OIMGPU_MEM_DEVICE) {
+		/* caller-owned device arrays, used in place; completions go to the array given through
+		 * oimgpu_submit_device() or to the ring's device view */
+		if (Q.dev_count) return -EAGAIN;
+		Q.dev_reqs = reqs;
+		Q.dev_iovs = iovs;
+		Q.dev_cpls = nullptr;
+		Q.dev_count = nreqs;
+		return 0;
+	}
+	if (mem != OIMGPU_MEM_HOST) return -EINVAL;
+	if (nreqs > L->queue_size - (Q.tail - Q.reaped)) return -EAGAIN;
+	if (niovs > L->iov_cap) return -E2BIG;
+	/* copy into the ring, rebasing iov_start onto the ring's SG table */
+	const uint32_t qmask = L->queue_size - 1, imask = L->iov_cap - 1;
+	for (uint32_t i = 0; i < niovs; i++) Q.h_iovs[(Q.iov_tail + i) & imask] = iovs[i];
+	for (uint32_t i = 0; i < nreqs; i++) {
+		oimgpu_req r = reqs[i];
+		r.iov_start += Q.iov_tail;
+		Q.h_reqs[(Q.tail + i) & qmask] = r;
+	}
+	Q.tail += nreqs;
+	Q.iov_tail += niovs;
+	return 0;
+}
+
+/* OIMGPU_MEM_DEVICE submission with an explicit completion array in HBM */
+extern "C" int oimgpu_submit_device(oimgpu_lun *L, uint32_t q, const oimgpu_req *d_reqs, uint32_t nreqs,
+				    const oimgpu_iov *d_iovs, oimgpu_cpl *d_cpls)
+{
+	if (!L || q >= L->num_queues || !d_reqs || !d_cpls) return -EINVAL;
+	Queue &Q = L->queues[q];
+	if (Q.dev_count) return -EAGAIN;
+	Q.dev_reqs = d_reqs;
+	Q.dev_iovs = d_iovs;
+	Q.dev_cpls = d_cpls;
+	Q.dev_count = nreqs;
+	return 0;
+}
+
+extern "C" int oimgpu_kick(oimgpu_lun *L)
+{
+	if (!L) return -EINVAL;
+	CU_OK(cudaSetDevice(L->device));
+	uint32_t nd = 0;
+	for (uint32_t q = 0; q < L->num_queues; q++) {
+		Queue &Q = L->queues[q];
+		if (Q.dev_count) {
+			QueueDesc &D = L->h_desc[nd++];
+			D.reqs = Q.dev_reqs;
+			D.iovs = Q.dev_iovs;
+			D.cpls = Q.dev_cpls ? Q.dev_cpls : Q.d_cpls;
+			D.ring_mask = 0xffffffffu;
+			D.iov_mask = 0xffffffffu;
+			D.head = 0;
+			D.count = Q.dev_count;
+			Q.dev_count = 0;
+		}
+		if (Q.tail != Q.kicked) {
+			QueueDesc &D = L->h_desc[nd++];
+			D.reqs = Q.d_reqs;
+			D.iovs = Q.d_iovs;
+			D.cpls = Q.d_cpls;
+			D.ring_mask = L->queue_size - 1;
+			D.iov_mask = L->iov_cap - 1;
+			D.head = Q.kicked;
+			D.count = Q.tail - Q.kicked;
+			Q.kicked = Q.tail;
+		}
+		if (nd > L->num_queues) return -EOVERFLOW;
+		if (nd == L->num_queues && q + 1 < L->num_queues) {
+			/* both a device-array and a ring submission pending on many queues: flush what we have */
+			break;
+		}
+	}
+	if (nd == 0) return 0;
+	CU_OK(cudaMemcpyAsync(L->d_desc, L->h_desc, sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
+	const uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap);
+	oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, L->d_desc, nd);
+	CU_OK(cudaGetLastError());
+	CU_OK(cudaEventRecord(L->done, L->stream));
+	L->launches++;
+	return (int)nd;
+}
+
+extern "C" int oimgpu_lun_sync(oimgpu_lun *L)
+{
+	if (!L) return -EINVAL;
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaStreamSynchronize(L->stream));
+	return 0;
+}
+
+extern "C" int oimgpu_poll(oimgpu_lun *L, uint32_t q, oimgpu_cpl *cpls, uint32_t max, int wait)
+{
+	if (!L || q >= L->num_queues) return -EINVAL;
+	Queue &Q = L->queues[q];
+	if (Q.kicked == Q.reaped) return 0;
+	if (wait) {
+		int rc = oimgpu_lun_sync(L);
+		if (rc) return rc;
+	} else if (cudaEventQuery(L->done) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return 0;
+	}
+	uint32_t n = std::min(max, Q.kicked - Q.reaped);
+	const uint32_t qmask = L->queue_size - 1;
+	for (uint32_t i = 0; i < n; i++) cpls[i] = Q.h_cpls[(Q.reaped + i) & qmask];
+	Q.reaped += n;
+	return (int)n;
+}
+
+/* submit to queues 0..nq-1 (queue i gets reqs[i*per_q .. (i+1)*per_q)) and kick; asynchronous */
+extern "C" int oimgpu_submit_batch(oimgpu_lun *L, uint32_t nq, uint32_t per_q, const oimgpu_req *reqs,
+				   const oimgpu_iov *iovs, uint32_t niovs, oimgpu_cpl *cpls, int mem)
+{
+	if (!L || nq == 0 || nq > L->num_queues || !reqs) return -EINVAL;
+	if (mem == OIMGPU_MEM_DEVICE) {
+		if (!cpls) return -EINVAL;
+		for (uint32_t q = 0; q < nq; q++) {
+			int rc = oimgpu_submit_device(L, q, reqs + (size_t)q * per_q, per_q, iovs, cpls + (size_t)q * per_q);
+			if (rc) return rc;
+		}
+		return oimgpu_kick(L);
+	}
+	if (mem != OIMGPU_MEM_HOST) return -EINVAL;
+	/* host arrays: every queue's requests index the one SG table of the call */
+	for (uint32_t q = 0; q < nq; q++) {
+		const oimgpu_req *r = reqs + (size_t)q * per_q;
+		uint32_t lo = 0xffffffffu, hi = 0;
+		for (uint32_t i = 0; i < per_q; i++) {
+			if (r[i].iovcnt == 0) continue;
+			lo = std::min(lo, r[i].iov_start);
+			hi = std::max(hi, r[i].iov_start + r[i].iovcnt);
+		}
+		if (lo == 0xffffffffu) lo = hi = 0;
+		if (hi > niovs) return -EINVAL;
+		Queue &Q = L->queues[q];
+		if (per_q > L->queue_size - (Q.tail - Q.reaped)) return -EAGAIN;
+		if (hi - lo > L->iov_cap) return -E2BIG;
+		const uint32_t qmask = L->queue_size - 1, imask = L->iov_cap - 1;
+		for (uint32_t i = lo; i < hi; i++) Q.h_iovs[(Q.iov_tail + (i - lo)) & imask] = iovs[i];
+		for (uint32_t i = 0; i < per_q; i++) {
+			oimgpu_req t = r[i];
+			t.iov_start = t.iov_start - lo + Q.iov_tail;
+			Q.h_reqs[(Q.tail + i) & qmask] = t;
+		}
+		Q.tail += per_q;
+		Q.iov_tail += hi - lo;
+	}
+	return oimgpu_kick(L);
+}
+
+extern "C" int oimgpu_submit_and_wait(oimgpu_lun *L, uint32_t nq, uint32_t per_q, const oimgpu_req *reqs,
+				      const oimgpu_iov *iovs, uint32_t niovs, oimgpu_cpl *cpls, int mem)
+{
+	int rc = oimgpu_submit_batch(L, nq, per_q, reqs, iovs, niovs, cpls, mem);
+	if (rc < 0) return rc;
+	rc = oimgpu_lun_sync(L);
+	if (rc) return rc;
+	if (mem == OIMGPU_MEM_DEVICE) return 0;
+	for (uint32_t q = 0; q < nq; q++) {
+		int n = oimgpu_poll(L, q, cpls + (size_t)q * per_q, per_q, 0);
+		if (n != (int)per_q) return -EIO;
+	}
+	return 0;
+}
+
+extern "C" int oimgpu_lun_iostat(oimgpu_lun *L, oimgpu_iostat *out)
+{
+	if (!L || !out) return -EINVAL;
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaStreamSynchronize(L->stream));
+	LunCtx c;
+	CU_OK(cudaMemcpy(&c, L->d_ctx, sizeof(c), cudaMemcpyDeviceToHost));
+	memset(out, 0, sizeof(*out));
+	out->num_read_ops = c.stats[0];
+	out->num_write_ops = c.stats[1];
+	out->num_unmap_ops = c.stats[2];
+	out->num_other_ops = c.stats[3];
+	out->bytes_read = c.stats[4];
+	out->bytes_written = c.stats[5];
+	out->bytes_unmapped = c.stats[6];
+	out->num_errors = c.stats[7];
+	out->kernel_launches = L->launches;
+	return 0;
+}
+
+/* session-visible target state: hot-remove flags (vhost_scsi.c:1093-1100, lun.c:171-176) */
+extern "C" int oimgpu_lun_set_removed(oimgpu_lun *L, int removed, int lun_removed)
+{
+	if (!L) return -EINVAL;
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaStreamSynchronize(L->stream));
+	L->h_ctx.removed = removed != 0;
+	L->h_ctx.lun_removed = lun_removed != 0;
+	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, offsetof(LunCtx, stats), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+/* ---- device-timed region helpers (bench.py times on the LUN's own stream) ------------------------- */
+
+extern "C" int oimgpu_timer_create(void **start, void **stop)
+{
+	cudaEvent_t a, b;
+	CU_OK(cudaEventCreate(&a));
+	CU_OK(cudaEventCreate(&b));
+	*start = a;
+	*stop = b;
+	return 0;
+}
+
+extern "C" int oimgpu_timer_record(oimgpu_lun *L, void *ev)
+{
+	if (!L || !ev) return -EINVAL;
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaEventRecord((cudaEvent_t)ev, L->stream));
+	return 0;
+}
+
+extern "C" int oimgpu_timer_elapsed_ms(void *start, void *stop, float *ms)
+{
+	CU_OK(cudaEventSynchronize((cudaEvent_t)stop));
+	CU_OK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+	return 0;
+}
+
+extern "C" void oimgpu_timer_destroy(void *start, void *stop)
+{
+	if (start) cudaEventDestroy((cudaEvent_t)start);
+	if (stop) cudaEventDestroy((cudaEvent_t)stop);
+}
+
+/* ---- copy-engine level ----------------------------------------------------------------------------- */
+
+extern "C" int oimgpu_copy_submit(oimgpu_lun *L, void *dst, const void *src, uint64_t nbytes)
+{
+	if (!L || !dst || !src) return -EINVAL;
+	if (nbytes == 0) return 0;
+	CU_OK(cudaSetDevice(L->device));
+	const uint64_t units = (nbytes + kUnitBytes - 1) / kUnitBytes;
+	const uint32_t grid = (uint32_t)std::min<uint64_t>((units + kWarps - 1) / kWarps, (uint64_t)L->sm_count * 8);
+	oim_copy_kernel<<<grid, kThreads, 0, L->stream>>>((uint8_t *)dst, (const uint8_t *)src, nbytes);
+	CU_OK(cudaGetLastError());
+	L->launches++;
+	return 0;
+}
+
+extern "C" int oimgpu_fill_submit(oimgpu_lun *L, void *dst, uint8_t fill, uint64_t nbytes)
+{
+	if (!L || !dst) return -EINVAL;
+	if (nbytes == 0) return 0;
+	CU_OK(cudaSetDevice(L->device));
+	const uint32_t grid = (uint32_t)std::min<uint64_t>((nbytes / 16 + kThreads - 1) / kThreads + 1, (uint64_t)L->sm_count * 8);
+	oim_fill_kernel<<<grid, kThreads, 0, L->stream>>>((uint8_t *)dst, fill, nbytes);
+	CU_OK(cudaGetLastError());
+	L->launches++;
+	return 0;
+}

@@ -75,6 +75,13 @@ class _Oracle:
     def set_removed(self, target: int, removed: bool = True) -> None:
         self._set_removed(self.h, target, int(removed))
 
+    @classmethod
+    def describe(cls) -> str:
+        lib = C.CDLL(cls.path)
+        fn = getattr(lib, cls.prefix + "_describe")
+        fn.restype = C.c_char_p
+        return fn().decode()
+
     def close(self) -> None:
         if self.h:
             self.store = None

@@ -1,0 +1,284 @@
+"""The parity tests proper: the CUDA path (through the C ABI) against the oracle, bit for bit.
+
+Run on the B200 box: python -m pytest tests -m gpu.  /root/reference does not exist there; the
+checkers are the C restatement (compiled on the box) and, when it travelled, the prebuilt
+oracle/_ref/liboim_ref.so, plus the golden vectors committed under tests/golden/.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from oim_b200 import abi, traces
+from test_oracle import GOLDEN, bdevio_cases, load_golden, run_bdevio  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+@pytest.mark.parametrize("mem", ["device", "host"])
+def test_cuda_matches_reference_golden_vectors(gpu, path, mem):
+    t, z = load_golden(path)
+    cpls, arena, store, _ = util.run_cuda(gpu, t, int(z["num_blocks"]), mem=mem, removed=bool(z["removed"]))
+    util.assert_cpls_equal(cpls, z["cpls"], t.reqs, f"cuda[{mem}]:{t.name}")
+    assert util.sha(arena) == str(z["arena_sha"]), "client buffers differ from the reference's"
+    assert util.sha(store) == str(z["store_sha"]), "backing store differs from the reference's"
+
+
+@pytest.mark.parametrize("seed", range(300, 316))
+def test_cuda_matches_oracle_on_fuzz(gpu, oracles, seed):
+    """fresh seeded traces: all opcodes, ragged/unaligned/empty SG lists, limits, malformed requests,
+    with a hot spot so that RAW/WAW/WAR hazards inside a 32-request pass are common"""
+    nb = 32768
+    t = traces.fuzz_trace(500, nb, seed=seed, max_io_blocks=[8, 64, 300, 1024][seed % 4],
+                          arena_bytes=(8 << 20) if seed % 4 < 3 else (48 << 20))
+    want = util.run_oracle(oracles.PortOracle, t, nb)
+    got = util.run_cuda(gpu, t, nb, mem="device" if seed % 2 else "host")
+    util.assert_cpls_equal(got[0], want[0], t.reqs, f"seed {seed}")
+    assert (got[1] == want[1]).all(), f"client arena differs at {np.nonzero(got[1] != want[1])[0][:8]}"
+    assert (got[2] == want[2]).all(), f"store differs at {np.nonzero(got[2] != want[2])[0][:8]}"
+    if oracles.ref_available():         # the compiled reference itself, when it travelled to the box
+        ref = util.run_oracle(oracles.RefOracle, t, nb)
+        util.assert_cpls_equal(got[0], ref[0], t.reqs, f"seed {seed} vs reference")
+        assert (got[1] == ref[1]).all() and (got[2] == ref[2]).all()
+
+
+def test_cuda_hazards_same_lba_chain(gpu, oracles):
+    """32 requests of one pass all on the same blocks: W,R,W,R,... must serialise exactly"""
+    nb = 4096
+    b = abi.Batch(0)
+    off = 64
+    for i in range(64):
+        if i % 2 == 0:
+            b.write(100, 8, [(off, 4096)])
+        else:
+            b.read(100 + (i % 3), 4, [(off, 2048)])
+        off += 4096
+    reqs, iovs = b.arrays()
+    t = traces.Trace(reqs, iovs, off + 4096, "chain")
+    want = util.run_oracle(oracles.PortOracle, t, nb)
+    got = util.run_cuda(gpu, t, nb)
+    util.assert_cpls_equal(got[0], want[0], t.reqs)
+    assert (got[1] == want[1]).all() and (got[2] == want[2]).all()
+
+
+def test_cuda_non_pow2_block_size(gpu, oracles):
+    nb, bs = 9000, 520
+    t = traces.fuzz_trace(300, nb, block_size=bs, seed=77, max_io_blocks=16)
+    want = util.run_oracle(oracles.PortOracle, t, nb, block_size=bs)
+    got = util.run_cuda(gpu, t, nb, block_size=bs)
+    util.assert_cpls_equal(got[0], want[0], t.reqs)
+    assert (got[1] == want[1]).all() and (got[2] == want[2]).all()
+
+
+class DevBuf:
+    """client buffer in HBM (torch tensor: plumbing for device memory only)"""
+
+    def __init__(self, n):
+        import torch
+        self.t = torch.zeros(max(n, 1), dtype=torch.uint8, device="cuda:0")
+        self.addr = self.t.data_ptr()
+
+    def set(self, v):
+        import torch
+        if hasattr(v, "__len__"):
+            self.t[:len(v)] = torch.from_numpy(np.asarray(v, dtype=np.uint8)).to("cuda:0")
+        else:
+            self.t.fill_(int(v))
+        torch.cuda.synchronize()
+
+    def get(self):
+        import torch
+        torch.cuda.synchronize()
+        return self.t.cpu().numpy()
+
+
+def test_cuda_bdevio_suite(gpu):
+    """S/test/bdev/bdevio/bdevio.c:388-800 against an HBM-resident 32 MiB Malloc bdev"""
+    nb = 65536
+    gpu.construct_malloc_bdev(nb, 512, name="bdevio0", device=0)
+    gpu.construct_vhost_scsi_controller("bdevio.ctl")
+    gpu.add_vhost_scsi_lun("bdevio.ctl", 0, "bdevio0")
+    try:
+        with gpu.Lun("bdevio.ctl", 0) as lun:
+            run_bdevio(lambda r, i: lun.run(r, i), DevBuf, nb)
+    finally:
+        gpu.remove_vhost_scsi_target("bdevio.ctl", 0)
+        gpu.remove_vhost_controller("bdevio.ctl")
+        gpu.delete_bdev("bdevio0")
+
+
+def test_cuda_multi_queue_partitioned_mixed(gpu, oracles):
+    """many queues in one launch; queue q confined to LBA window q; 70/30 r/w (bdevperf.c:484-485)"""
+    import torch
+    nb, nq, per_q = 1 << 18, 24, 96
+    t = traces.partitioned_queues(nq, per_q, nb, pattern="randrw", read_pct=70, io_blocks=8)
+    host = np.zeros(t.arena_bytes, dtype=np.uint8)
+    traces.fill_arena(host, t)
+    want_cpls, want_arena, want_store = None, None, None
+    o = oracles.PortOracle(nb)
+    o.store[:] = traces.pattern_bytes(7, 0, o.store.size)
+    oa = host.copy()
+    want_cpls = o.submit(t.reqs, t.bind(oa.ctypes.data))
+    want_store = o.store.copy()
+    o.close()
+
+    gpu.construct_malloc_bdev(nb, 512, name="mq0", device=0)
+    gpu.construct_vhost_scsi_controller("mq.ctl")
+    gpu.add_vhost_scsi_lun("mq.ctl", 0, "mq0")
+    try:
+        gpu.bdev_write_raw("mq0", 0, traces.pattern_bytes(7, 0, nb * 512))
+        dev = torch.from_numpy(host).to("cuda:0")
+        with gpu.Lun("mq.ctl", 0, num_queues=nq, queue_size=128) as lun:
+            iovs = t.bind(dev.data_ptr())
+            k = len(iovs) // (nq * per_q)
+            for q in range(nq):
+                r = t.reqs[q * per_q:(q + 1) * per_q].copy()
+                r["iov_start"] -= np.uint32(q * per_q * k)
+                lun.submit(q, r, iovs[q * per_q * k:(q + 1) * per_q * k])
+            assert lun.kick() == nq
+            got = np.concatenate([lun.poll(q, per_q) for q in range(nq)])
+            stats = lun.iostat()
+        torch.cuda.synchronize()
+        util.assert_cpls_equal(got, want_cpls, t.reqs)
+        assert (dev.cpu().numpy() == oa).all()
+        assert (gpu.bdev_read_raw("mq0", 0, nb * 512) == want_store).all()
+        assert stats["num_read_ops"] == t.meta["reads"]
+        assert stats["num_write_ops"] == nq * per_q - t.meta["reads"]
+        assert stats["bytes_read"] == t.meta["reads"] * 4096
+    finally:
+        gpu.remove_vhost_scsi_target("mq.ctl", 0)
+        gpu.remove_vhost_controller("mq.ctl")
+        gpu.delete_bdev("mq0")
+
+
+def test_cuda_full_size_properties(gpu):
+    """BASELINE config sizes (8 GiB bdev): size-independent properties instead of a CPU replay.
+    write(seeded pattern) -> read back == pattern; random 4 KiB reads return the bytes the position-keyed
+    pattern predicts; unmap -> zeros; idempotence of a repeated trace."""
+    import torch
+    nb = 16777216
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 14 << 30:
+        pytest.skip("not enough free HBM")
+    gpu.construct_malloc_bdev(nb, 512, name="big0", device=0)
+    gpu.construct_vhost_scsi_controller("big.ctl")
+    gpu.add_vhost_scsi_lun("big.ctl", 0, "big0")
+    try:
+        nq, per_q = 64, 128
+        with gpu.Lun("big.ctl", 0, num_queues=nq, queue_size=128) as lun:
+            def run(t, dev):
+                iovs = t.bind(dev.data_ptr())
+                k = len(iovs) // (nq * per_q)
+                for q in range(nq):
+                    r = t.reqs[q * per_q:(q + 1) * per_q].copy()
+                    r["iov_start"] -= np.uint32(q * per_q * k)
+                    lun.submit(q, r, iovs[q * per_q * k:(q + 1) * per_q * k])
+                lun.kick()
+                return np.concatenate([lun.poll(q, per_q) for q in range(nq)])
+            # 1. 128 KiB sequential writes of a position-keyed pattern over 1 GiB in 32-page SG lists
+            wt = traces.partitioned_queues(nq, per_q, nb // 8, pattern="seqwrite", io_blocks=256, sg="pages")
+            payload = traces.pattern_bytes(0xC3, 0, wt.arena_bytes)
+            dev = torch.from_numpy(payload).to("cuda:0")
+            c = run(wt, dev)
+            assert (c["status"] == 0).all() and (c["resid"] == 0).all()
+            # 2. read the same LBAs back into a second arena with a single-element SG list
+            rt = traces.partitioned_queues(nq, per_q, nb // 8, pattern="seqread", io_blocks=256, sg="single")
+            back = torch.zeros(rt.arena_bytes, dtype=torch.uint8, device="cuda:0")
+            c = run(rt, back)
+            assert (c["status"] == 0).all()
+            torch.cuda.synchronize()
+            assert torch.equal(back, dev), "encode->decode round trip"
+            # 3. idempotence: replaying the write trace changes nothing
+            run(wt, dev)
+            back2 = torch.zeros_like(back)
+            run(rt, back2)
+            torch.cuda.synchronize()
+            assert torch.equal(back2, dev)
+            # 4. random 4 KiB reads across the whole 8 GiB: untouched area is zero (fresh Malloc bdev)
+            rr = traces.partitioned_queues(nq, per_q, nb, pattern="randread", io_blocks=8)
+            lbas = np.array([int.from_bytes(bytes(x[2:6]), "big") for x in rr.reqs["cdb"]])
+            out = torch.full((rr.arena_bytes,), 0x5A, dtype=torch.uint8, device="cuda:0")
+            c = run(rr, out)
+            assert (c["status"] == 0).all()
+            torch.cuda.synchronize()
+            o = out.cpu().numpy().reshape(-1, 4096)
+            untouched = lbas >= nb // 8
+            assert (o[untouched] == 0).all()
+        store_tail = gpu.bdev_read_raw("big0", (nb - 8) * 512, 4096)
+        assert (store_tail == 0).all()
+    finally:
+        gpu.remove_vhost_scsi_target("big.ctl", 0)
+        gpu.remove_vhost_controller("big.ctl")
+        gpu.delete_bdev("big0")
+
+
+def test_cuda_control_plane_errors(gpu):
+    """error behaviour of the control entry points = the reference RPCs' """
+    import errno
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.construct_malloc_bdev(0, 512)                 # bdev_malloc.c:384 "Disk must be more than 0 blocks"
+    assert e.value.rc == -errno.EINVAL
+    name = gpu.construct_malloc_bdev(2048, 512)
+    assert name.startswith("Malloc")                      # auto-name Malloc%d (bdev_malloc.c:412)
+    info = gpu.get_bdevs(name)[0]
+    assert info["product_name"] == "Malloc disk" and info["num_blocks"] == 2048 and not info["claimed"]
+    with pytest.raises(gpu.OimGpuError):
+        gpu.get_bdevs("no-such-bdev")
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.add_vhost_scsi_lun("nope", 0, name)
+    assert e.value.rc == -errno.ENODEV
+    gpu.construct_vhost_scsi_controller("/some/dir/cp.ctl")   # socket-dir prefix is stripped (vhost.c:611-628)
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.construct_vhost_scsi_controller("cp.ctl")
+    assert e.value.rc == -errno.EEXIST
+    assert gpu.add_vhost_scsi_lun("cp.ctl", 3, name) == 3
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.add_vhost_scsi_lun("cp.ctl", 3, name)
+    assert e.value.rc == -errno.EEXIST
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.add_vhost_scsi_lun("cp.ctl", 8, name)
+    assert e.value.rc == -errno.EINVAL
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.add_vhost_scsi_lun("cp.ctl", 4, "missing-bdev")
+    assert e.value.rc == -errno.EINVAL
+    c = gpu.get_vhost_controllers("cp.ctl")[0]
+    assert c["cpumask"] == "0x1" and c["backend_specific"]["scsi"][0]["target_name"] == "Target 3"
+    assert c["backend_specific"]["scsi"][0]["luns"] == [{"id": 0, "bdev_name": name}]
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.remove_vhost_controller("cp.ctl")             # still has a target -> EBUSY (vhost_scsi.c:837-842)
+    assert e.value.rc == -errno.EBUSY
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.delete_bdev(name)
+    assert e.value.rc == -errno.EBUSY
+    gpu.remove_vhost_scsi_target("cp.ctl", 3)
+    gpu.remove_vhost_controller("cp.ctl")
+    gpu.delete_bdev(name)
+
+
+def test_cuda_copy_engine_level(gpu):
+    """B2: struct spdk_copy_engine {copy, fill} on device buffers, odd sizes and alignments"""
+    import torch
+    gpu.construct_malloc_bdev(2048, 512, name="ce0", device=0)
+    gpu.construct_vhost_scsi_controller("ce.ctl")
+    gpu.add_vhost_scsi_lun("ce.ctl", 0, "ce0")
+    try:
+        with gpu.Lun("ce.ctl", 0) as lun:
+            src = torch.randint(0, 256, (5 << 20,), dtype=torch.uint8, device="cuda:0")
+            dst = torch.zeros_like(src)
+            torch.cuda.synchronize()
+            for (do, so, n) in [(0, 0, 5 << 20), (1, 3, 100003), (16, 32, 4096), (5, 5, 17), (7, 0, 1)]:
+                dst.zero_()
+                torch.cuda.synchronize()
+                lun.copy(dst.data_ptr() + do, src.data_ptr() + so, n)
+                lun.sync()
+                assert torch.equal(dst[do:do + n], src[so:so + n]), (do, so, n)
+                assert int(dst[do + n:do + n + 64].sum()) == 0 and int(dst[:do].sum()) == 0
+                lun.fill(dst.data_ptr() + do, 0xAB, n)
+                lun.sync()
+                assert bool((dst[do:do + n] == 0xAB).all()) and int(dst[do + n:do + n + 64].sum()) == 0
+    finally:
+        gpu.remove_vhost_scsi_target("ce.ctl", 0)
+        gpu.remove_vhost_controller("ce.ctl")
+        gpu.delete_bdev("ce0")
