@@ -15,18 +15,6 @@ namespace oimgpu {
 
 /* ---- parser: one lane, one request ------------------------------------------------------- */
 
-struct LaneState {
-	Parsed p;
-	TaskStatus st;
-	uint32_t data_transferred;
-	uint32_t used_len;
-	uint32_t units;
-	uint8_t  response;
-	uint8_t  resp_valid;
-	uint8_t  hazard;	/* 0 none, 1 reads store, 2 writes store, 3 barrier (multi-range writer) */
-	uint8_t  unmap_ok_descs;	/* UNMAP: descriptors (incl. empty ones) to walk when emitting */
-};
-
 __device__ __forceinline__ uint32_t units_of(uint64_t len) { return (uint32_t)((len + kUnitBytes - 1) / kUnitBytes); }
 
 /* spdk_bdev_bytes_to_blocks + spdk_bdev_io_valid_blocks (bdev.c:2474-2509) on (offset, nbytes) */
@@ -52,38 +40,38 @@ __device__ __forceinline__ void scsi_readwrite(const LunCtx &L, LaneState &s, ui
 {
 	s.data_transferred = 0;
 	if (dxfer_dir != OIMGPU_DIR_NONE && dxfer_dir != (is_read ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV)) {
-		s.st.check(SK_NO_SENSE, ASC_NONE);
+		set_check(s, SK_NO_SENSE, ASC_NONE);
 		return;
 	}
 	if (L.num_blocks <= lba || L.num_blocks - lba < xfer_len) {
-		s.st.check(SK_ILLEGAL_REQUEST, ASC_LBA_OOR);
+		set_check(s, SK_ILLEGAL_REQUEST, ASC_LBA_OOR);
 		return;
 	}
 	if (xfer_len == 0) {
-		s.st.good();
+		s.status = SC_GOOD;
 		return;
 	}
 	if (xfer_len > OIMGPU_MAX_XFER_BYTES / L.block_size) {
-		s.st.check(SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD);
+		set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD);
 		return;
 	}
 	uint64_t nblk;
 	if (!is_read) {
 		if ((uint64_t)xfer_len * L.block_size > transfer_len) {
-			s.st.check(SK_NO_SENSE, ASC_NONE);
+			set_check(s, SK_NO_SENSE, ASC_NONE);
 			return;
 		}
 	}
 	/* both directions move task->length bytes, not xfer_len blocks (scsi_bdev.c:1333, 1387) */
-	if (!bdev_range_ok(L, lba, s.p.length, &nblk)) {
-		s.st.check(SK_NO_SENSE, ASC_NONE);
+	if (!bdev_range_ok(L, lba, s.length, &nblk)) {
+		set_check(s, SK_NO_SENSE, ASC_NONE);
 		return;
 	}
-	s.data_transferred = s.p.length;
-	s.p.off = lba * L.block_size;
-	s.p.store_lo = lba;
-	s.p.store_hi = lba + nblk;
-	s.p.op = is_read ? OP_READ : OP_WRITE;
+	s.data_transferred = s.length;
+	s.off = lba * L.block_size;
+	s.store_lo = lba;
+	s.store_hi = lba + nblk;
+	s.op = is_read ? OP_READ : OP_WRITE;
 	s.hazard = nblk ? (is_read ? 1 : 2) : 0;
 }
 
@@ -92,26 +80,26 @@ __device__ __forceinline__ void scsi_readwrite(const LunCtx &L, LaneState &s, ui
 __device__ inline void scsi_unmap(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, uint32_t iovcnt,
 				  LaneState &s, Segment *emit, uint32_t *emit_unit, uint16_t wave)
 {
-	const uint32_t data_len = s.p.length;
+	const uint32_t data_len = s.length;
 	int desc_count = -1;
 	if (data_len >= 8) {
 		uint16_t ddl = (uint16_t)(gather_byte(q, r, iovcnt, 2) << 8 | gather_byte(q, r, iovcnt, 3));
 		if (ddl <= data_len - 8 && ddl / 16 <= OIMGPU_MAX_UNMAP_DESC) desc_count = ddl / 16;
 	}
 	if (desc_count < 0) {
-		if (!emit) s.st.check(SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD);
+		if (!emit) set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD);
 		return;
 	}
 	uint32_t nseg = 0, units = 0;
 	for (int i = 0; i < desc_count; i++) {
-		uint8_t d[12];
-		for (int k = 0; k < 12; k++) d[k] = gather_byte(q, r, iovcnt, 8 + 16 * i + k);
-		uint64_t ob = be64(d);
-		uint32_t nb = be32(d + 8);
+		uint64_t ob = 0;
+		uint32_t nb = 0;
+		for (int k = 0; k < 8; k++) ob = ob << 8 | gather_byte(q, r, iovcnt, 8 + 16 * i + k);
+		for (int k = 8; k < 12; k++) nb = nb << 8 | gather_byte(q, r, iovcnt, 8 + 16 * i + k);
 		if (nb == 0) continue;
 		if (ob + nb < ob || ob + nb > L.num_blocks) {
 			/* spdk_bdev_unmap_blocks -> -EINVAL: earlier descriptors stay applied, the rest are skipped */
-			if (!emit) s.st.check(SK_NO_SENSE, ASC_NONE);
+			if (!emit) set_check(s, SK_NO_SENSE, ASC_NONE);
 			break;
 		}
 		uint64_t bytes = (uint64_t)nb * L.block_size;
@@ -129,9 +117,9 @@ __device__ inline void scsi_unmap(const LunCtx &L, const QueueDesc &q, const oim
 		units += units_of(bytes);
 	}
 	if (!emit) {
-		s.p.nseg = nseg;
+		s.nseg = nseg;
 		s.units = units;
-		s.p.op = OP_UNMAP;
+		s.op = OP_UNMAP;
 		s.hazard = nseg ? 3 : 0;
 	}
 }
@@ -143,26 +131,26 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 	const uint32_t dxfer_dir = from_dev ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV;
 	uint32_t len = 0, nonzero = 0, units = 0;
 
-	s.p.op = OP_NONE; s.p.nseg = 0; s.p.valid = 1; s.p.length = 0; s.p.off = 0;
-	s.p.store_lo = s.p.store_hi = 0;
-	s.st.status = SC_GOOD; s.st.has_sense = 0; s.st.sk = 0; s.st.asc = 0;
+	s.op = OP_NONE; s.nseg = 0; s.valid = 1; s.length = 0; s.off = 0;
+	s.store_lo = s.store_hi = 0;
+	s.status = SC_GOOD; s.sk = 0; s.asc = 0;
 	s.data_transferred = 0; s.units = 0; s.hazard = 0; s.response = OIMGPU_S_OK; s.resp_valid = 1;
 
 	/* ---- task_data_setup (vhost_scsi.c:490-624): walk the SG list ---- */
 	for (uint32_t j = 0; j < cnt; j++) {
-		if (j >= OIMGPU_IOVS_MAX) { s.p.valid = 0; break; }
+		if (j >= OIMGPU_IOVS_MAX) { s.valid = 0; break; }
 		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
-		if (v.addr == 0) { s.p.valid = 0; break; }
+		if (v.addr == 0) { s.valid = 0; break; }
 		len += v.len;
 		if (v.len) { nonzero++; units += units_of(v.len); }
 	}
-	if (!s.p.valid) {
+	if (!s.valid) {
 		s.used_len = 0;		/* invalid_request(): used element only (vhost_scsi.c:347-358) */
 		s.resp_valid = 0;
 		s.response = 0;
 		return;
 	}
-	s.p.length = len;
+	s.length = len;
 	s.used_len = from_dev ? OIMGPU_RESP_SIZE + len : OIMGPU_RESP_SIZE;
 
 	/* ---- spdk_vhost_scsi_task_init_target (vhost_scsi.c:361-387) ---- */
@@ -177,23 +165,23 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 	if (null_lun) {
 		/* spdk_scsi_task_process_null_lun (task.c:258-293) */
 		if (cdb[0] == 0x12) {
-			uint8_t buf[36];
+			uint8_t *buf = s.scratch;
 			for (int k = 0; k < 36; k++) buf[k] = 0;
 			buf[0] = 0x03 << 5 | 0x1f;
 			buf[4] = 36 - 5;
 			uint32_t alloc_len = be16(&cdb[3]);
-			if (scatter_small(q, r, cnt, len, buf, alloc_len < 36 ? alloc_len : 36, s.st) >= 0) {
+			if (scatter_small(q, r, cnt, len, buf, alloc_len < 36 ? alloc_len : 36, s) >= 0) {
 				s.data_transferred = 36;
-				s.st.good();
+				s.status = SC_GOOD;
 			}
 		} else {
-			s.st.check(SK_ILLEGAL_REQUEST, ASC_LUN_NOT_SUPPORTED);
+			set_check(s, SK_ILLEGAL_REQUEST, ASC_LUN_NOT_SUPPORTED);
 			s.data_transferred = 0;
 		}
 		return;
 	}
 	if (L.lun_removed) {
-		s.st.check(SK_ABORTED_COMMAND, ASC_NONE);	/* spdk_scsi_task_process_abort */
+		set_check(s, SK_ABORTED_COMMAND, ASC_NONE);	/* spdk_scsi_task_process_abort */
 		return;
 	}
 
@@ -215,21 +203,21 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 		scsi_readwrite(L, s, dxfer_dir, len, be64(&cdb[2]), be32(&cdb[10]), cdb[0] == 0x88);
 		break;
 	case 0x25: {	/* READ CAPACITY (10) */
-		uint8_t buf[8];
+		uint8_t *buf = s.scratch;
 		uint64_t last = L.num_blocks - 1;
 		uint32_t v = last > 0xffffffffULL ? 0xffffffffu : (uint32_t)last;
 		buf[0] = v >> 24; buf[1] = v >> 16; buf[2] = v >> 8; buf[3] = v;
 		buf[4] = L.block_size >> 24; buf[5] = L.block_size >> 16; buf[6] = L.block_size >> 8; buf[7] = L.block_size;
 		uint32_t l = len < 8 ? len : 8;
-		if (scatter_small(q, r, cnt, len, buf, l, s.st) >= 0) {
+		if (scatter_small(q, r, cnt, len, buf, l, s) >= 0) {
 			s.data_transferred = l;
-			s.st.good();
+			s.status = SC_GOOD;
 		}
 		break;
 	}
 	case 0x9e:
 		if ((cdb[1] & 0x1f) == 0x10) {	/* READ CAPACITY (16) */
-			uint8_t buf[32];
+			uint8_t *buf = s.scratch;
 			for (int k = 0; k < 32; k++) buf[k] = 0;
 			uint64_t last = L.num_blocks - 1;
 			for (int k = 0; k < 8; k++) buf[k] = (uint8_t)(last >> (56 - 8 * k));
@@ -237,12 +225,12 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 			buf[14] |= 1 << 7;
 			uint32_t al = be32(&cdb[10]);
 			uint32_t l = al < 32 ? al : 32;
-			if (scatter_small(q, r, cnt, len, buf, l, s.st) >= 0) {
+			if (scatter_small(q, r, cnt, len, buf, l, s) >= 0) {
 				s.data_transferred = l;
-				s.st.good();
+				s.status = SC_GOOD;
 			}
 		} else {
-			s.st.check(SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
+			set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
 		}
 		break;
 	case 0x35: case 0x91: {	/* SYNCHRONIZE CACHE: bounds check only; FLUSH is a no-op on a RAM disk */
@@ -251,7 +239,7 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 		else { lba = be64(&cdb[2]); n = be32(&cdb[10]); }
 		if (n == 0) n = (uint32_t)(L.num_blocks - lba);
 		if (n != 0 && (lba >= L.num_blocks || n > L.num_blocks || lba > L.num_blocks - n)) {
-			s.st.check(SK_NO_SENSE, ASC_NONE);
+			set_check(s, SK_NO_SENSE, ASC_NONE);
 		}
 		break;
 	}
@@ -261,26 +249,26 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 	/* ---- spdk_bdev_scsi_process_primary (scsi_bdev.c:1827-2077), table-free commands ---- */
 	case 0x03:	/* REQUEST SENSE */
 		if (!(cdb[1] & 0x1)) {
-			uint8_t buf[18];
+			uint8_t *buf = s.scratch;
 			for (int k = 0; k < 18; k++) buf[k] = 0;
 			buf[0] = 0xf0; buf[7] = 10;
 			uint32_t al = cdb[4];
-			scatter_small(q, r, cnt, len, buf, al < 18 ? al : 18, s.st);
+			scatter_small(q, r, cnt, len, buf, al < 18 ? al : 18, s);
 			s.data_transferred = al < 18 ? al : 18;
 		}
-		s.st.good();	/* rc >= 0 path overrides whatever status was set (scsi_bdev.c:2066-2069) */
+		s.status = SC_GOOD;	/* rc >= 0 path overrides whatever status was set (scsi_bdev.c:2066-2069) */
 		break;
 	case 0x4c: case 0x4d:	/* LOG SELECT / LOG SENSE */
-		s.st.check(SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
+		set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
 		break;
 	case 0x00: case 0x1b:	/* TEST UNIT READY / START STOP UNIT */
 		break;
 	default:
-		s.st.check(SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
+		set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
 		break;
 	}
-	if (s.p.op == OP_READ || s.p.op == OP_WRITE) {
-		s.p.nseg = nonzero;
+	if (s.op == OP_READ || s.op == OP_WRITE) {
+		s.nseg = nonzero;
 		s.units = units;
 	}
 }
@@ -289,20 +277,20 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 __device__ inline void emit_segments(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, LaneState &s,
 				     Segment *out, uint32_t first_unit, uint16_t wave)
 {
-	if (s.p.op == OP_UNMAP) {
+	if (s.op == OP_UNMAP) {
 		uint32_t u = first_unit;
 		scsi_unmap(L, q, r, r.iovcnt, s, out, &u, wave);
 		return;
 	}
-	if (s.p.op != OP_READ && s.p.op != OP_WRITE) return;
-	uint8_t *pos = L.store[0] + s.p.off;
+	if (s.op != OP_READ && s.op != OP_WRITE) return;
+	uint8_t *pos = L.store[0] + s.off;
 	uint32_t k = 0, u = first_unit;
 	for (uint32_t j = 0; j < r.iovcnt; j++) {
 		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
 		if (v.len == 0) continue;
 		Segment &g = out[k++];
 		uint8_t *client = (uint8_t *)(uintptr_t)v.addr;
-		if (s.p.op == OP_READ) { g.src = pos; g.dst = client; g.mirror = 0; }
+		if (s.op == OP_READ) { g.src = pos; g.dst = client; g.mirror = 0; }
 		else { g.src = client; g.dst = pos; g.mirror = 1; }
 		g.len = v.len;
 		g.first_unit = u;
@@ -314,7 +302,10 @@ __device__ inline void emit_segments(const LunCtx &L, const QueueDesc &q, const 
 
 /* ---- the kernel ----------------------------------------------------------------------------- */
 
-__global__ void __launch_bounds__(kThreads, 4)
+#ifndef OIM_MIN_BLOCKS
+#define OIM_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
 oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -337,13 +328,13 @@ oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 			__syncthreads();
 
 			/* 2. parse + hazards + first round bookkeeping (warp 0) */
-			LaneState s;
+			LaneState &s = sh.lane[lane];	/* meaningful for warp 0 only */
 			uint16_t wave = 0;
 			uint32_t nwaves = 1;
 			if (warp == 0) {
 				const bool active = (uint32_t)lane < n;
 				if (active) parse_request(L, q, sh.req[lane], s);
-				else { s.p.nseg = 0; s.units = 0; s.hazard = 0; s.p.op = OP_NONE; s.p.valid = 0; }
+				else { s.nseg = 0; s.units = 0; s.hazard = 0; s.op = OP_NONE; s.valid = 0; s.store_lo = s.store_hi = 0; }
 
 				/* hazard waves.  Writers are visited in ring order; a writer is pushed behind every
 				 * earlier request it overlaps, every later overlapping request behind the writer. */
@@ -354,11 +345,11 @@ oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 					while (w) {
 						const int j = __ffs(w) - 1;
 						w &= w - 1;
-						const uint64_t jlo = __shfl_sync(0xffffffffu, s.p.store_lo, j);
-						const uint64_t jhi = __shfl_sync(0xffffffffu, s.p.store_hi, j);
+						const uint64_t jlo = __shfl_sync(0xffffffffu, s.store_lo, j);
+						const uint64_t jhi = __shfl_sync(0xffffffffu, s.store_hi, j);
 						const int jhaz = __shfl_sync(0xffffffffu, (int)s.hazard, j);
 						const bool overlap = s.hazard != 0 && lane != j &&
-							(jhaz == 3 || s.hazard == 3 || (s.p.store_lo < jhi && jlo < s.p.store_hi));
+							(jhaz == 3 || s.hazard == 3 || (s.store_lo < jhi && jlo < s.store_hi));
 						/* earlier overlapping requests decide the writer's wave */
 						uint32_t need = (overlap && lane < j) ? (uint32_t)wave + 1 : 0;
 						need = __reduce_max_sync(0xffffffffu, need);
@@ -377,7 +368,7 @@ oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 				if (warp == 0) {
 					/* prefix sums of segment and unit counts over requests r0.. */
 					const bool in = (uint32_t)lane >= r0 && (uint32_t)lane < n;
-					uint32_t segs = in ? s.p.nseg : 0, units = in ? s.units : 0;
+					uint32_t segs = in ? s.nseg : 0, units = in ? s.units : 0;
 					uint32_t seg_incl = segs, unit_incl = units;
 #pragma unroll
 					for (int o = 1; o < 32; o <<= 1) {
@@ -432,7 +423,7 @@ oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 			/* 4. completion records (spdk_vhost_scsi_task_cpl, vhost_scsi.c:311-331) */
 			if (warp == 0) {
 				if ((uint32_t)lane < n) {
-					oimgpu_cpl c;
+					__align__(16) oimgpu_cpl c;
 					int4 *cz = reinterpret_cast<int4 *>(&c);
 					cz[0] = cz[1] = cz[2] = make_int4(0, 0, 0, 0);
 					c.tag = sh.req[lane].tag;
@@ -440,13 +431,13 @@ oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 					c.resp_valid = s.resp_valid;
 					c.response = s.response;
 					if (s.resp_valid && s.response == OIMGPU_S_OK) {
-						c.status = s.st.status;
-						if (s.st.status != SC_GOOD) {
-							c.sense[0] = 0xf0; c.sense[2] = s.st.sk & 0xf; c.sense[7] = 10;
-							c.sense[12] = s.st.asc; c.sense[13] = 0;
+						c.status = s.status;
+						if (s.status != SC_GOOD) {
+							c.sense[0] = 0xf0; c.sense[2] = s.sk & 0xf; c.sense[7] = 10;
+							c.sense[12] = s.asc; c.sense[13] = 0;
 							c.sense_len = OIMGPU_SENSE_SIZE;
 						}
-						c.resid = s.p.length - s.data_transferred;
+						c.resid = s.length - s.data_transferred;
 						c.data_transferred = s.data_transferred;
 					}
 					sh.cpl[lane] = c;
@@ -458,13 +449,13 @@ oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 						reinterpret_cast<const int4 *>(&sh.cpl[v / 3])[v % 3]);
 				}
 				/* counters for get_bdevs_iostat: one atomic per counter per pass */
-				const bool ok = (uint32_t)lane < n && s.resp_valid && s.response == OIMGPU_S_OK && s.st.status == SC_GOOD;
-				const uint32_t rd = __popc(__ballot_sync(0xffffffffu, ok && s.p.op == OP_READ));
-				const uint32_t wr = __popc(__ballot_sync(0xffffffffu, ok && s.p.op == OP_WRITE));
-				const uint32_t um = __popc(__ballot_sync(0xffffffffu, ok && s.p.op == OP_UNMAP));
+				const bool ok = (uint32_t)lane < n && s.resp_valid && s.response == OIMGPU_S_OK && s.status == SC_GOOD;
+				const uint32_t rd = __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_READ));
+				const uint32_t wr = __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_WRITE));
+				const uint32_t um = __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_UNMAP));
 				const uint32_t er = __popc(__ballot_sync(0xffffffffu, (uint32_t)lane < n && !ok));
-				uint32_t rb = (ok && s.p.op == OP_READ) ? s.p.length : 0;
-				uint32_t wb = (ok && s.p.op == OP_WRITE) ? s.p.length : 0;
+				uint32_t rb = (ok && s.op == OP_READ) ? s.length : 0;
+				uint32_t wb = (ok && s.op == OP_WRITE) ? s.length : 0;
 				unsigned long long rbt = __reduce_add_sync(0xffffffffu, rb >> 9), wbt = __reduce_add_sync(0xffffffffu, wb >> 9);
 				if (lane == 0) {
 					if (rd) { atomicAdd(&lun->stats[0], rd); atomicAdd(&lun->stats[4], rbt << 9); }

@@ -45,6 +45,8 @@ constexpr int kSegCap = 768;			/* SG segments staged in shared memory per round 
 constexpr uint32_t kUnitBytes = 4096;		/* bytes one warp moves per step: 8 x 16 B per lane */
 constexpr int kMaxReplicas = 4;
 
+enum : uint8_t { OP_NONE = 0, OP_READ = 1, OP_WRITE = 2, OP_UNMAP = 3 };
+
 enum : uint8_t { SC_GOOD = 0x00, SC_CHECK = 0x02 };
 enum : uint8_t { SK_NO_SENSE = 0x0, SK_ILLEGAL_REQUEST = 0x5, SK_ABORTED_COMMAND = 0xb };
 enum : uint8_t { ASC_NONE = 0x00, ASC_INVALID_OPCODE = 0x20, ASC_LBA_OOR = 0x21, ASC_INVALID_FIELD = 0x24,
@@ -85,9 +87,29 @@ struct Segment {
 	uint16_t mirror;		/* 1: dst is in the backing store -> replicate to peers */
 };
 
+/* What a parser lane knows about its request after decode; lives in shared memory so that the
+ * parser's state never competes with the movers' data registers */
+struct LaneState {
+	uint64_t off;			/* byte offset in the backing store */
+	uint64_t store_lo, store_hi;	/* block range touched, for hazard detection */
+	uint32_t length;		/* task->length: sum of SG element lengths */
+	uint32_t nseg;			/* segments this request emits */
+	uint32_t units;
+	uint32_t data_transferred;
+	uint32_t used_len;
+	uint8_t  op;			/* OP_* */
+	uint8_t  valid;			/* 0: invalid_request() */
+	uint8_t  status, sk, asc;
+	uint8_t  response;
+	uint8_t  resp_valid;
+	uint8_t  hazard;		/* 0 none, 1 reads store, 2 writes store, 3 barrier (multi-range writer) */
+	uint8_t  scratch[40];		/* small control payloads (READ CAPACITY, INQUIRY, REQUEST SENSE) */
+};
+
 struct __align__(16) PassShared {
 	oimgpu_req req[kPass];
 	oimgpu_cpl cpl[kPass];
+	LaneState lane[kPass];
 	Segment seg[kSegCap];
 	uint32_t nseg;
 	uint32_t nunits;
@@ -130,13 +152,6 @@ __device__ __forceinline__ uint32_t be32(const uint8_t *p)
 	return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
 }
 __device__ __forceinline__ uint64_t be64(const uint8_t *p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
-
-/* spdk_scsi_task_set_status + build_sense_data (S/lib/scsi/task.c:198-247) into the completion */
-struct TaskStatus {
-	uint8_t status, sk, asc, has_sense;
-	__device__ __forceinline__ void good() { status = SC_GOOD; }
-	__device__ __forceinline__ void check(uint8_t k, uint8_t a) { status = SC_CHECK; sk = k; asc = a; has_sense = 1; }
-};
 
 /* Move `n` (<= kUnitBytes) bytes with one warp.  Fast path: both sides 16-byte aligned. */
 __device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
@@ -199,25 +214,19 @@ __device__ __forceinline__ void zero_unit(uint8_t *dst, uint32_t n, int lane)
 	}
 }
 
-/* What a parser lane knows about its request after decode */
-struct Parsed {
-	uint64_t off;		/* byte offset in the backing store */
-	uint64_t store_lo, store_hi;	/* block range touched, for hazard detection */
-	uint32_t length;	/* task->length: sum of SG element lengths */
-	uint32_t nseg;		/* segments this request emits */
-	uint8_t  op;		/* 0 none, 1 read (store->sg), 2 write (sg->store), 3 unmap, 4 small scatter */
-	uint8_t  valid;		/* 0: invalid_request() */
-};
-
-enum : uint8_t { OP_NONE = 0, OP_READ = 1, OP_WRITE = 2, OP_UNMAP = 3 };
 
 /* spdk_scsi_task_scatter_data (task.c:111-152) of a <=36-byte control payload into the SG list */
+__device__ __forceinline__ void set_check(LaneState &s, uint8_t sk, uint8_t asc)
+{
+	s.status = SC_CHECK; s.sk = sk; s.asc = asc;
+}
+
 __device__ inline int scatter_small(const QueueDesc &q, const oimgpu_req &r, uint32_t iovcnt, uint32_t total_len,
-				    const uint8_t *buf, uint32_t buf_len, TaskStatus &st)
+				    const uint8_t *buf, uint32_t buf_len, LaneState &st)
 {
 	if (buf_len == 0) return 0;
 	if (total_len < buf_len) {
-		st.check(SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD);
+		set_check(st, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD);
 		return -1;
 	}
 	uint32_t left = buf_len;

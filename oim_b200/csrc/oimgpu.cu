@@ -587,7 +587,7 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	L->sm_count = g.devices[find_device_slot(L->device)].sm_count;
 	L->num_queues = num_queues;
 	L->queue_size = queue_size;
-	L->iov_cap = queue_size * 4 < 1024 ? 1024 : queue_size * 4;	/* power of two >= 8 x 129 */
+	L->iov_cap = queue_size * 8 < 1024 ? 1024 : queue_size * 8;	/* power of two >= 7 x 129 */
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
 	CU_OK(cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming));

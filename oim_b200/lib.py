@@ -315,7 +315,7 @@ class Lun:
         """submit + kick + wait + reap on one queue, in chunks that fit the ring; returns completions.
         Assumes the SG table is laid out in request order (as Batch/traces build it)."""
         out = []
-        iov_cap = max(1024, self.queue_size * 4)
+        iov_cap = max(1024, self.queue_size * 8)
         starts = reqs["iov_start"].astype(np.int64)
         ends = starts + reqs["iovcnt"]
         lo, n = 0, len(reqs)

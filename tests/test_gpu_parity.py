@@ -167,7 +167,7 @@ def test_cuda_full_size_properties(gpu):
     gpu.add_vhost_scsi_lun("big.ctl", 0, "big0")
     try:
         nq, per_q = 64, 128
-        with gpu.Lun("big.ctl", 0, num_queues=nq, queue_size=128) as lun:
+        with gpu.Lun("big.ctl", 0, num_queues=nq, queue_size=1024) as lun:
             def run(t, dev):
                 iovs = t.bind(dev.data_ptr())
                 k = len(iovs) // (nq * per_q)
