@@ -27,16 +27,20 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defs: str | None = None, out: str = LIB) -> str:
+    """defs: extra -D flags for tuning builds (e.g. "-DOIM_MOVERS=8 -DOIM_MIN_BLOCKS=2")."""
+    defs = defs if defs is not None else os.environ.get("OIM_NVCC_DEFS", "")
+    if os.environ.get("OIM_LIB_PATH") and out == LIB:
+        return os.environ["OIM_LIB_PATH"]           # a tuning build was selected explicitly
+    if not force and not defs and out == LIB and not _stale():
         return LIB
-    cmd = [NVCC, *FLAGS, "-Xptxas", "-v", "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [NVCC, *FLAGS, *defs.split(), "-Xptxas", "-v", "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
     if verbose:
         print(out.stderr[-3000:])
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -1,17 +1,53 @@
 /*
  * lun_kernel.cu — oim_lun_queue_kernel: see lun_kernel.cuh for the map onto the reference.
  *
- * Launch shape: grid = min(#queues, SMs x CTAs/SM), block = 256 threads.  CTA b owns queues
- * b, b+grid, ... and for each runs passes of <= 32 requests:
- *   1. stage the 32 request slots (2 KiB) in shared memory, 16 B per thread, coalesced
- *   2. warp 0: lane i parses request i (SG walk, LUN check, CDB decode, limits), the warp finds
- *      LBA hazards, and the lanes emit SG segments + completion records to shared memory
- *   3. all warps move payload, one 4 KiB unit per warp-step, 8 x 16-byte loads in flight per lane
- *   4. warp 0 writes the 32 completion records (48 B each) coalesced
+ * Warp-specialised: every CTA is a small "reactor" with
+ *   warp 0            the PARSER   = vdev_worker/process_requestq (vhost_scsi.c:690-772): pulls <= 32
+ *                     request slots per pass, lane i parses request i (SG walk, LUN check, CDB
+ *                     decode, limits), the warp orders LBA hazards, emits SG segments into a stage
+ *                     and later publishes the pass's completion records;
+ *   warps 1..kMovers  the MOVERS   = bdev_malloc_readv/writev/unmap + mem_copy_submit
+ *                     (bdev_malloc.c:153-233, copy_engine.c:114-140): stream the payload of the
+ *                     stage, one 4 KiB unit per warp-step, 8 x 16-byte loads in flight per lane.
+ * Parser and movers are decoupled by a ring of kStages stages guarded by mbarriers
+ * (full[s]: parser -> movers, empty[s]: movers -> parser), so request fetch, SG walk and CDB decode
+ * of pass p+1/p+2 overlap the data movement of pass p.  Request slots of the next pass are
+ * prefetched into registers while the current one is parsed.
+ *
+ * Launch shape: grid = min(#queues, SMs x CTAs/SM) CTAs of (1 + kMovers) x 32 threads; CTA b owns
+ * queues b, b+grid, ... and keeps the pipeline running across queue boundaries.
  */
 #include "lun_kernel.cuh"
 
 namespace oimgpu {
+
+/* ---- mbarrier helpers (shared::cta) ------------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra DONE_%=;\n\t"
+		"bra WAIT_%=;\n\t"
+		"DONE_%=:\n\t}"
+		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void movers_barrier()
+{
+	asm volatile("bar.sync 1, %0;" :: "n"(kMovers * 32) : "memory");
+}
 
 /* ---- parser: one lane, one request ------------------------------------------------------- */
 
@@ -77,8 +113,8 @@ __device__ __forceinline__ void scsi_readwrite(const LunCtx &L, LaneState &s, ui
 
 /* UNMAP parameter list walk (scsi_bdev.c:1545-1679).  emit == nullptr: validate and count;
  * otherwise also write one zero-fill segment per accepted descriptor. */
-__device__ inline void scsi_unmap(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, uint32_t iovcnt,
-				  LaneState &s, Segment *emit, uint32_t *emit_unit, uint16_t wave)
+__device__ __noinline__ void scsi_unmap(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, uint32_t iovcnt,
+					LaneState &s, Segment *emit, uint32_t first_unit, uint16_t wave)
 {
 	const uint32_t data_len = s.length;
 	int desc_count = -1;
@@ -108,10 +144,9 @@ __device__ inline void scsi_unmap(const LunCtx &L, const QueueDesc &q, const oim
 			g.src = nullptr;
 			g.dst = L.store[0] + ob * L.block_size;
 			g.len = bytes;
-			g.first_unit = *emit_unit;
+			g.first_unit = first_unit + units;
 			g.wave = wave;
 			g.mirror = 1;
-			*emit_unit += units_of(bytes);
 		}
 		nseg++;
 		units += units_of(bytes);
@@ -124,7 +159,54 @@ __device__ inline void scsi_unmap(const LunCtx &L, const QueueDesc &q, const oim
 	}
 }
 
-__device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, LaneState &s)
+/* control payloads: READ CAPACITY 10/16, REQUEST SENSE, null-LUN INQUIRY (kept out of line: rare) */
+__device__ __noinline__ void scsi_control(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, uint32_t cnt,
+					  uint32_t len, LaneState &s, int which)
+{
+	uint8_t *buf = s.scratch;
+	for (int k = 0; k < 36; k++) buf[k] = 0;
+	const uint8_t *cdb = r.cdb;
+	if (which == 0) {		/* spdk_scsi_task_process_null_lun INQUIRY (task.c:263-281) */
+		buf[0] = 0x03 << 5 | 0x1f;
+		buf[4] = 36 - 5;
+		uint32_t alloc_len = be16(&cdb[3]);
+		if (scatter_small(q, r, cnt, len, buf, alloc_len < 36 ? alloc_len : 36, s) >= 0) {
+			s.data_transferred = 36;
+			s.status = SC_GOOD;
+		}
+	} else if (which == 1) {	/* READ CAPACITY (10) (scsi_bdev.c:1729-1749) */
+		uint64_t last = L.num_blocks - 1;
+		uint32_t v = last > 0xffffffffULL ? 0xffffffffu : (uint32_t)last;
+		buf[0] = v >> 24; buf[1] = v >> 16; buf[2] = v >> 8; buf[3] = v;
+		buf[4] = L.block_size >> 24; buf[5] = L.block_size >> 16; buf[6] = L.block_size >> 8; buf[7] = L.block_size;
+		uint32_t l = len < 8 ? len : 8;
+		if (scatter_small(q, r, cnt, len, buf, l, s) >= 0) {
+			s.data_transferred = l;
+			s.status = SC_GOOD;
+		}
+	} else if (which == 2) {	/* READ CAPACITY (16) (scsi_bdev.c:1751-1777) */
+		uint64_t last = L.num_blocks - 1;
+		for (int k = 0; k < 8; k++) buf[k] = (uint8_t)(last >> (56 - 8 * k));
+		buf[8] = L.block_size >> 24; buf[9] = L.block_size >> 16; buf[10] = L.block_size >> 8; buf[11] = L.block_size;
+		buf[14] |= 1 << 7;	/* TPE: UNMAP supported */
+		uint32_t al = be32(&cdb[10]);
+		uint32_t l = al < 32 ? al : 32;
+		if (scatter_small(q, r, cnt, len, buf, l, s) >= 0) {
+			s.data_transferred = l;
+			s.status = SC_GOOD;
+		}
+	} else {			/* REQUEST SENSE (scsi_bdev.c:1997-2026) */
+		if (!(cdb[1] & 0x1)) {
+			buf[0] = 0xf0; buf[7] = 10;
+			uint32_t al = cdb[4];
+			scatter_small(q, r, cnt, len, buf, al < 18 ? al : 18, s);
+			s.data_transferred = al < 18 ? al : 18;
+		}
+		s.status = SC_GOOD;	/* rc >= 0 path overrides whatever status was set (scsi_bdev.c:2066-2069) */
+	}
+}
+
+__device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, LaneState &s)
 {
 	const uint32_t cnt = r.iovcnt;
 	const bool from_dev = (r.dir == OIMGPU_DIR_FROM_DEV) || cnt == 0;
@@ -137,14 +219,16 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 	s.data_transferred = 0; s.units = 0; s.hazard = 0; s.response = OIMGPU_S_OK; s.resp_valid = 1;
 
 	/* ---- task_data_setup (vhost_scsi.c:490-624): walk the SG list ---- */
+	bool valid = true;
 	for (uint32_t j = 0; j < cnt; j++) {
-		if (j >= OIMGPU_IOVS_MAX) { s.valid = 0; break; }
+		if (j >= OIMGPU_IOVS_MAX) { valid = false; break; }
 		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
-		if (v.addr == 0) { s.valid = 0; break; }
+		if (v.addr == 0) { valid = false; break; }
 		len += v.len;
 		if (v.len) { nonzero++; units += units_of(v.len); }
 	}
-	if (!s.valid) {
+	if (!valid) {
+		s.valid = 0;
 		s.used_len = 0;		/* invalid_request(): used element only (vhost_scsi.c:347-358) */
 		s.resp_valid = 0;
 		s.response = 0;
@@ -155,25 +239,15 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 
 	/* ---- spdk_vhost_scsi_task_init_target (vhost_scsi.c:361-387) ---- */
 	const uint16_t lun_id = (uint16_t)((((uint16_t)r.lun[2] << 8) | r.lun[3]) & 0x3FFF);
-	if (r.lun[0] != 1 || r.lun[1] >= OIMGPU_CTRLR_MAX_DEVS || (r.lun[1] != L.target) ) {
+	if (r.lun[0] != 1 || r.lun[1] >= OIMGPU_CTRLR_MAX_DEVS || r.lun[1] != L.target) {
 		s.response = OIMGPU_S_BAD_TARGET;	/* resp->response only; nothing else is written */
 		return;
 	}
-	const bool null_lun = L.removed || lun_id != 0;
 	const uint8_t *cdb = r.cdb;
-
-	if (null_lun) {
+	if (L.removed || lun_id != 0) {
 		/* spdk_scsi_task_process_null_lun (task.c:258-293) */
 		if (cdb[0] == 0x12) {
-			uint8_t *buf = s.scratch;
-			for (int k = 0; k < 36; k++) buf[k] = 0;
-			buf[0] = 0x03 << 5 | 0x1f;
-			buf[4] = 36 - 5;
-			uint32_t alloc_len = be16(&cdb[3]);
-			if (scatter_small(q, r, cnt, len, buf, alloc_len < 36 ? alloc_len : 36, s) >= 0) {
-				s.data_transferred = 36;
-				s.status = SC_GOOD;
-			}
+			scsi_control(L, q, r, cnt, len, s, 0);
 		} else {
 			set_check(s, SK_ILLEGAL_REQUEST, ASC_LUN_NOT_SUPPORTED);
 			s.data_transferred = 0;
@@ -202,36 +276,12 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 	case 0x88: case 0x8a:
 		scsi_readwrite(L, s, dxfer_dir, len, be64(&cdb[2]), be32(&cdb[10]), cdb[0] == 0x88);
 		break;
-	case 0x25: {	/* READ CAPACITY (10) */
-		uint8_t *buf = s.scratch;
-		uint64_t last = L.num_blocks - 1;
-		uint32_t v = last > 0xffffffffULL ? 0xffffffffu : (uint32_t)last;
-		buf[0] = v >> 24; buf[1] = v >> 16; buf[2] = v >> 8; buf[3] = v;
-		buf[4] = L.block_size >> 24; buf[5] = L.block_size >> 16; buf[6] = L.block_size >> 8; buf[7] = L.block_size;
-		uint32_t l = len < 8 ? len : 8;
-		if (scatter_small(q, r, cnt, len, buf, l, s) >= 0) {
-			s.data_transferred = l;
-			s.status = SC_GOOD;
-		}
+	case 0x25:
+		scsi_control(L, q, r, cnt, len, s, 1);
 		break;
-	}
 	case 0x9e:
-		if ((cdb[1] & 0x1f) == 0x10) {	/* READ CAPACITY (16) */
-			uint8_t *buf = s.scratch;
-			for (int k = 0; k < 32; k++) buf[k] = 0;
-			uint64_t last = L.num_blocks - 1;
-			for (int k = 0; k < 8; k++) buf[k] = (uint8_t)(last >> (56 - 8 * k));
-			buf[8] = L.block_size >> 24; buf[9] = L.block_size >> 16; buf[10] = L.block_size >> 8; buf[11] = L.block_size;
-			buf[14] |= 1 << 7;
-			uint32_t al = be32(&cdb[10]);
-			uint32_t l = al < 32 ? al : 32;
-			if (scatter_small(q, r, cnt, len, buf, l, s) >= 0) {
-				s.data_transferred = l;
-				s.status = SC_GOOD;
-			}
-		} else {
-			set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
-		}
+		if ((cdb[1] & 0x1f) == 0x10) scsi_control(L, q, r, cnt, len, s, 2);
+		else set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
 		break;
 	case 0x35: case 0x91: {	/* SYNCHRONIZE CACHE: bounds check only; FLUSH is a no-op on a RAM disk */
 		uint64_t lba; uint32_t n;
@@ -244,19 +294,11 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 		break;
 	}
 	case 0x42:
-		scsi_unmap(L, q, r, cnt, s, nullptr, nullptr, 0);
+		scsi_unmap(L, q, r, cnt, s, nullptr, 0, 0);
 		break;
 	/* ---- spdk_bdev_scsi_process_primary (scsi_bdev.c:1827-2077), table-free commands ---- */
-	case 0x03:	/* REQUEST SENSE */
-		if (!(cdb[1] & 0x1)) {
-			uint8_t *buf = s.scratch;
-			for (int k = 0; k < 18; k++) buf[k] = 0;
-			buf[0] = 0xf0; buf[7] = 10;
-			uint32_t al = cdb[4];
-			scatter_small(q, r, cnt, len, buf, al < 18 ? al : 18, s);
-			s.data_transferred = al < 18 ? al : 18;
-		}
-		s.status = SC_GOOD;	/* rc >= 0 path overrides whatever status was set (scsi_bdev.c:2066-2069) */
+	case 0x03:
+		scsi_control(L, q, r, cnt, len, s, 3);
 		break;
 	case 0x4c: case 0x4d:	/* LOG SELECT / LOG SENSE */
 		set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
@@ -273,25 +315,25 @@ __device__ inline void parse_request(const LunCtx &L, const QueueDesc &q, const 
 	}
 }
 
-/* emit the payload segments of one parsed request into shared memory */
-__device__ inline void emit_segments(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, LaneState &s,
-				     Segment *out, uint32_t first_unit, uint16_t wave)
+/* emit the payload segments of one parsed request into a stage */
+__device__ __forceinline__ void emit_segments(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, LaneState &s,
+					      Segment *out, uint32_t first_unit, uint16_t wave)
 {
 	if (s.op == OP_UNMAP) {
-		uint32_t u = first_unit;
-		scsi_unmap(L, q, r, r.iovcnt, s, out, &u, wave);
+		scsi_unmap(L, q, r, r.iovcnt, s, out, first_unit, wave);
 		return;
 	}
-	if (s.op != OP_READ && s.op != OP_WRITE) return;
 	uint8_t *pos = L.store[0] + s.off;
+	const bool rd = s.op == OP_READ;
 	uint32_t k = 0, u = first_unit;
 	for (uint32_t j = 0; j < r.iovcnt; j++) {
 		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
 		if (v.len == 0) continue;
 		Segment &g = out[k++];
 		uint8_t *client = (uint8_t *)(uintptr_t)v.addr;
-		if (s.op == OP_READ) { g.src = pos; g.dst = client; g.mirror = 0; }
-		else { g.src = client; g.dst = pos; g.mirror = 1; }
+		g.src = rd ? pos : client;
+		g.dst = rd ? client : pos;
+		g.mirror = rd ? 0 : 1;
 		g.len = v.len;
 		g.first_unit = u;
 		g.wave = wave;
@@ -300,57 +342,135 @@ __device__ inline void emit_segments(const LunCtx &L, const QueueDesc &q, const 
 	}
 }
 
+/* completion record of one request (spdk_vhost_scsi_task_cpl, vhost_scsi.c:311-331) into the stage */
+__device__ __forceinline__ void build_cpl(const oimgpu_req &r, const LaneState &s, oimgpu_cpl *out)
+{
+	__align__(16) oimgpu_cpl c;
+	int4 *cz = reinterpret_cast<int4 *>(&c);
+	cz[0] = cz[1] = cz[2] = make_int4(0, 0, 0, 0);
+	c.tag = r.tag;
+	c.used_len = s.used_len;
+	c.resp_valid = s.resp_valid;
+	c.response = s.response;
+	if (s.resp_valid && s.response == OIMGPU_S_OK) {
+		c.status = s.status;
+		if (s.status != SC_GOOD) {
+			c.sense[0] = 0xf0; c.sense[2] = s.sk & 0xf; c.sense[7] = 10;
+			c.sense[12] = s.asc; c.sense[13] = 0;
+			c.sense_len = OIMGPU_SENSE_SIZE;
+		}
+		c.resid = s.length - s.data_transferred;
+		c.data_transferred = s.data_transferred;
+	}
+	int4 *o = reinterpret_cast<int4 *>(out);
+	o[0] = cz[0]; o[1] = cz[1]; o[2] = cz[2];
+}
+
 /* ---- the kernel ----------------------------------------------------------------------------- */
 
+/* parser side: publish the completions of the fill that occupied `st` (all movers are done with it) */
+__device__ __forceinline__ void reap_stage(Stage &st, int lane)
+{
+	const uint32_t n = st.ncpl;
+	for (uint32_t v = lane; v < n * 3; v += 32) {
+		const uint32_t slot = (st.cpl_slot0 + v / 3) & st.cpl_mask;
+		st_cg16(reinterpret_cast<int4 *>(&st.cpl_ring[slot]) + v % 3,
+			reinterpret_cast<const int4 *>(&st.cpl[v / 3])[v % 3]);
+	}
+}
+
 #ifndef OIM_MIN_BLOCKS
-#define OIM_MIN_BLOCKS 2
+#define OIM_MIN_BLOCKS 2	/* 128 registers: the mover loop must stay spill-free (80-register builds lose ~25%) */
 #endif
 __global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
 oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	PassShared &sh = *reinterpret_cast<PassShared *>(smem_raw);
+	CtaShared &sh = *reinterpret_cast<CtaShared *>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const LunCtx &L = *lun;
 
-	for (uint32_t qi = blockIdx.x; qi < nqueues; qi += gridDim.x) {
-		const QueueDesc q = queues[qi];
-		for (uint32_t done = 0; done < q.count; done += kPass) {
-			const uint32_t n = min((uint32_t)kPass, q.count - done);
-			const uint32_t slot0 = q.head + done;
+	if (tid == 0) {
+		for (int s = 0; s < kStages; s++) {
+			mbar_init(&sh.full[s], 1);
+			mbar_init(&sh.empty[s], kMovers);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
 
-			/* 1. stage request slots: n x 64 B as 16-byte vectors */
-			for (uint32_t v = tid; v < n * 4; v += kThreads) {
-				const uint32_t slot = (slot0 + (v >> 2)) & q.ring_mask;
-				reinterpret_cast<int4 *>(&sh.req[v >> 2])[v & 3] =
-					ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
+	if (warp == 0) {
+		/* ======================= PARSER ======================= */
+		const LunCtx &L = *lun;
+		LaneState &s = sh.lane[lane];
+		uint32_t fills = 0;			/* stage fills so far */
+		uint32_t reaped = 0;			/* fills whose completions are published */
+		/* previous pass's store range per lane, for cross-pass hazards */
+		uint64_t prev_lo = 0, prev_hi = 0;
+		uint32_t prev_haz = 0;
+		uint32_t st_rd = 0, st_wr = 0, st_um = 0, st_er = 0;
+		unsigned long long st_rb = 0, st_wb = 0;
+
+		for (uint32_t qi = blockIdx.x; qi < nqueues; qi += gridDim.x) {
+			const QueueDesc q = queues[qi];
+			/* request slots are prefetched one pass ahead: 4 x 16 B per lane, coalesced
+			 * (vector v = k*32+lane of the pass -> request v/4, quarter v%4) */
+			int4 pre[4];
+			if (q.count) {
+				const uint32_t n0 = min((uint32_t)kPass, q.count);
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const uint32_t v = k * 32 + lane;
+					if ((v >> 2) < n0) {
+						const uint32_t slot = (q.head + (v >> 2)) & q.ring_mask;
+						pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
+					}
+				}
 			}
-			__syncthreads();
+			for (uint32_t done = 0; done < q.count; done += kPass) {
+				const uint32_t n = min((uint32_t)kPass, q.count - done);
+				const uint32_t slot0 = q.head + done;
+				__syncwarp();
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const uint32_t v = k * 32 + lane;
+					if ((v >> 2) < n) reinterpret_cast<int4 *>(&sh.req[v >> 2])[v & 3] = pre[k];
+				}
+				__syncwarp();
+				if (done + kPass < q.count) {
+					const uint32_t n1 = min((uint32_t)kPass, q.count - done - kPass);
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const uint32_t v = k * 32 + lane;
+						if ((v >> 2) < n1) {
+							const uint32_t slot = (slot0 + kPass + (v >> 2)) & q.ring_mask;
+							pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
+						}
+					}
+				}
 
-			/* 2. parse + hazards + first round bookkeeping (warp 0) */
-			LaneState &s = sh.lane[lane];	/* meaningful for warp 0 only */
-			uint16_t wave = 0;
-			uint32_t nwaves = 1;
-			if (warp == 0) {
 				const bool active = (uint32_t)lane < n;
 				if (active) parse_request(L, q, sh.req[lane], s);
 				else { s.nseg = 0; s.units = 0; s.hazard = 0; s.op = OP_NONE; s.valid = 0; s.store_lo = s.store_hi = 0; }
+				const uint32_t haz = active ? s.hazard : 0;
+				const uint64_t lo = s.store_lo, hi = s.store_hi;
 
-				/* hazard waves.  Writers are visited in ring order; a writer is pushed behind every
-				 * earlier request it overlaps, every later overlapping request behind the writer. */
-				uint32_t writers = __ballot_sync(0xffffffffu, active && s.hazard >= 2);
-				uint32_t touching = __ballot_sync(0xffffffffu, active && s.hazard != 0);
+				/* hazards inside the pass -> waves.  Writers are visited in ring order; a writer is
+				 * pushed behind every earlier request it overlaps, every later overlapping request
+				 * behind the writer. */
+				uint16_t wave = 0;
+				uint32_t nwaves = 1;
+				const uint32_t writers = __ballot_sync(0xffffffffu, haz >= 2);
+				const uint32_t touching = __ballot_sync(0xffffffffu, haz != 0);
 				if (writers && (touching & (touching - 1))) {
 					uint32_t w = writers;
 					while (w) {
 						const int j = __ffs(w) - 1;
 						w &= w - 1;
-						const uint64_t jlo = __shfl_sync(0xffffffffu, s.store_lo, j);
-						const uint64_t jhi = __shfl_sync(0xffffffffu, s.store_hi, j);
-						const int jhaz = __shfl_sync(0xffffffffu, (int)s.hazard, j);
-						const bool overlap = s.hazard != 0 && lane != j &&
-							(jhaz == 3 || s.hazard == 3 || (s.store_lo < jhi && jlo < s.store_hi));
-						/* earlier overlapping requests decide the writer's wave */
+						const uint64_t jlo = __shfl_sync(0xffffffffu, lo, j);
+						const uint64_t jhi = __shfl_sync(0xffffffffu, hi, j);
+						const uint32_t jhaz = __shfl_sync(0xffffffffu, haz, j);
+						const bool overlap = haz != 0 && lane != j &&
+							(jhaz == 3 || haz == 3 || (lo < jhi && jlo < hi));
 						uint32_t need = (overlap && lane < j) ? (uint32_t)wave + 1 : 0;
 						need = __reduce_max_sync(0xffffffffu, need);
 						if (lane == j && need > wave) wave = (uint16_t)need;
@@ -359,138 +479,184 @@ oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 					}
 					nwaves = __reduce_max_sync(0xffffffffu, (uint32_t)wave) + 1;
 				}
-				if (lane == 0) sh.nwaves = nwaves;
-			}
+				/* hazards against the previous pass, whose movers may still be running */
+				bool drain = false;
+				{
+					const uint32_t pw = __ballot_sync(0xffffffffu, prev_haz >= 2);
+					const uint32_t pt = __ballot_sync(0xffffffffu, prev_haz != 0);
+					uint32_t scan = writers ? pt : pw;	/* only pairs with a writer on one side matter */
+					bool hit = false;
+					if (touching) {
+						while (scan) {
+							const int j = __ffs(scan) - 1;
+							scan &= scan - 1;
+							const uint64_t jlo = __shfl_sync(0xffffffffu, prev_lo, j);
+							const uint64_t jhi = __shfl_sync(0xffffffffu, prev_hi, j);
+							const uint32_t jhaz = __shfl_sync(0xffffffffu, prev_haz, j);
+							if (haz != 0 && (jhaz >= 2 || haz >= 2) &&
+							    (jhaz == 3 || haz == 3 || (lo < jhi && jlo < hi))) hit = true;
+						}
+					}
+					drain = __any_sync(0xffffffffu, hit);
+					prev_lo = lo; prev_hi = hi; prev_haz = haz;
+				}
 
-			/* rounds: as many whole requests as fit in the segment table */
-			uint32_t r0 = 0;
-			while (r0 < n) {
-				if (warp == 0) {
-					/* prefix sums of segment and unit counts over requests r0.. */
+				/* counters for get_bdevs_iostat */
+				const bool ok = active && s.resp_valid && s.response == OIMGPU_S_OK && s.status == SC_GOOD;
+				st_rd += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_READ));
+				st_wr += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_WRITE));
+				st_um += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_UNMAP));
+				st_er += __popc(__ballot_sync(0xffffffffu, active && !ok));
+				if (ok && s.op == OP_READ) st_rb += s.length;
+				if (ok && s.op == OP_WRITE) st_wb += s.length;
+
+				/* rounds: as many whole requests as fit in one stage's segment table */
+				uint32_t r0 = 0;
+				while (r0 < n) {
 					const bool in = (uint32_t)lane >= r0 && (uint32_t)lane < n;
-					uint32_t segs = in ? s.nseg : 0, units = in ? s.units : 0;
+					const uint32_t segs = in ? s.nseg : 0, units = in ? s.units : 0;
 					uint32_t seg_incl = segs, unit_incl = units;
 #pragma unroll
 					for (int o = 1; o < 32; o <<= 1) {
-						uint32_t a = __shfl_up_sync(0xffffffffu, seg_incl, o);
-						uint32_t b = __shfl_up_sync(0xffffffffu, unit_incl, o);
+						const uint32_t a = __shfl_up_sync(0xffffffffu, seg_incl, o);
+						const uint32_t b = __shfl_up_sync(0xffffffffu, unit_incl, o);
 						if (lane >= o) { seg_incl += a; unit_incl += b; }
 					}
 					const uint32_t fits = __ballot_sync(0xffffffffu, in && seg_incl <= (uint32_t)kSegCap);
-					/* lanes r0..r1-1 fit (prefix property: seg_incl is monotonic) */
-					const uint32_t r1 = r0 + __popc(fits);
+					const uint32_t r1 = r0 + __popc(fits);	/* prefix property: seg_incl is monotonic */
 					const bool mine = in && (uint32_t)lane < r1;
-					if (mine && segs) {
-						emit_segments(L, q, sh.req[lane], s, &sh.seg[seg_incl - segs], unit_incl - units, wave);
-					}
-					const uint32_t last = r1 - 1;
-					const uint32_t tot_seg = __shfl_sync(0xffffffffu, seg_incl, last);
-					const uint32_t tot_unit = __shfl_sync(0xffffffffu, unit_incl, last);
-					if (lane == 0) { sh.nseg = tot_seg; sh.nunits = tot_unit; sh.round_reqs = r1 - r0; }
-				}
-				__syncthreads();
 
-				/* 3. move payload */
-				const uint32_t nseg = sh.nseg, nunits = sh.nunits, nw = sh.nwaves;
-				for (uint32_t w = 0; w < nw; w++) {
-					for (uint32_t u = warp; u < nunits; u += kWarps) {
-						uint32_t lo = 0, hi = nseg;	/* last segment with first_unit <= u */
-						while (hi - lo > 1) {
-							const uint32_t mid = (lo + hi) >> 1;
-							if (sh.seg[mid].first_unit <= u) lo = mid; else hi = mid;
-						}
-						const Segment &g = sh.seg[lo];
-						if (nw > 1 && g.wave != w) continue;
-						const uint64_t off = (uint64_t)(u - g.first_unit) * kUnitBytes;
-						const uint32_t nbytes = (uint32_t)min((uint64_t)kUnitBytes, g.len - off);
-						if (g.src) move_unit(g.dst + off, g.src + off, nbytes, lane);
-						else zero_unit(g.dst + off, nbytes, lane);
-						if (g.mirror && L.nreplicas > 1) {
-							/* mirrored bdev: same bytes to every peer replica over NVLink (P2P stores) */
-							const uint64_t soff = (uint64_t)(g.dst - L.store[0]) + off;
-							for (uint32_t rep = 1; rep < L.nreplicas; rep++) {
-								if (g.src) move_unit(L.store[rep] + soff, g.src + off, nbytes, lane);
-								else zero_unit(L.store[rep] + soff, nbytes, lane);
-							}
-						}
+					/* claim the next stage: wait until its previous fill is consumed, publish that
+					 * fill's completions, then refill */
+					const uint32_t sidx = fills % kStages;
+					Stage &st = sh.stage[sidx];
+					if (fills >= kStages) {
+						mbar_wait(&sh.empty[sidx], ((fills / kStages) - 1) & 1);
+						reap_stage(st, lane);
+						reaped++;
+						__syncwarp();
 					}
-					if (nw > 1) __syncthreads();
+					if (mine) {
+						if (segs) emit_segments(L, q, sh.req[lane], s, &st.seg[seg_incl - segs], unit_incl - units, wave);
+						build_cpl(sh.req[lane], s, &st.cpl[lane - r0]);
+					}
+					const uint32_t tot_seg = __shfl_sync(0xffffffffu, seg_incl, r1 - 1);
+					const uint32_t tot_unit = __shfl_sync(0xffffffffu, unit_incl, r1 - 1);
+					if (lane == 0) {
+						st.nseg = tot_seg;
+						st.nunits = tot_unit;
+						st.nwaves = nwaves;
+						st.drain = (drain || r0 > 0) ? 1 : 0;
+						st.stop = 0;
+						st.ncpl = r1 - r0;
+						st.cpl_ring = q.cpls;
+						st.cpl_slot0 = slot0 + r0;
+						st.cpl_mask = q.ring_mask;
+					}
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&sh.full[sidx]);
+					fills++;
+					r0 = r1;
 				}
-				r0 += sh.round_reqs;
-				__syncthreads();
 			}
-
-			/* 4. completion records (spdk_vhost_scsi_task_cpl, vhost_scsi.c:311-331) */
-			if (warp == 0) {
-				if ((uint32_t)lane < n) {
-					__align__(16) oimgpu_cpl c;
-					int4 *cz = reinterpret_cast<int4 *>(&c);
-					cz[0] = cz[1] = cz[2] = make_int4(0, 0, 0, 0);
-					c.tag = sh.req[lane].tag;
-					c.used_len = s.used_len;
-					c.resp_valid = s.resp_valid;
-					c.response = s.response;
-					if (s.resp_valid && s.response == OIMGPU_S_OK) {
-						c.status = s.status;
-						if (s.status != SC_GOOD) {
-							c.sense[0] = 0xf0; c.sense[2] = s.sk & 0xf; c.sense[7] = 10;
-							c.sense[12] = s.asc; c.sense[13] = 0;
-							c.sense_len = OIMGPU_SENSE_SIZE;
-						}
-						c.resid = s.length - s.data_transferred;
-						c.data_transferred = s.data_transferred;
-					}
-					sh.cpl[lane] = c;
-				}
+		}
+		/* tell the movers to stop, then publish the completions still in flight */
+		{
+			const uint32_t sidx = fills % kStages;
+			Stage &st = sh.stage[sidx];
+			if (fills >= kStages) {
+				mbar_wait(&sh.empty[sidx], ((fills / kStages) - 1) & 1);
+				reap_stage(st, lane);
+				reaped++;
 				__syncwarp();
-				for (uint32_t v = lane; v < n * 3; v += 32) {
-					const uint32_t slot = (slot0 + v / 3) & q.ring_mask;
-					st_cg16(reinterpret_cast<int4 *>(&q.cpls[slot]) + v % 3,
-						reinterpret_cast<const int4 *>(&sh.cpl[v / 3])[v % 3]);
-				}
-				/* counters for get_bdevs_iostat: one atomic per counter per pass */
-				const bool ok = (uint32_t)lane < n && s.resp_valid && s.response == OIMGPU_S_OK && s.status == SC_GOOD;
-				const uint32_t rd = __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_READ));
-				const uint32_t wr = __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_WRITE));
-				const uint32_t um = __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_UNMAP));
-				const uint32_t er = __popc(__ballot_sync(0xffffffffu, (uint32_t)lane < n && !ok));
-				uint32_t rb = (ok && s.op == OP_READ) ? s.length : 0;
-				uint32_t wb = (ok && s.op == OP_WRITE) ? s.length : 0;
-				unsigned long long rbt = __reduce_add_sync(0xffffffffu, rb >> 9), wbt = __reduce_add_sync(0xffffffffu, wb >> 9);
-				if (lane == 0) {
-					if (rd) { atomicAdd(&lun->stats[0], rd); atomicAdd(&lun->stats[4], rbt << 9); }
-					if (wr) { atomicAdd(&lun->stats[1], wr); atomicAdd(&lun->stats[5], wbt << 9); }
-					if (um) atomicAdd(&lun->stats[2], um);
-					if (er) atomicAdd(&lun->stats[7], er);
-				}
 			}
-			__syncthreads();
+			if (lane == 0) { st.stop = 1; st.nunits = 0; st.nseg = 0; st.nwaves = 1; st.drain = 0; st.ncpl = 0; }
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&sh.full[sidx]);
+		}
+		while (reaped < fills) {
+			const uint32_t sidx = reaped % kStages;
+			mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
+			reap_stage(sh.stage[sidx], lane);
+			reaped++;
+		}
+		/* flush counters: one atomic per counter per CTA */
+		st_rb = __reduce_add_sync(0xffffffffu, (uint32_t)(st_rb >> 9));
+		st_wb = __reduce_add_sync(0xffffffffu, (uint32_t)(st_wb >> 9));
+		if (lane == 0) {
+			if (st_rd) { atomicAdd(&lun->stats[0], (unsigned long long)st_rd); atomicAdd(&lun->stats[4], st_rb << 9); }
+			if (st_wr) { atomicAdd(&lun->stats[1], (unsigned long long)st_wr); atomicAdd(&lun->stats[5], st_wb << 9); }
+			if (st_um) atomicAdd(&lun->stats[2], (unsigned long long)st_um);
+			if (st_er) atomicAdd(&lun->stats[7], (unsigned long long)st_er);
+		}
+	} else {
+		/* ======================= MOVERS ======================= */
+		const int mw = warp - 1;
+		const uint32_t nrep = lun->nreplicas;
+		for (uint32_t c = 0;; c++) {
+			const uint32_t sidx = c % kStages;
+			Stage &st = sh.stage[sidx];
+			mbar_wait(&sh.full[sidx], (c / kStages) & 1);
+			if (st.stop) break;
+			const uint32_t nseg = st.nseg, nunits = st.nunits, nw = st.nwaves;
+			if (st.drain && c > 0) {
+				/* RAW/WAW/WAR against the previous fill: wait until every mover has left it */
+				const uint32_t p = c - 1;
+				mbar_wait(&sh.empty[p % kStages], (p / kStages) & 1);
+			}
+			for (uint32_t w = 0; w < nw; w++) {
+				for (uint32_t u = mw; u < nunits; u += kMovers) {
+					uint32_t lo = 0, hi = nseg;	/* last segment with first_unit <= u */
+					while (hi - lo > 1) {
+						const uint32_t mid = (lo + hi) >> 1;
+						if (st.seg[mid].first_unit <= u) lo = mid; else hi = mid;
+					}
+					const Segment &g = st.seg[lo];
+					if (nw > 1 && g.wave != w) continue;
+					const uint64_t off = (uint64_t)(u - g.first_unit) * kUnitBytes;
+					const uint32_t nbytes = (uint32_t)min((uint64_t)kUnitBytes, g.len - off);
+					const uint8_t *src = g.src;
+					uint8_t *dst = g.dst;
+					if (src) move_unit(dst + off, src + off, nbytes, lane);
+					else zero_unit(dst + off, nbytes, lane);
+					if (g.mirror && nrep > 1) {
+						/* mirrored bdev: the same bytes go to every peer replica over NVLink (P2P stores) */
+						const uint64_t soff = (uint64_t)(dst - lun->store[0]) + off;
+						for (uint32_t rep = 1; rep < nrep; rep++) {
+							if (src) move_unit(lun->store[rep] + soff, src + off, nbytes, lane);
+							else zero_unit(lun->store[rep] + soff, nbytes, lane);
+						}
+					}
+				}
+				if (nw > 1) movers_barrier();
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&sh.empty[sidx]);
 		}
 	}
 }
 
 /* struct spdk_copy_engine.copy / .fill (S/include/spdk_internal/copy_engine.h:47-53) for
  * device-resident buffers: a plain grid-stride mover built from the same unit routines */
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 oim_copy_kernel(uint8_t *dst, const uint8_t *src, uint64_t nbytes)
 {
 	const int lane = threadIdx.x & 31;
-	const uint64_t warp = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
-	const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+	const uint64_t warp = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+	const uint64_t nwarps = (uint64_t)gridDim.x * 8;
 	const uint64_t nunits = (nbytes + kUnitBytes - 1) / kUnitBytes;
 	for (uint64_t u = warp; u < nunits; u += nwarps) {
 		const uint64_t off = u * kUnitBytes;
 		const uint32_t n = (uint32_t)min((uint64_t)kUnitBytes, nbytes - off);
-		if (src) move_unit(dst + off, src + off, n, lane);
-		else zero_unit(dst + off, n, lane);
+		move_unit(dst + off, src + off, n, lane);
 	}
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes)
 {
-	const uint64_t i0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
-	const uint64_t stride = (uint64_t)gridDim.x * kThreads * 16;
+	const uint64_t i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 16;
+	const uint64_t stride = (uint64_t)gridDim.x * 256 * 16;
 	const uint32_t w = fill * 0x01010101u;
 	const int4 v = make_int4(w, w, w, w);
 	if (((uintptr_t)dst & 15) == 0) {
@@ -498,10 +664,10 @@ oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes)
 		const uint64_t tail = nbytes & ~15ull;
 		if (blockIdx.x == 0 && threadIdx.x < (nbytes & 15)) dst[tail + threadIdx.x] = fill;
 	} else {
-		for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < nbytes; i += (uint64_t)gridDim.x * kThreads) dst[i] = fill;
+		for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < nbytes; i += (uint64_t)gridDim.x * 256) dst[i] = fill;
 	}
 }
 
-size_t lun_kernel_smem_bytes() { return sizeof(PassShared); }
+size_t lun_kernel_smem_bytes() { return sizeof(CtaShared); }
 
 }  // namespace oimgpu

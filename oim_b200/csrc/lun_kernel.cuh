@@ -39,9 +39,16 @@
 namespace oimgpu {
 
 constexpr int kPass = OIMGPU_REQS_PER_PASS;	/* 32 = one warp of parser lanes */
-constexpr int kThreads = 256;			/* CTA size: parser warp + 7 more mover warps */
-constexpr int kWarps = kThreads / 32;
-constexpr int kSegCap = 768;			/* SG segments staged in shared memory per round */
+#ifndef OIM_MOVERS
+#define OIM_MOVERS 7
+#endif
+#ifndef OIM_STAGES
+#define OIM_STAGES 3
+#endif
+constexpr int kMovers = OIM_MOVERS;		/* mover warps per CTA */
+constexpr int kThreads = (1 + kMovers) * 32;	/* parser warp + movers */
+constexpr int kStages = OIM_STAGES;		/* parser -> mover pipeline depth */
+constexpr int kSegCap = 256;			/* SG segments per stage (>= 256 UNMAP descriptors, >= 129 iovecs) */
 constexpr uint32_t kUnitBytes = 4096;		/* bytes one warp moves per step: 8 x 16 B per lane */
 constexpr int kMaxReplicas = 4;
 
@@ -106,17 +113,23 @@ struct LaneState {
 	uint8_t  scratch[40];		/* small control payloads (READ CAPACITY, INQUIRY, REQUEST SENSE) */
 };
 
-struct __align__(16) PassShared {
-	oimgpu_req req[kPass];
-	oimgpu_cpl cpl[kPass];
-	LaneState lane[kPass];
+/* one pipeline stage: what the movers need for (part of) one pass + its completion records */
+struct __align__(16) Stage {
 	Segment seg[kSegCap];
-	uint32_t nseg;
-	uint32_t nunits;
-	uint32_t nwaves;
-	uint32_t wave_first_unit[kPass + 2];
-	uint32_t round_reqs;		/* how many of the pass's requests this round covers */
-	uint32_t scan_tmp[kWarps];
+	oimgpu_cpl cpl[kPass];
+	oimgpu_cpl *cpl_ring;		/* where the records go once the movers are done */
+	uint32_t cpl_slot0, cpl_mask, ncpl;
+	uint32_t nseg, nunits, nwaves;
+	uint32_t drain;			/* conflicts with the previous fill: wait for it to finish */
+	uint32_t stop;
+};
+
+struct __align__(16) CtaShared {
+	Stage stage[kStages];
+	oimgpu_req req[kPass];		/* parser-private: the pass being parsed */
+	LaneState lane[kPass];
+	uint64_t full[kStages];		/* mbarriers */
+	uint64_t empty[kStages];
 };
 
 /* ------------------------------------------------------------------------------------------ */

@@ -923,8 +923,8 @@ extern "C" int oimgpu_copy_submit(oimgpu_lun *L, void *dst, const void *src, uin
 	if (nbytes == 0) return 0;
 	CU_OK(cudaSetDevice(L->device));
 	const uint64_t units = (nbytes + kUnitBytes - 1) / kUnitBytes;
-	const uint32_t grid = (uint32_t)std::min<uint64_t>((units + kWarps - 1) / kWarps, (uint64_t)L->sm_count * 8);
-	oim_copy_kernel<<<grid, kThreads, 0, L->stream>>>((uint8_t *)dst, (const uint8_t *)src, nbytes);
+	const uint32_t grid = (uint32_t)std::min<uint64_t>((units + 7) / 8, (uint64_t)L->sm_count * 8);
+	oim_copy_kernel<<<grid, 256, 0, L->stream>>>((uint8_t *)dst, (const uint8_t *)src, nbytes);
 	CU_OK(cudaGetLastError());
 	L->launches++;
 	return 0;
@@ -935,8 +935,8 @@ extern "C" int oimgpu_fill_submit(oimgpu_lun *L, void *dst, uint8_t fill, uint64
 	if (!L || !dst) return -EINVAL;
 	if (nbytes == 0) return 0;
 	CU_OK(cudaSetDevice(L->device));
-	const uint32_t grid = (uint32_t)std::min<uint64_t>((nbytes / 16 + kThreads - 1) / kThreads + 1, (uint64_t)L->sm_count * 8);
-	oim_fill_kernel<<<grid, kThreads, 0, L->stream>>>((uint8_t *)dst, fill, nbytes);
+	const uint32_t grid = (uint32_t)std::min<uint64_t>((nbytes / 16 + 255) / 256 + 1, (uint64_t)L->sm_count * 8);
+	oim_fill_kernel<<<grid, 256, 0, L->stream>>>((uint8_t *)dst, fill, nbytes);
 	CU_OK(cudaGetLastError());
 	L->launches++;
 	return 0;

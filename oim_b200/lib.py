@@ -17,7 +17,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboimgpu.so")
+LIB_PATH = os.environ.get("OIM_LIB_PATH") or os.path.join(_HERE, "liboimgpu.so")   # override: tuning builds only
 
 
 class OimGpuError(OSError):
