@@ -39,8 +39,11 @@ def parse_args():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--queues", type=int, default=int(os.environ.get("OIM_BENCH_QUEUES", 1184)))
-    p.add_argument("--per-queue", type=int, default=int(os.environ.get("OIM_BENCH_PER_QUEUE", 512)))
+    # 1024 queues x 4096 requests = the 2^22-request C2 trace of SURVEY.md 8(d) per step
+    p.add_argument("--queues", type=int, default=int(os.environ.get("OIM_BENCH_QUEUES", 1024)))
+    p.add_argument("--per-queue", type=int, default=int(os.environ.get("OIM_BENCH_PER_QUEUE", 4096)))
+    p.add_argument("--seq-queues", type=int, default=256)
+    p.add_argument("--seq-per-queue", type=int, default=256)
     p.add_argument("--e2e-queues", type=int, default=256)
     p.add_argument("--e2e-per-queue", type=int, default=512)
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -58,6 +61,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(key: str, requests_per_launch: int):
+    """DRAM bytes per launch from the committed ncu capture, scaled if the launch size differs"""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        return e["dram_bytes_per_launch"] * requests_per_launch / e["requests_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -71,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -223,7 +235,10 @@ def run_ours(args, rank, world, local):
     lib.add_vhost_scsi_lun(f"vhost.{rank}", 0, bname)
     store_ptr = lib.get_bdevs(bname)[0]["device_ptr"]
     nq, per_q = args.queues, args.per_queue
-    lun = lib.Lun(f"vhost.{rank}", 0, num_queues=max(nq, args.e2e_queues), queue_size=1024)
+    # two handles on the same target: the resident legs use caller-owned HBM arrays (tiny rings),
+    # the e2e leg uses the library's host-visible rings
+    lun = lib.Lun(f"vhost.{rank}", 0, num_queues=max(nq, args.seq_queues), queue_size=32)
+    lun_e2e = lib.Lun(f"vhost.{rank}", 0, num_queues=args.e2e_queues, queue_size=1024)
     device_pattern_fill(lun, store_ptr, NUM_BLOCKS * BLOCK, 0xB2000000 + rank, torch)
     timer = lib.Timer()
     out = {}
@@ -279,7 +294,6 @@ def run_ours(args, rank, world, local):
     if rank == 0:
         sampler.start()
     n, ms, launches, _ = resident_leg(8, "randread", "single", nq, per_q, args.steps, args.warmup, check_randread)
-    clocks = sampler.stop() if rank == 0 else {}
     iops = n * args.steps * world / (ms / 1e3)
     per_launch_ms = ms / max(1, launches)
     achieved = 2 * 4096 * n / (per_launch_ms / 1e3) / 1e9
@@ -297,7 +311,7 @@ def run_ours(args, rank, world, local):
         L = lib.load()
 
         def e2e_step():
-            rc = L.oimgpu_submit_and_wait(lun.h, eq, ep, t.reqs.ctypes.data, iovs.ctypes.data, len(iovs),
+            rc = L.oimgpu_submit_and_wait(lun_e2e.h, eq, ep, t.reqs.ctypes.data, iovs.ctypes.data, len(iovs),
                                           cpls.ctypes.data, abi.MEM_HOST)
             assert rc == 0, rc
             return int(cpls["status"].sum())       # device->host read of the step's result
@@ -322,12 +336,14 @@ def run_ours(args, rank, world, local):
     # ---- second metric: 128 KiB sequential write (runs last: it overwrites the patterned store) ----
     seq = None
     if not args.no_seq:
-        sq, sp = max(1, nq // 8), 128
+        sq, sp = args.seq_queues, args.seq_per_queue       # 256 x 256 x 128 KiB = one pass over the 8 GiB device
         n2, ms2, l2, _ = resident_leg(256, "seqwrite", "pages", sq, sp, args.steps, args.warmup, None)
         seq_gbs = n2 * args.steps * world * 131072 / (ms2 / 1e3) / 1e9
         seq = {"metric": "128KiB seq-write GB/s (32 x 4 KiB SG pages)", "value": seq_gbs, "unit": "GB/s",
                "ms_per_step": ms2 / args.steps, "hbm_frac": 2 * seq_gbs / world / peak,
                "requests_per_step": n2, "queues": sq}
+
+    clocks = sampler.stop() if rank == 0 else {}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -335,6 +351,7 @@ def run_ours(args, rank, world, local):
         cpu = {**info, "value": v}
 
     lun.close()
+    lun_e2e.close()
     if rank == 0:
         line = {
             "metric": "4KiB rand-read IOPS", "value": iops, "unit": "IOPS", "n_gpus": world, "steps": args.steps,
@@ -347,7 +364,8 @@ def run_ours(args, rank, world, local):
                              f"({n * 4096 >> 20} MiB) per step"},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic("rand4k", n), "peak_source": peak_src,
+                         "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
             "seq128k": seq, "e2e": e2e, "cpu_baseline": cpu,
         }

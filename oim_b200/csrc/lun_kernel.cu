@@ -14,8 +14,9 @@
  * of pass p+1/p+2 overlap the data movement of pass p.  Request slots of the next pass are
  * prefetched into registers while the current one is parsed.
  *
- * Launch shape: grid = min(#queues, SMs x CTAs/SM) CTAs of (1 + kMovers) x 32 threads; CTA b owns
- * queues b, b+grid, ... and keeps the pipeline running across queue boundaries.
+ * Launch shape: grid = min(#queues, SMs x CTAs/SM) CTAs of (1 + kMovers) x 32 threads; CTA b starts on
+ * queue b, then draws further queues from a shared counter (KickHeader.next, preset to the grid size),
+ * and keeps the pipeline running across queue boundaries.
  */
 #include "lun_kernel.cuh"
 
@@ -383,7 +384,7 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 #define OIM_MIN_BLOCKS 2	/* 128 registers: the mover loop must stay spill-free (80-register builds lose ~25%) */
 #endif
 __global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
-oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
+oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	CtaShared &sh = *reinterpret_cast<CtaShared *>(smem_raw);
@@ -409,8 +410,16 @@ oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues)
 		uint32_t prev_haz = 0;
 		uint32_t st_rd = 0, st_wr = 0, st_um = 0, st_er = 0;
 		unsigned long long st_rb = 0, st_wb = 0;
+		bool first = true;
 
-		for (uint32_t qi = blockIdx.x; qi < nqueues; qi += gridDim.x) {
+		const uint32_t nqueues = hdr->nqueues;
+		for (;;) {
+			/* next queue: first one static (no atomic on the critical path), then work-stealing */
+			uint32_t qi = 0;
+			if (lane == 0) qi = first ? blockIdx.x : atomicAdd(&hdr->next, 1u);
+			qi = __shfl_sync(0xffffffffu, qi, 0);
+			first = false;
+			if (qi >= nqueues) break;
 			const QueueDesc q = queues[qi];
 			/* request slots are prefetched one pass ahead: 4 x 16 B per lane, coalesced
 			 * (vector v = k*32+lane of the pass -> request v/4, quarter v%4) */

@@ -73,6 +73,14 @@ struct LunCtx {
 	unsigned long long stats[8];	/* read ops, write ops, unmap ops, other, bytes r/w/unmapped, errors */
 };
 
+/* per-launch work header: CTAs draw queue indices from `next` so that uneven queue counts and
+ * lengths balance across the grid (copied to the device together with the QueueDesc array) */
+struct KickHeader {
+	uint32_t next;
+	uint32_t nqueues;
+	uint32_t pad[2];
+};
+
 /* one request queue as the kernel sees it for one launch */
 struct QueueDesc {
 	const oimgpu_req *reqs;

@@ -25,7 +25,7 @@
 #include "lun_kernel.cuh"
 
 namespace oimgpu {
-__global__ void oim_lun_queue_kernel(LunCtx *lun, const QueueDesc *queues, uint32_t nqueues);
+__global__ void oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_copy_kernel(uint8_t *dst, const uint8_t *src, uint64_t nbytes);
 __global__ void oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes);
 size_t lun_kernel_smem_bytes();
@@ -117,7 +117,12 @@ struct oimgpu_lun {
 	LunCtx h_ctx{};
 	uint32_t num_queues = 0, queue_size = 0, iov_cap = 0;
 	std::vector<Queue> queues;
-	QueueDesc *h_desc = nullptr;	/* pinned */
+	/* pinned staging ring for {KickHeader, QueueDesc[]}: a slot is reused only after its upload ran */
+	static constexpr int kKickSlots = 4;
+	uint8_t *h_kick[kKickSlots] = {};
+	cudaEvent_t kick_ev[kKickSlots] = {};
+	uint64_t kicks = 0;
+	uint8_t *d_kick = nullptr;
 	QueueDesc *d_desc = nullptr;
 	uint64_t launches = 0;
 	int grid_cap = 0;
@@ -602,8 +607,12 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	CU_OK(cudaMalloc((void **)&L->d_ctx, sizeof(LunCtx)));
 	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, sizeof(LunCtx), cudaMemcpyHostToDevice));
 
-	CU_OK(cudaHostAlloc((void **)&L->h_desc, sizeof(QueueDesc) * num_queues, cudaHostAllocDefault));
-	CU_OK(cudaMalloc((void **)&L->d_desc, sizeof(QueueDesc) * num_queues));
+	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
+		CU_OK(cudaHostAlloc((void **)&L->h_kick[k], sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 2, cudaHostAllocDefault));
+		CU_OK(cudaEventCreateWithFlags(&L->kick_ev[k], cudaEventDisableTiming));
+	}
+	CU_OK(cudaMalloc((void **)&L->d_kick, sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 2));	/* ring + device-array submission per queue */
+	L->d_desc = (QueueDesc *)(L->d_kick + sizeof(KickHeader));
 	L->queues.resize(num_queues);
 	/* one mapped pinned slab per LUN, carved into per-queue rings: the "virtqueues" */
 	const size_t per_q = sizeof(oimgpu_req) * queue_size + sizeof(oimgpu_iov) * L->iov_cap + sizeof(oimgpu_cpl) * queue_size;
@@ -639,8 +648,11 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 	cudaSetDevice(L->device);
 	cudaStreamSynchronize(L->stream);
 	if (!L->queues.empty()) cudaFreeHost(L->queues[0].h_reqs);
-	cudaFreeHost(L->h_desc);
-	cudaFree(L->d_desc);
+	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
+		cudaFreeHost(L->h_kick[k]);
+		cudaEventDestroy(L->kick_ev[k]);
+	}
+	cudaFree(L->d_kick);
 	cudaFree(L->d_ctx);
 	cudaEventDestroy(L->done);
 	cudaStreamDestroy(L->stream);
@@ -726,11 +738,14 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 {
 	if (!L) return -EINVAL;
 	CU_OK(cudaSetDevice(L->device));
+	const int slot = (int)(L->kicks % oimgpu_lun::kKickSlots);
+	if (L->kicks >= (uint64_t)oimgpu_lun::kKickSlots) CU_OK(cudaEventSynchronize(L->kick_ev[slot]));
+	QueueDesc *h_desc = (QueueDesc *)(L->h_kick[slot] + sizeof(KickHeader));
 	uint32_t nd = 0;
 	for (uint32_t q = 0; q < L->num_queues; q++) {
 		Queue &Q = L->queues[q];
 		if (Q.dev_count) {
-			QueueDesc &D = L->h_desc[nd++];
+			QueueDesc &D = h_desc[nd++];
 			D.reqs = Q.dev_reqs;
 			D.iovs = Q.dev_iovs;
 			D.cpls = Q.dev_cpls ? Q.dev_cpls : Q.d_cpls;
@@ -741,7 +756,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 			Q.dev_count = 0;
 		}
 		if (Q.tail != Q.kicked) {
-			QueueDesc &D = L->h_desc[nd++];
+			QueueDesc &D = h_desc[nd++];
 			D.reqs = Q.d_reqs;
 			D.iovs = Q.d_iovs;
 			D.cpls = Q.d_cpls;
@@ -751,16 +766,16 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 			D.count = Q.tail - Q.kicked;
 			Q.kicked = Q.tail;
 		}
-		if (nd > L->num_queues) return -EOVERFLOW;
-		if (nd == L->num_queues && q + 1 < L->num_queues) {
-			/* both a device-array and a ring submission pending on many queues: flush what we have */
-			break;
-		}
 	}
 	if (nd == 0) return 0;
-	CU_OK(cudaMemcpyAsync(L->d_desc, L->h_desc, sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
 	const uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap);
-	oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, L->d_desc, nd);
+	KickHeader *kh = (KickHeader *)L->h_kick[slot];
+	kh->next = grid;	/* queues 0..grid-1 are taken statically by CTA index */
+	kh->nqueues = nd;
+	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
+	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
+	L->kicks++;
+	oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->done, L->stream));
 	L->launches++;
