@@ -108,6 +108,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def shard_plan(rank: int, world: int) -> dict:
+    """LUNs are independent units; LUN i (its bdev, controller, trace seed) lives on
+    rank i = GPU i.  No state is shared between ranks, so there is no data-path collective."""
+    assert 0 <= rank < world
+    return {"bdev": f"Malloc{rank}", "ctrlr": f"vhost.{rank}", "target": 0, "store_seed": 0xB2000000 + rank,
+            "trace_seed": 0xB2000000 + rank, "e2e_seed": 0xE2E00000 + rank}
+
+
+def aggregate(units_per_rank: int, steps: int, world: int, max_ms: float) -> float:
+    """whole-job throughput: units processed by ALL ranks / the slowest rank's device time"""
+    return units_per_rank * steps * world / (max_ms / 1e3)
+
+
 def dist_setup(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -119,48 +132,62 @@ def dist_setup(args):
 # reference arm / cpu_baseline: the reference's own C on the host cores
 # ------------------------------------------------------------------------------------------------
 
-def cpu_leg(seconds: float, io_blocks: int, pattern: str):
+class CpuLeg:
     """Replay the workload through oracle/_ref (the compiled reference) or, where that did not
     travel, the C restatement.  One thread: SPDK polls one vhost controller - hence one LUN - on
-    one reactor core (S/lib/vhost/vhost_scsi.c:1314-1318).  Returns (iops, info)."""
-    from oracle import bindings
-    try:
-        bindings.build()
-    except Exception:
-        pass
-    cls, kind = (bindings.RefOracle, "reference") if bindings.ref_available() else (bindings.PortOracle, "port")
-    o = cls(NUM_BLOCKS, BLOCK)
-    io_bytes = io_blocks * BLOCK
-    chunk = (1 << 18) if io_blocks <= 8 else (1 << 13)
-    t = traces.uniform_trace(chunk, NUM_BLOCKS, io_blocks=io_blocks, pattern=pattern, seed=0xB2000000)
-    arena = np.zeros(t.arena_bytes, dtype=np.uint8)
-    if "write" in pattern:
-        arena[:] = traces.pattern_bytes(0xC3, 0, arena.size)
-    iovs = t.bind(arena.ctypes.data)
-    o.submit(t.reqs[:4096], iovs)                       # warm-up pass
-    done, t0, busy = 0, time.perf_counter(), 0.0
-    while time.perf_counter() - t0 < seconds:
-        a = time.perf_counter()
-        o.submit(t.reqs, iovs)
-        busy += time.perf_counter() - a
-        done += chunk
-    o.close()
-    iops = done / busy
-    return iops, {"kind": kind, "cores": 1, "unit": "IOPS",
-                  "sample": f"{done} x {io_bytes} B {pattern} requests over the 8 GiB bdev in {busy:.1f} s, "
-                            f"{chunk}-request trace replayed; client buffers {arena.size >> 20} MiB host memory; "
-                            f"1 reactor thread (SPDK: one core per vhost controller)"}
+    one reactor core (S/lib/vhost/vhost_scsi.c:1314-1318)."""
+
+    def __init__(self, io_blocks: int = 8, pattern: str = "randread"):
+        from oracle import bindings
+        try:
+            bindings.build()
+        except Exception:  # noqa: BLE001  (prebuilt libraries may be all there is on the GPU box)
+            pass
+        cls, self.kind = ((bindings.RefOracle, "reference") if bindings.ref_available()
+                          else (bindings.PortOracle, "port"))
+        self.o = cls(NUM_BLOCKS, BLOCK)
+        self.io_bytes, self.pattern = io_blocks * BLOCK, pattern
+        self.chunk = (1 << 18) if io_blocks <= 8 else (1 << 13)
+        self.t = traces.uniform_trace(self.chunk, NUM_BLOCKS, io_blocks=io_blocks, pattern=pattern, seed=0xB2000000)
+        self.arena = np.zeros(self.t.arena_bytes, dtype=np.uint8)
+        if "write" in pattern:
+            self.arena[:] = traces.pattern_bytes(0xC3, 0, self.arena.size)
+        self.iovs = self.t.bind(self.arena.ctypes.data)
+        self.o.submit(self.t.reqs[:4096], self.iovs)                       # warm-up pass
+
+    def run(self, seconds: float):
+        """-> (iops, info): IOPS over the time spent inside the reference's poller
+        (process_requestq + completion polling), not this harness's descriptor building"""
+        done, t0, wall = 0, time.perf_counter(), 0.0
+        self.o.busy_ns(reset=True)
+        while time.perf_counter() - t0 < seconds:
+            a = time.perf_counter()
+            self.o.submit(self.t.reqs, self.iovs)
+            wall += time.perf_counter() - a
+            done += self.chunk
+        busy = self.o.busy_ns(reset=True) / 1e9 or wall
+        return done / busy, {
+            "kind": self.kind, "cores": 1, "unit": "IOPS",
+            "sample": f"{done} x {self.io_bytes} B {self.pattern} requests over the 8 GiB bdev, {busy:.1f} s inside the "
+                      f"reference's poller ({wall:.1f} s incl. the harness building vring descriptors); "
+                      f"{self.chunk}-request trace replayed; client buffers {self.arena.size >> 20} MiB host memory; "
+                      f"1 reactor thread (SPDK: one core per vhost controller)"}
+
+    def close(self):
+        self.o.close()
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = max(0.5, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
+    leg = CpuLeg(8, "randread")
     vals = []
     for i in range(args.warmup + args.steps):
-        iops, info = cpu_leg(per_step, 8, "randread")
+        iops, info = leg.run(per_step)
         if i >= args.warmup:
             vals.append(iops)
+    leg.close()
     v = statistics.mean(vals)
     line = {"impl": "reference", "metric": "4KiB rand-read IOPS", "value": v, "unit": "IOPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
@@ -230,22 +257,23 @@ def run_ours(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    bname = lib.construct_malloc_bdev(NUM_BLOCKS, BLOCK, name=f"Malloc{rank}", device=local)
-    lib.construct_vhost_scsi_controller(f"vhost.{rank}")
-    lib.add_vhost_scsi_lun(f"vhost.{rank}", 0, bname)
+    plan = shard_plan(rank, world)
+    bname = lib.construct_malloc_bdev(NUM_BLOCKS, BLOCK, name=plan["bdev"], device=local)
+    lib.construct_vhost_scsi_controller(plan["ctrlr"])
+    lib.add_vhost_scsi_lun(plan["ctrlr"], plan["target"], bname)
     store_ptr = lib.get_bdevs(bname)[0]["device_ptr"]
     nq, per_q = args.queues, args.per_queue
     # two handles on the same target: the resident legs use caller-owned HBM arrays (tiny rings),
     # the e2e leg uses the library's host-visible rings
-    lun = lib.Lun(f"vhost.{rank}", 0, num_queues=max(nq, args.seq_queues), queue_size=32)
-    lun_e2e = lib.Lun(f"vhost.{rank}", 0, num_queues=args.e2e_queues, queue_size=1024)
-    device_pattern_fill(lun, store_ptr, NUM_BLOCKS * BLOCK, 0xB2000000 + rank, torch)
+    lun = lib.Lun(plan["ctrlr"], plan["target"], num_queues=max(nq, args.seq_queues), queue_size=32)
+    lun_e2e = lib.Lun(plan["ctrlr"], plan["target"], num_queues=args.e2e_queues, queue_size=1024)
+    device_pattern_fill(lun, store_ptr, NUM_BLOCKS * BLOCK, plan["store_seed"], torch)
     timer = lib.Timer()
     out = {}
 
     def resident_leg(io_blocks, pattern, sg, nq, per_q, steps, warmup, check):
         n = nq * per_q
-        t = traces.uniform_trace(n, NUM_BLOCKS, io_blocks=io_blocks, pattern=pattern, sg=sg, seed=0xB2000000 + rank)
+        t = traces.uniform_trace(n, NUM_BLOCKS, io_blocks=io_blocks, pattern=pattern, sg=sg, seed=plan["trace_seed"])
         arena = torch.empty(t.arena_bytes, dtype=torch.uint8, device="cuda")
         if "write" in pattern:
             arena.view(torch.int64)[:] = 0x0123456789ABCDEF
@@ -287,14 +315,14 @@ def run_ours(args, rank, world, local):
         for i in rng.integers(0, len(t.reqs), 256):
             lba = int.from_bytes(bytes(t.reqs["cdb"][i][2:6]), "big")
             got = arena[i * 4096:(i + 1) * 4096].cpu().numpy()
-            want = traces.pattern_bytes(0xB2000000 + rank, lba * BLOCK, 4096)
+            want = traces.pattern_bytes(plan["store_seed"], lba * BLOCK, 4096)
             assert (got == want).all(), f"request {i} lba {lba}: payload differs from the store pattern"
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n, ms, launches, _ = resident_leg(8, "randread", "single", nq, per_q, args.steps, args.warmup, check_randread)
-    iops = n * args.steps * world / (ms / 1e3)
+    iops = aggregate(n, args.steps, world, ms)
     per_launch_ms = ms / max(1, launches)
     achieved = 2 * 4096 * n / (per_launch_ms / 1e3) / 1e9
     out["rand4k"] = (iops, ms / args.steps, launches)
@@ -304,7 +332,7 @@ def run_ours(args, rank, world, local):
     if not args.no_e2e:
         eq, ep = args.e2e_queues, args.e2e_per_queue
         en = eq * ep
-        t = traces.uniform_trace(en, NUM_BLOCKS, io_blocks=8, pattern="randread", seed=0xE2E00000 + rank)
+        t = traces.uniform_trace(en, NUM_BLOCKS, io_blocks=8, pattern="randread", seed=plan["e2e_seed"])
         host = torch.empty(t.arena_bytes, dtype=torch.uint8).pin_memory()
         iovs = t.bind(host.data_ptr())
         cpls = np.zeros(en, dtype=abi.cpl_dtype)
@@ -325,7 +353,7 @@ def run_ours(args, rank, world, local):
         wall = max_over_ranks(time.perf_counter() - t0)
         got = host[:4096].numpy()
         lba0 = int.from_bytes(bytes(t.reqs["cdb"][0][2:6]), "big")
-        assert (got == traces.pattern_bytes(0xB2000000 + rank, lba0 * BLOCK, 4096)).all()
+        assert (got == traces.pattern_bytes(plan["store_seed"], lba0 * BLOCK, 4096)).all()
         e2e = {"value": en * args.steps * world / wall, "unit": "IOPS",
                "h2d_bytes_per_step": int(en * 64 + len(iovs) * 16),
                "d2h_bytes_per_step": int(en * 4096 + en * 48),
@@ -347,7 +375,9 @@ def run_ours(args, rank, world, local):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, info = cpu_leg(args.cpu_seconds, 8, "randread")
+        leg = CpuLeg(8, "randread")
+        v, info = leg.run(args.cpu_seconds)
+        leg.close()
         cpu = {**info, "value": v}
 
     lun.close()

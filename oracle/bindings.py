@@ -53,6 +53,9 @@ class _Oracle:
         self._submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         self._set_removed = getattr(self.lib, p + "_set_removed")
         self._set_removed.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self._busy = getattr(self.lib, p + "_busy_ns")
+        self._busy.restype = C.c_uint64
+        self._busy.argtypes = [C.c_void_p, C.c_int]
         self.h = self._create(num_blocks, block_size, target)
         if not self.h:
             raise RuntimeError(f"{p}_create failed")
@@ -71,6 +74,10 @@ class _Oracle:
         if rc != 0:
             raise RuntimeError(f"{self.prefix}_submit rc={rc}")
         return cpls
+
+    def busy_ns(self, reset: bool = True) -> int:
+        """ns spent inside the checker's own request processing (0 = not instrumented: time the call)"""
+        return int(self._busy(self.h, int(reset)))
 
     def set_removed(self, target: int, removed: bool = True) -> None:
         self._set_removed(self.h, target, int(removed))

@@ -631,6 +631,8 @@ int oimorc_desc_to_iov(const uint64_t *regions, uint32_t nregions, uint64_t addr
 	return (int)(idx - start_index);
 }
 
+uint64_t oimorc_busy_ns(void *h, int reset) { (void)h; (void)reset; return 0; }	/* caller times the call */
+
 const char *oimorc_describe(void)
 {
 	return "port: plain-C restatement of SPDK v19.04-pre vhost-scsi/scsi/bdev/malloc path (oracle/oim_oracle.c)";

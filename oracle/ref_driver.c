@@ -88,6 +88,7 @@ struct oimref {
 	struct virtio_scsi_cmd_resp	*resp_bufs;	/* [OIMGPU_REQS_PER_PASS] */
 	struct vring_desc		*indirect;	/* [OIMGPU_REQS_PER_PASS][REF_INDIRECT_MAX] */
 	uint16_t			used_seen;
+	uint64_t			poller_ns;	/* time spent inside the reference's poller only */
 	int				eventfd;
 	struct oimref			*next_on_thread;
 };
@@ -308,6 +309,7 @@ int oimref_submit(void *h, const struct oimgpu_req *reqs, uint32_t nreqs,
 {
 	struct oimref *r = h;
 	uint32_t done = 0;
+	struct timespec t0, t1;
 
 	(void)niovs;
 	spdk_set_thread(g_thread);
@@ -327,6 +329,7 @@ int oimref_submit(void *h, const struct oimgpu_req *reqs, uint32_t nreqs,
 		__sync_synchronize();
 		r->avail->idx = avail_idx + batch;
 
+		clock_gettime(CLOCK_MONOTONIC, &t0);
 		process_requestq(r->svsession, r->vq);
 		/* The Malloc module copies inline, but bdev.c defers the completion callback of an I/O
 		 * that finished inside submit_request to the next thread poll (bdev.c:3213-3229), so
@@ -336,6 +339,8 @@ int oimref_submit(void *h, const struct oimgpu_req *reqs, uint32_t nreqs,
 			spdk_thread_poll(g_thread, 0, 0);
 		}
 		spdk_vhost_vq_used_signal(&r->svsession->vsession, r->vq);
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		r->poller_ns += (uint64_t)(t1.tv_sec - t0.tv_sec) * 1000000000ull + (uint64_t)(t1.tv_nsec - t0.tv_nsec);
 
 		if ((uint16_t)(r->used->idx - r->used_seen) != batch) return -EIO;
 		for (i = 0; i < batch; i++) {
@@ -393,6 +398,16 @@ int oimref_desc_to_iov(const uint64_t *regions, uint32_t nregions, uint64_t addr
 		out[i - start_index].flags = 0;
 	}
 	return idx - start_index;
+}
+
+/* nanoseconds spent in process_requestq() + completion polling + used_signal since the last reset:
+ * the reference's own work, without this driver's descriptor-chain building (which a guest does) */
+uint64_t oimref_busy_ns(void *h, int reset)
+{
+	struct oimref *r = h;
+	uint64_t v = r->poller_ns;
+	if (reset) r->poller_ns = 0;
+	return v;
 }
 
 const char *oimref_describe(void)
