@@ -249,6 +249,23 @@ int oimgpu_lun_iostat(oimgpu_lun *lun, struct oimgpu_iostat *out);
 /* raw CUDA stream handle (cudaStream_t) of the LUN, for callers that time with CUDA events */
 void *oimgpu_lun_stream(oimgpu_lun *lun);
 
+/* ---- virtqueue mode: hand the guest's own virtio split rings to the GPU ---------------------
+ * Replaces spdk_vhost_vq_avail_ring_get / spdk_vhost_vq_get_desc / spdk_vhost_vring_desc_to_iov /
+ * task_data_setup / spdk_vhost_vq_used_ring_enqueue (S/lib/vhost/vhost.c:178-247,397-509,
+ * S/lib/vhost/vhost_scsi.c:490-624): the kernel walks descriptor chains (direct and INDIRECT),
+ * translates guest-physical addresses through the memory table, and writes the response buffers and
+ * the used ring itself. */
+struct oimgpu_mem_region {		/* struct rte_vhost_mem_region, S/lib/vhost/rte_vhost/rte_vhost.h:52-60 */
+	uint64_t guest_phys_addr;
+	uint64_t size;
+	uint64_t addr;			/* device-accessible address the range is mapped at */
+};
+int oimgpu_lun_set_mem_table(oimgpu_lun *lun, const struct oimgpu_mem_region *regions, uint32_t nregions);
+int oimgpu_vq_attach(oimgpu_lun *lun, uint32_t q, const void *desc, const void *avail, void *used,
+		     uint32_t size, uint16_t last_avail_idx, uint16_t last_used_idx);
+int oimgpu_vq_detach(oimgpu_lun *lun, uint32_t q, uint16_t *last_avail_idx, uint16_t *last_used_idx);
+int oimgpu_vq_kick(oimgpu_lun *lun);	/* process every attached ring up to its avail->idx; asynchronous */
+
 /* Session-visible hot-remove state of the target (S/lib/vhost/vhost_scsi.c:1093-1100: `removed`;
  * S/lib/scsi/lun.c:171-176: `lun_removed`). */
 int oimgpu_lun_set_removed(oimgpu_lun *lun, int removed, int lun_removed);

@@ -367,16 +367,203 @@ __device__ __forceinline__ void build_cpl(const oimgpu_req &r, const LaneState &
 	o[0] = cz[0]; o[1] = cz[1]; o[2] = cz[2];
 }
 
+/* ---- virtqueue mode: the split-ring walk of the reference's poller on one parser lane ---------- */
+
+__device__ __forceinline__ uint16_t ld_vol16(const void *p)
+{
+	uint16_t r;
+	asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+	return r;
+}
+
+/* rte_vhost_gpa_to_vva (rte_vhost.h:133-150): first region containing gpa, no length check */
+__device__ __forceinline__ uint64_t gpa_to_dev(const LunCtx &L, uint64_t gpa)
+{
+	for (uint32_t i = 0; i < L.nregions; i++) {
+		if (gpa >= L.region[i].gpa && gpa < L.region[i].gpa + L.region[i].size) return gpa - L.region[i].gpa + L.region[i].addr;
+	}
+	return 0;
+}
+
+/* spdk_vhost_gpa_to_vva (vhost.c:93-106): the whole [gpa, gpa+len) must lie inside one region */
+__device__ __forceinline__ uint64_t gpa_to_dev_len(const LunCtx &L, uint64_t gpa, uint64_t len)
+{
+	for (uint32_t i = 0; i < L.nregions; i++) {
+		if (gpa >= L.region[i].gpa && gpa < L.region[i].gpa + L.region[i].size) {
+			if (len > L.region[i].gpa + L.region[i].size - gpa) return 0;
+			return gpa - L.region[i].gpa + L.region[i].addr;
+		}
+	}
+	return 0;
+}
+
+struct VDesc { uint64_t addr; uint32_t len; uint16_t flags, next; };	/* struct vring_desc */
+enum : uint16_t { VD_NEXT = 1, VD_WRITE = 2, VD_INDIRECT = 4 };
+
+__device__ __forceinline__ VDesc load_desc(const uint8_t *p)
+{
+	VDesc d;
+	if (((uintptr_t)p & 15) == 0) {
+		const int4 v = ld_cg16(p);
+		d.addr = (uint64_t)(uint32_t)v.x | (uint64_t)(uint32_t)v.y << 32;
+		d.len = (uint32_t)v.z;
+		d.flags = (uint16_t)((uint32_t)v.w & 0xffff);
+		d.next = (uint16_t)((uint32_t)v.w >> 16);
+	} else {
+		uint64_t a = 0; uint32_t l = 0, w = 0;
+		for (int k = 7; k >= 0; k--) a = a << 8 | ld_cg8(p + k);
+		for (int k = 11; k >= 8; k--) l = l << 8 | ld_cg8(p + k);
+		for (int k = 15; k >= 12; k--) w = w << 8 | ld_cg8(p + k);
+		d.addr = a; d.len = l; d.flags = (uint16_t)(w & 0xffff); d.next = (uint16_t)(w >> 16);
+	}
+	return d;
+}
+
+/* spdk_vhost_vring_desc_get_next (vhost.c:433-453): 0 = ok (have == false: end of chain), -1 = bad index */
+__device__ __forceinline__ int desc_get_next(VDesc &d, bool &have, const uint8_t *table, uint32_t table_size)
+{
+	if ((d.flags & VD_NEXT) == 0) { have = false; return 0; }
+	if (d.next >= table_size) { have = false; return -1; }
+	d = load_desc(table + (size_t)d.next * 16);
+	return 0;
+}
+
+/* spdk_vhost_vring_desc_to_iov (vhost.c:461-509): append the iovecs of one descriptor to the lane's
+ * scratch SG row; split only where two sides of a 2 MiB boundary are not contiguous in device VA */
+__device__ __forceinline__ int desc_to_iov(const LunCtx &L, oimgpu_iov *row, uint32_t &iov_index, const VDesc &d)
+{
+	const uint64_t MB2 = 2ull << 20;
+	uint32_t remaining = d.len;
+	uint64_t payload = d.addr;
+	do {
+		if (iov_index >= OIMGPU_IOVS_MAX) return -1;
+		const uint64_t vva = gpa_to_dev(L, payload);
+		if (vva == 0) return -1;
+		const uint32_t to_boundary = (uint32_t)(MB2 - (payload & (MB2 - 1)));
+		uint32_t len;
+		if (remaining <= to_boundary) {
+			len = remaining;
+		} else {
+			len = to_boundary;
+			while (len < remaining) {
+				if (vva + len != gpa_to_dev(L, payload + len)) break;
+				len += (remaining - len) < MB2 ? (remaining - len) : (uint32_t)MB2;
+			}
+		}
+		oimgpu_iov v;
+		v.addr = vva; v.len = len; v.flags = 0;
+		row[iov_index] = v;
+		remaining -= len;
+		payload += len;
+		iov_index++;
+	} while (remaining);
+	return 0;
+}
+
+/* task_data_setup (vhost_scsi.c:490-624) for the chain starting at ring index `head`.  Fills the
+ * request slot `r` (virtio header + direction + SG row reference) and *resp (device address of the
+ * guest's response buffer).  Returns false for every `goto invalid_task`. */
+__device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc &q, uint32_t head, oimgpu_req &r,
+						oimgpu_iov *row, uint32_t row_index, uint64_t *resp)
+{
+	*resp = 0;
+	/* spdk_vhost_vq_get_desc (vhost.c:219-247) */
+	if (head >= q.vq_size) return false;
+	const uint8_t *table = q.vq_desc;
+	uint32_t table_size = q.vq_size;
+	VDesc d = load_desc(table + (size_t)head * 16);
+	if (d.flags & VD_INDIRECT) {
+		table_size = d.len / 16;
+		table = (const uint8_t *)(uintptr_t)gpa_to_dev_len(L, d.addr, 16ull * table_size);
+		if (table == nullptr) return false;
+		d = load_desc(table);
+	}
+	/* first descriptor: readable, holds a whole virtio_scsi_cmd_req */
+	if ((d.flags & VD_WRITE) || d.len < 51) return false;
+	const uint8_t *req = (const uint8_t *)(uintptr_t)gpa_to_dev_len(L, d.addr, 51);
+	if (req == nullptr) return false;
+	uint8_t *rb = reinterpret_cast<uint8_t *>(&r);
+	if (((uintptr_t)req & 3) == 0) {
+		for (int k = 0; k < 12; k++) reinterpret_cast<uint32_t *>(rb)[k] = ld_cg32(req + 4 * k);
+		for (int k = 48; k < 51; k++) rb[k] = ld_cg8(req + k);
+	} else {
+		for (int k = 0; k < 51; k++) rb[k] = ld_cg8(req + k);
+	}
+	bool have = true;
+	desc_get_next(d, have, table, table_size);
+	if (!have) return false;	/* neither payload nor response buffer */
+	const bool from_dev = (d.flags & VD_WRITE) != 0;
+	uint32_t iovcnt = 0;
+	if (from_dev) {
+		/* FROM_DEV: [RD_req][WR_resp][WR_buf0]...[WR_bufN] */
+		*resp = gpa_to_dev_len(L, d.addr, OIMGPU_RESP_SIZE);
+		if (d.len < OIMGPU_RESP_SIZE || *resp == 0) return false;
+		if (desc_get_next(d, have, table, table_size) != 0) return false;
+		while (have) {
+			if (!(d.flags & VD_WRITE)) return false;
+			if (desc_to_iov(L, row, iovcnt, d)) return false;
+			if (desc_get_next(d, have, table, table_size) != 0) return false;
+		}
+	} else {
+		/* TO_DEV: [RD_req][RD_buf0]...[RD_bufN][WR_resp] */
+		while (!(d.flags & VD_WRITE)) {
+			if (desc_to_iov(L, row, iovcnt, d)) return false;
+			desc_get_next(d, have, table, table_size);
+			if (!have) return false;	/* no response descriptor */
+		}
+		*resp = gpa_to_dev_len(L, d.addr, OIMGPU_RESP_SIZE);
+		if (d.len < OIMGPU_RESP_SIZE || *resp == 0) return false;
+	}
+	r.dir = from_dev ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV;
+	r.iovcnt = (uint16_t)iovcnt;	/* 0 with from_dev == the reference's "no payload" task (iovcnt 1, len 0) */
+	r.flags = 0;
+	r.iov_start = row_index;
+	r.reserved = 0;
+	return true;
+}
+
 /* ---- the kernel ----------------------------------------------------------------------------- */
 
 /* parser side: publish the completions of the fill that occupied `st` (all movers are done with it) */
 __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 {
 	const uint32_t n = st.ncpl;
-	for (uint32_t v = lane; v < n * 3; v += 32) {
-		const uint32_t slot = (st.cpl_slot0 + v / 3) & st.cpl_mask;
-		st_cg16(reinterpret_cast<int4 *>(&st.cpl_ring[slot]) + v % 3,
-			reinterpret_cast<const int4 *>(&st.cpl[v / 3])[v % 3]);
+	if (st.mode == QMODE_SLOTS) {
+		for (uint32_t v = lane; v < n * 3; v += 32) {
+			const uint32_t slot = (st.cpl_slot0 + v / 3) & st.cpl_mask;
+			st_cg16(reinterpret_cast<int4 *>(&st.cpl_ring[slot]) + v % 3,
+				reinterpret_cast<const int4 *>(&st.cpl[v / 3])[v % 3]);
+		}
+		return;
+	}
+	/* virtqueue mode: spdk_vhost_scsi_task_cpl writes into the guest's response buffer
+	 * (vhost_scsi.c:311-331), then spdk_vhost_vq_used_ring_enqueue publishes {id, len} (vhost.c:397-431) */
+	if ((uint32_t)lane < n) {
+		const oimgpu_cpl &c = st.cpl[lane];
+		uint8_t *resp = (uint8_t *)(uintptr_t)st.resp[lane];
+		if (c.resp_valid && resp) {
+			resp[11] = c.response;
+			if (c.response == OIMGPU_S_OK) {
+				resp[10] = c.status;
+				if (c.status != SC_GOOD) {
+					for (int k = 0; k < OIMGPU_SENSE_SIZE; k++) resp[12 + k] = c.sense[k];
+					resp[0] = (uint8_t)c.sense_len; resp[1] = 0; resp[2] = 0; resp[3] = 0;
+				}
+				resp[4] = (uint8_t)c.resid; resp[5] = (uint8_t)(c.resid >> 8);
+				resp[6] = (uint8_t)(c.resid >> 16); resp[7] = (uint8_t)(c.resid >> 24);
+			}
+		}
+		const uint32_t slot = (st.used_base + lane) & (st.vq_size - 1);
+		uint32_t *ue = reinterpret_cast<uint32_t *>(st.vq_used + 4 + 8 * (size_t)slot);
+		ue[0] = st.vq_head[lane];
+		ue[1] = c.used_len;
+	}
+	__threadfence_system();		/* "Ensure the used ring is updated before we ... increment used->idx" */
+	__syncwarp();
+	if (lane == 0 && n) {
+		const uint32_t idx = st.used_base + n;
+		*reinterpret_cast<volatile uint16_t *>(st.vq_used + 2) = (uint16_t)idx;
+		st.vq_state->last_used = idx & 0xffff;
 	}
 }
 
@@ -420,11 +607,28 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 			qi = __shfl_sync(0xffffffffu, qi, 0);
 			first = false;
 			if (qi >= nqueues) break;
-			const QueueDesc q = queues[qi];
+			QueueDesc q = queues[qi];
+			uint32_t vq_last_avail = 0, vq_last_used = 0;
+			if (q.mode == QMODE_VRING) {
+				/* spdk_vhost_vq_avail_ring_get (vhost.c:178-211): everything up to avail->idx */
+				uint32_t cnt = 0;
+				if (lane == 0) {
+					vq_last_avail = q.vq_state->last_avail;
+					vq_last_used = q.vq_state->last_used;
+					cnt = (uint16_t)(ld_vol16(q.vq_avail + 2) - (uint16_t)vq_last_avail);
+					if (cnt > q.vq_size) cnt = 0;	/* "the queue is unrecoverably broken" */
+				}
+				q.count = __shfl_sync(0xffffffffu, cnt, 0);
+				vq_last_avail = __shfl_sync(0xffffffffu, vq_last_avail, 0);
+				vq_last_used = __shfl_sync(0xffffffffu, vq_last_used, 0);
+				q.head = vq_last_avail;
+				q.iov_mask = 0xffffffffu;
+				q.iovs += (size_t)blockIdx.x * kPass * kIovRow;	/* this CTA's scratch SG rows */
+			}
 			/* request slots are prefetched one pass ahead: 4 x 16 B per lane, coalesced
 			 * (vector v = k*32+lane of the pass -> request v/4, quarter v%4) */
 			int4 pre[4];
-			if (q.count) {
+			if (q.count && q.mode == QMODE_SLOTS) {
 				const uint32_t n0 = min((uint32_t)kPass, q.count);
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
@@ -439,13 +643,15 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 				const uint32_t n = min((uint32_t)kPass, q.count - done);
 				const uint32_t slot0 = q.head + done;
 				__syncwarp();
+				if (q.mode == QMODE_SLOTS) {
 #pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const uint32_t v = k * 32 + lane;
-					if ((v >> 2) < n) reinterpret_cast<int4 *>(&sh.req[v >> 2])[v & 3] = pre[k];
+					for (int k = 0; k < 4; k++) {
+						const uint32_t v = k * 32 + lane;
+						if ((v >> 2) < n) reinterpret_cast<int4 *>(&sh.req[v >> 2])[v & 3] = pre[k];
+					}
 				}
 				__syncwarp();
-				if (done + kPass < q.count) {
+				if (q.mode == QMODE_SLOTS && done + kPass < q.count) {
 					const uint32_t n1 = min((uint32_t)kPass, q.count - done - kPass);
 #pragma unroll
 					for (int k = 0; k < 4; k++) {
@@ -458,7 +664,22 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 				}
 
 				const bool active = (uint32_t)lane < n;
-				if (active) parse_request(L, q, sh.req[lane], s);
+				uint64_t my_resp = 0;
+				uint32_t my_head = 0;
+				bool chain_ok = true;
+				if (q.mode == QMODE_VRING && active) {
+					my_head = reinterpret_cast<const uint16_t *>(q.vq_avail + 4)[(slot0 + lane) & (q.vq_size - 1)];
+					chain_ok = vq_task_data_setup(L, q, my_head, sh.req[lane], const_cast<oimgpu_iov *>(q.iovs) + (size_t)lane * kIovRow,
+								      lane * kIovRow, &my_resp);
+				}
+				if (active && chain_ok) parse_request(L, q, sh.req[lane], s);
+				else if (active) {
+					/* invalid_request(): used element of length 0, response untouched (vhost_scsi.c:347-358) */
+					s.op = OP_NONE; s.nseg = 0; s.units = 0; s.hazard = 0; s.valid = 0; s.store_lo = s.store_hi = 0;
+					s.length = 0; s.data_transferred = 0; s.used_len = 0; s.resp_valid = 0; s.response = 0;
+					s.status = SC_GOOD; s.sk = 0; s.asc = 0;
+					sh.req[lane].tag = 0; sh.req[lane].iovcnt = 0;
+				}
 				else { s.nseg = 0; s.units = 0; s.hazard = 0; s.op = OP_NONE; s.valid = 0; s.store_lo = s.store_hi = 0; }
 				const uint32_t haz = active ? s.hazard : 0;
 				const uint64_t lo = s.store_lo, hi = s.store_hi;
@@ -548,6 +769,10 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 					if (mine) {
 						if (segs) emit_segments(L, q, sh.req[lane], s, &st.seg[seg_incl - segs], unit_incl - units, wave);
 						build_cpl(sh.req[lane], s, &st.cpl[lane - r0]);
+						if (q.mode == QMODE_VRING) {
+							st.resp[lane - r0] = my_resp;
+							st.vq_head[lane - r0] = (uint16_t)my_head;
+						}
 					}
 					const uint32_t tot_seg = __shfl_sync(0xffffffffu, seg_incl, r1 - 1);
 					const uint32_t tot_unit = __shfl_sync(0xffffffffu, unit_incl, r1 - 1);
@@ -561,6 +786,11 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 						st.cpl_ring = q.cpls;
 						st.cpl_slot0 = slot0 + r0;
 						st.cpl_mask = q.ring_mask;
+						st.mode = q.mode;
+						st.vq_used = q.vq_used;
+						st.vq_state = q.vq_state;
+						st.vq_size = q.vq_size;
+						st.used_base = vq_last_used + done + r0;
 					}
 					__syncwarp();
 					if (lane == 0) mbar_arrive(&sh.full[sidx]);
@@ -568,6 +798,7 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 					r0 = r1;
 				}
 			}
+			if (q.mode == QMODE_VRING && lane == 0) q.vq_state->last_avail = (vq_last_avail + q.count) & 0xffff;
 		}
 		/* tell the movers to stop, then publish the completions still in flight */
 		{
@@ -579,7 +810,7 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 				reaped++;
 				__syncwarp();
 			}
-			if (lane == 0) { st.stop = 1; st.nunits = 0; st.nseg = 0; st.nwaves = 1; st.drain = 0; st.ncpl = 0; }
+			if (lane == 0) { st.stop = 1; st.nunits = 0; st.nseg = 0; st.nwaves = 1; st.drain = 0; st.ncpl = 0; st.mode = QMODE_SLOTS; }
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&sh.full[sidx]);
 		}

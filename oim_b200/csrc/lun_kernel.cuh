@@ -51,6 +51,8 @@ constexpr int kStages = OIM_STAGES;		/* parser -> mover pipeline depth */
 constexpr int kSegCap = 256;			/* SG segments per stage (>= 256 UNMAP descriptors, >= 129 iovecs) */
 constexpr uint32_t kUnitBytes = 4096;		/* bytes one warp moves per step: 8 x 16 B per lane */
 constexpr int kMaxReplicas = 4;
+constexpr int kMaxRegions = 8;			/* VHOST_MEMORY_MAX_NREGIONS */
+constexpr int kIovRow = OIMGPU_IOVS_MAX + 1;	/* scratch SG row per parser lane in virtqueue mode */
 
 enum : uint8_t { OP_NONE = 0, OP_READ = 1, OP_WRITE = 2, OP_UNMAP = 3 };
 
@@ -70,6 +72,10 @@ struct LunCtx {
 	uint8_t  present[OIMGPU_CTRLR_MAX_DEVS];	/* which target slots of the controller are occupied */
 	uint8_t  removed;		/* session saw a hot-remove of this target */
 	uint8_t  lun_removed;
+	/* guest memory table for virtqueue mode: struct rte_vhost_memory (rte_vhost.h:52-66) with
+	 * host_user_addr replaced by a device-accessible address */
+	uint32_t nregions;
+	struct { uint64_t gpa, size, addr; } region[kMaxRegions];
 	unsigned long long stats[8];	/* read ops, write ops, unmap ops, other, bytes r/w/unmapped, errors */
 };
 
@@ -81,15 +87,29 @@ struct KickHeader {
 	uint32_t pad[2];
 };
 
+/* ring cursors of an attached virtqueue, device-resident so they survive across launches */
+struct VqState {
+	uint32_t last_avail;		/* rte_vhost_vring.last_avail_idx (16 significant bits) */
+	uint32_t last_used;
+};
+
+enum : uint32_t { QMODE_SLOTS = 0, QMODE_VRING = 1 };
+
 /* one request queue as the kernel sees it for one launch */
 struct QueueDesc {
 	const oimgpu_req *reqs;
-	const oimgpu_iov *iovs;
+	const oimgpu_iov *iovs;		/* SG table (virtqueue mode: this launch's scratch rows) */
 	oimgpu_cpl       *cpls;
 	uint32_t ring_mask;		/* slot index mask (0xffffffff: linear array) */
 	uint32_t iov_mask;
 	uint32_t head;			/* first slot to process */
 	uint32_t count;			/* number of slots to process */
+	uint32_t mode;			/* QMODE_* */
+	uint32_t vq_size;		/* virtqueue mode: a real virtio split ring (linux/virtio_ring.h) */
+	const uint8_t *vq_desc;		/* struct vring_desc[vq_size] */
+	const uint8_t *vq_avail;	/* struct vring_avail */
+	uint8_t       *vq_used;		/* struct vring_used */
+	VqState       *vq_state;
 };
 
 /* one contiguous piece of payload to move (or to zero when src == nullptr) */
@@ -127,6 +147,12 @@ struct __align__(16) Stage {
 	oimgpu_cpl cpl[kPass];
 	oimgpu_cpl *cpl_ring;		/* where the records go once the movers are done */
 	uint32_t cpl_slot0, cpl_mask, ncpl;
+	/* virtqueue mode: guest response buffers + used ring instead of completion slots */
+	uint64_t resp[kPass];
+	uint16_t vq_head[kPass];
+	uint8_t  *vq_used;
+	VqState  *vq_state;
+	uint32_t vq_size, used_base, mode;
 	uint32_t nseg, nunits, nwaves;
 	uint32_t drain;			/* conflicts with the previous fill: wait for it to finish */
 	uint32_t stop;

@@ -102,6 +102,11 @@ struct Queue {
 	const oimgpu_iov *dev_iovs = nullptr;
 	oimgpu_cpl *dev_cpls = nullptr;
 	uint32_t dev_count = 0;
+	/* attached virtio split ring (virtqueue mode) */
+	const uint8_t *vq_desc = nullptr, *vq_avail = nullptr;
+	uint8_t *vq_used = nullptr;
+	uint32_t vq_size = 0;
+	bool vq_pending = false;
 };
 
 }  // namespace
@@ -126,6 +131,8 @@ struct oimgpu_lun {
 	QueueDesc *d_desc = nullptr;
 	uint64_t launches = 0;
 	int grid_cap = 0;
+	VqState *d_vq_state = nullptr;		/* [num_queues] ring cursors */
+	oimgpu_iov *d_iov_scratch = nullptr;	/* [grid_cap][32][kIovRow] SG rows built by the parser lanes */
 };
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -608,10 +615,10 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, sizeof(LunCtx), cudaMemcpyHostToDevice));
 
 	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
-		CU_OK(cudaHostAlloc((void **)&L->h_kick[k], sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 2, cudaHostAllocDefault));
+		CU_OK(cudaHostAlloc((void **)&L->h_kick[k], sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 3, cudaHostAllocDefault));
 		CU_OK(cudaEventCreateWithFlags(&L->kick_ev[k], cudaEventDisableTiming));
 	}
-	CU_OK(cudaMalloc((void **)&L->d_kick, sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 2));	/* ring + device-array submission per queue */
+	CU_OK(cudaMalloc((void **)&L->d_kick, sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 3));	/* ring + device-array + virtqueue per queue */
 	L->d_desc = (QueueDesc *)(L->d_kick + sizeof(KickHeader));
 	L->queues.resize(num_queues);
 	/* one mapped pinned slab per LUN, carved into per-queue rings: the "virtqueues" */
@@ -653,6 +660,8 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 		cudaEventDestroy(L->kick_ev[k]);
 	}
 	cudaFree(L->d_kick);
+	cudaFree(L->d_vq_state);
+	cudaFree(L->d_iov_scratch);
 	cudaFree(L->d_ctx);
 	cudaEventDestroy(L->done);
 	cudaStreamDestroy(L->stream);
@@ -746,6 +755,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 		Queue &Q = L->queues[q];
 		if (Q.dev_count) {
 			QueueDesc &D = h_desc[nd++];
+			memset(&D, 0, sizeof(D));
 			D.reqs = Q.dev_reqs;
 			D.iovs = Q.dev_iovs;
 			D.cpls = Q.dev_cpls ? Q.dev_cpls : Q.d_cpls;
@@ -755,8 +765,21 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 			D.count = Q.dev_count;
 			Q.dev_count = 0;
 		}
+		if (Q.vq_pending) {
+			QueueDesc &D = h_desc[nd++];
+			memset(&D, 0, sizeof(D));
+			D.mode = QMODE_VRING;
+			D.iovs = L->d_iov_scratch;
+			D.vq_size = Q.vq_size;
+			D.vq_desc = Q.vq_desc;
+			D.vq_avail = Q.vq_avail;
+			D.vq_used = Q.vq_used;
+			D.vq_state = L->d_vq_state + q;
+			Q.vq_pending = false;
+		}
 		if (Q.tail != Q.kicked) {
 			QueueDesc &D = h_desc[nd++];
+			memset(&D, 0, sizeof(D));
 			D.reqs = Q.d_reqs;
 			D.iovs = Q.d_iovs;
 			D.cpls = Q.d_cpls;
@@ -895,6 +918,81 @@ extern "C" int oimgpu_lun_set_removed(oimgpu_lun *L, int removed, int lun_remove
 	L->h_ctx.lun_removed = lun_removed != 0;
 	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, offsetof(LunCtx, stats), cudaMemcpyHostToDevice));
 	return 0;
+}
+
+/* ---- virtqueue mode --------------------------------------------------------------------------------- */
+
+/* rte_vhost_memory table of the session (S/lib/vhost/rte_vhost/rte_vhost.h:52-66): guest-physical
+ * ranges and the device-accessible address each one is mapped at */
+extern "C" int oimgpu_lun_set_mem_table(oimgpu_lun *L, const oimgpu_mem_region *regions, uint32_t nregions)
+{
+	if (!L || (!regions && nregions) || nregions > (uint32_t)kMaxRegions) return -EINVAL;
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaStreamSynchronize(L->stream));
+	L->h_ctx.nregions = nregions;
+	for (uint32_t i = 0; i < nregions; i++) {
+		L->h_ctx.region[i].gpa = regions[i].guest_phys_addr;
+		L->h_ctx.region[i].size = regions[i].size;
+		L->h_ctx.region[i].addr = regions[i].addr;
+	}
+	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, offsetof(LunCtx, stats), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+/* Attach a virtio split ring to queue q: the three areas rte_vhost_get_vhost_vring reports
+ * (S/lib/vhost/vhost.c:1120-1134), as device-accessible addresses, plus the ring cursors. */
+extern "C" int oimgpu_vq_attach(oimgpu_lun *L, uint32_t q, const void *desc, const void *avail, void *used,
+				uint32_t size, uint16_t last_avail_idx, uint16_t last_used_idx)
+{
+	if (!L || q >= L->num_queues || !desc || !avail || !used) return -EINVAL;
+	if (size == 0 || size > OIMGPU_MAX_VQ_SIZE || (size & (size - 1))) return -EINVAL;
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaStreamSynchronize(L->stream));
+	if (!L->d_vq_state) {
+		CU_OK(cudaMalloc((void **)&L->d_vq_state, sizeof(VqState) * L->num_queues));
+		CU_OK(cudaMemset(L->d_vq_state, 0, sizeof(VqState) * L->num_queues));
+	}
+	if (!L->d_iov_scratch) {
+		CU_OK(cudaMalloc((void **)&L->d_iov_scratch, sizeof(oimgpu_iov) * (size_t)L->grid_cap * kPass * kIovRow));
+	}
+	VqState st = { last_avail_idx, last_used_idx };
+	CU_OK(cudaMemcpy(L->d_vq_state + q, &st, sizeof(st), cudaMemcpyHostToDevice));
+	Queue &Q = L->queues[q];
+	Q.vq_desc = (const uint8_t *)desc;
+	Q.vq_avail = (const uint8_t *)avail;
+	Q.vq_used = (uint8_t *)used;
+	Q.vq_size = size;
+	Q.vq_pending = false;
+	return 0;
+}
+
+extern "C" int oimgpu_vq_detach(oimgpu_lun *L, uint32_t q, uint16_t *last_avail_idx, uint16_t *last_used_idx)
+{
+	if (!L || q >= L->num_queues || !L->queues[q].vq_size) return -EINVAL;
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaStreamSynchronize(L->stream));
+	VqState st;
+	CU_OK(cudaMemcpy(&st, L->d_vq_state + q, sizeof(st), cudaMemcpyDeviceToHost));
+	if (last_avail_idx) *last_avail_idx = (uint16_t)st.last_avail;
+	if (last_used_idx) *last_used_idx = (uint16_t)st.last_used;
+	Queue &Q = L->queues[q];
+	Q.vq_desc = Q.vq_avail = nullptr;
+	Q.vq_used = nullptr;
+	Q.vq_size = 0;
+	Q.vq_pending = false;
+	return 0;
+}
+
+/* The guest's "kick": process every attached ring up to its avail->idx (one launch, asynchronous). */
+extern "C" int oimgpu_vq_kick(oimgpu_lun *L)
+{
+	if (!L) return -EINVAL;
+	int n = 0;
+	for (auto &Q : L->queues) {
+		if (Q.vq_size) { Q.vq_pending = true; n++; }
+	}
+	if (!n) return 0;
+	return oimgpu_kick(L);
 }
 
 /* ---- device-timed region helpers (bench.py times on the LUN's own stream) ------------------------- */

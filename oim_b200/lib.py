@@ -86,6 +86,10 @@ SYMBOLS = [
     ("oimgpu_lun_iostat", _I, [_VP, C.POINTER(IoStat)]),
     ("oimgpu_lun_stream", _VP, [_VP]),
     ("oimgpu_lun_set_removed", _I, [_VP, _I, _I]),
+    ("oimgpu_lun_set_mem_table", _I, [_VP, _VP, _U32]),
+    ("oimgpu_vq_attach", _I, [_VP, _U32, _VP, _VP, _VP, _U32, C.c_uint16, C.c_uint16]),
+    ("oimgpu_vq_detach", _I, [_VP, _U32, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]),
+    ("oimgpu_vq_kick", _I, [_VP]),
     ("oimgpu_timer_create", _I, [C.POINTER(_VP), C.POINTER(_VP)]),
     ("oimgpu_timer_record", _I, [_VP, _VP]),
     ("oimgpu_timer_elapsed_ms", _I, [_VP, _VP, C.POINTER(C.c_float)]),
@@ -339,6 +343,23 @@ class Lun:
 
     def set_removed(self, removed: bool = True, lun_removed: bool = False) -> None:
         _chk(load().oimgpu_lun_set_removed(self.h, int(removed), int(lun_removed)), "set_removed")
+
+    # ---- virtqueue mode ----
+    def set_mem_table(self, regions: np.ndarray) -> None:
+        """regions: flat uint64 array of {guest_phys_addr, size, device address} triples"""
+        regions = np.ascontiguousarray(regions, dtype=np.uint64)
+        _chk(load().oimgpu_lun_set_mem_table(self.h, regions.ctypes.data, len(regions) // 3), "set_mem_table")
+
+    def vq_attach(self, q: int, desc: int, avail: int, used: int, size: int, last_avail: int = 0, last_used: int = 0):
+        _chk(load().oimgpu_vq_attach(self.h, q, desc, avail, used, size, last_avail, last_used), "vq_attach")
+
+    def vq_detach(self, q: int) -> tuple[int, int]:
+        la, lu = C.c_uint16(), C.c_uint16()
+        _chk(load().oimgpu_vq_detach(self.h, q, C.byref(la), C.byref(lu)), "vq_detach")
+        return la.value, lu.value
+
+    def vq_kick(self) -> int:
+        return _chk(load().oimgpu_vq_kick(self.h), "vq_kick")
 
     def copy(self, dst: int, src: int, nbytes: int) -> None:
         _chk(load().oimgpu_copy_submit(self.h, dst, src, nbytes), "copy_submit")

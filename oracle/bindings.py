@@ -75,6 +75,22 @@ class _Oracle:
             raise RuntimeError(f"{self.prefix}_submit rc={rc}")
         return cpls
 
+    def vq_process(self, img, last_avail: int = 0, last_used: int = 0) -> tuple[int, int, int]:
+        """run the poller over a guest image's split ring (oim_b200.vring.GuestImage, host memory);
+        -> (used elements produced, new last_avail_idx, new last_used_idx)"""
+        fn = getattr(self.lib, self.prefix + "_vq_process")
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32,
+                       C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]
+        base = img.arena.ctypes.data
+        reg = img.region_table(base)
+        la, lu = C.c_uint16(last_avail), C.c_uint16(last_used)
+        n = fn(self.h, base + img.desc_off, base + img.avail_off, base + img.used_off, img.ring_size,
+               reg.ctypes.data, len(img.regions), C.byref(la), C.byref(lu))
+        if n < 0:
+            raise RuntimeError(f"{self.prefix}_vq_process rc={n}")
+        return n, la.value, lu.value
+
     def busy_ns(self, reset: bool = True) -> int:
         """ns spent inside the checker's own request processing (0 = not instrumented: time the call)"""
         return int(self._busy(self.h, int(reset)))

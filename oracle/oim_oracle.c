@@ -76,6 +76,9 @@ static inline uint64_t be64(const uint8_t *p) { return (uint64_t)be32(p) << 32 |
 static inline void to_be32(uint8_t *p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
 static inline void to_be64(uint8_t *p, uint64_t v) { to_be32(p, v >> 32); to_be32(p + 4, (uint32_t)v); }
 
+int oimorc_desc_to_iov(const uint64_t *regions, uint32_t nregions, uint64_t addr, uint32_t len,
+		       struct oimgpu_iov *out, uint32_t start_index);
+
 /* spdk_scsi_task_build_sense_data + spdk_scsi_task_set_status (S/lib/scsi/task.c:198-247) */
 static void task_set_status(struct orc_task *t, int sc, int sk, int asc, int ascq)
 {
@@ -452,6 +455,55 @@ static void task_process_null_lun(struct orc_task *t)
 	}
 }
 
+/* process_request after task_data_setup (vhost_scsi.c:633-653) -> task_submit / null-LUN early
+ * completion / BAD_TARGET, then spdk_vhost_scsi_task_cpl (311-331).  `t` carries the SG list. */
+static void execute_task(struct oimorc *o, struct orc_task *t, const uint8_t *lun, struct oimgpu_cpl *c)
+{
+	struct orc_tgt *tgt;
+	struct orc_bdev *lun_bdev = NULL;
+	uint16_t lun_id;
+
+	/* ---- spdk_vhost_scsi_task_init_target ---- */
+	lun_id = (((uint16_t)lun[2] << 8) | lun[3]) & 0x3FFF;
+	if (lun[0] != 1 || lun[1] >= OIMGPU_CTRLR_MAX_DEVS) {
+		c->response = OIMGPU_S_BAD_TARGET;
+		return;
+	}
+	tgt = &o->tgt[lun[1]];
+	if (tgt->bdev == NULL || tgt->removed) {
+		if (!tgt->removed) {
+			c->response = OIMGPU_S_BAD_TARGET;
+			return;
+		}
+		/* hot-detached: LUN stays NULL so the guest gets a sense code */
+	} else if (lun_id == 0) {
+		lun_bdev = tgt->bdev;	/* spdk_scsi_dev_get_lun(dev, 0) */
+	}
+
+	c->response = OIMGPU_S_OK;
+	if (lun_bdev == NULL) {
+		task_process_null_lun(t);
+	} else {
+		/* _spdk_scsi_lun_execute_task (S/lib/scsi/lun.c:163-189) */
+		t->status = SC_GOOD;
+		if (tgt->lun_removed) {
+			/* spdk_scsi_task_process_abort (task.c:295-302) */
+			task_set_status(t, SC_CHECK_CONDITION, SK_ABORTED_COMMAND, ASC_NONE, ASCQ_NONE);
+		} else {
+			scsi_execute(lun_bdev, t);
+		}
+	}
+
+	/* ---- spdk_vhost_scsi_task_cpl ---- */
+	c->status = t->status;
+	if (t->status != SC_GOOD) {
+		memcpy(c->sense, t->sense_data, t->sense_data_len);
+		c->sense_len = t->sense_data_len;
+	}
+	c->resid = t->length - t->data_transferred;
+	c->data_transferred = t->data_transferred;
+}
+
 /* One request through process_requestq's loop body (vhost_scsi.c:702-739):
  * task_data_setup (490-624) -> spdk_vhost_scsi_task_init_target (361-387) -> process_request
  * (626-653) -> task_submit / early completion / invalid_request -> spdk_vhost_scsi_task_cpl (311-331) */
@@ -461,9 +513,6 @@ static void process_one(struct oimorc *o, const struct oimgpu_req *q, const stru
 	struct orc_task t;
 	uint32_t cnt = q->iovcnt, len = 0, i, used_len;
 	bool from_dev = (q->dir == OIMGPU_DIR_FROM_DEV) || cnt == 0;
-	struct orc_tgt *tgt;
-	struct orc_bdev *lun_bdev = NULL;
-	uint16_t lun_id;
 
 	memset(&t, 0, sizeof(t));
 	memset(c, 0, sizeof(*c));
@@ -498,46 +547,7 @@ static void process_one(struct oimorc *o, const struct oimgpu_req *q, const stru
 	t.length = t.transfer_len = len;
 	c->used_len = used_len;
 	c->resp_valid = 1;
-
-	/* ---- spdk_vhost_scsi_task_init_target ---- */
-	lun_id = (((uint16_t)q->lun[2] << 8) | q->lun[3]) & 0x3FFF;
-	if (q->lun[0] != 1 || q->lun[1] >= OIMGPU_CTRLR_MAX_DEVS) {
-		c->response = OIMGPU_S_BAD_TARGET;
-		return;
-	}
-	tgt = &o->tgt[q->lun[1]];
-	if (tgt->bdev == NULL || tgt->removed) {
-		if (!tgt->removed) {
-			c->response = OIMGPU_S_BAD_TARGET;
-			return;
-		}
-		/* hot-detached: LUN stays NULL so the guest gets a sense code */
-	} else if (lun_id == 0) {
-		lun_bdev = tgt->bdev;	/* spdk_scsi_dev_get_lun(dev, 0) */
-	}
-
-	c->response = OIMGPU_S_OK;
-	if (lun_bdev == NULL) {
-		task_process_null_lun(&t);
-	} else {
-		/* _spdk_scsi_lun_execute_task (S/lib/scsi/lun.c:163-189) */
-		t.status = SC_GOOD;
-		if (tgt->lun_removed) {
-			/* spdk_scsi_task_process_abort (task.c:295-302) */
-			task_set_status(&t, SC_CHECK_CONDITION, SK_ABORTED_COMMAND, ASC_NONE, ASCQ_NONE);
-		} else {
-			scsi_execute(lun_bdev, &t);
-		}
-	}
-
-	/* ---- spdk_vhost_scsi_task_cpl ---- */
-	c->status = t.status;
-	if (t.status != SC_GOOD) {
-		memcpy(c->sense, t.sense_data, t.sense_data_len);
-		c->sense_len = t.sense_data_len;
-	}
-	c->resid = t.length - t.data_transferred;
-	c->data_transferred = t.data_transferred;
+	execute_task(o, &t, q->lun, c);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -629,6 +639,182 @@ int oimorc_desc_to_iov(const uint64_t *regions, uint32_t nregions, uint64_t addr
 		idx++;
 	} while (remaining);
 	return (int)(idx - start_index);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Virtqueue level: the split-ring walk of the reference's poller, restated.
+ * ------------------------------------------------------------------------------------------- */
+
+struct vq_desc { uint64_t addr; uint32_t len; uint16_t flags; uint16_t next; };	/* struct vring_desc */
+#define VQ_F_NEXT	1
+#define VQ_F_WRITE	2
+#define VQ_F_INDIRECT	4
+
+struct vq_ctx {
+	const uint64_t *regions;
+	uint32_t nregions;
+};
+
+/* spdk_vhost_gpa_to_vva (vhost.c:93-106) over rte_vhost_va_from_guest_pa (rte_vhost.h:167-190):
+ * the whole [gpa, gpa+len) must sit inside the region that contains gpa */
+static void *vq_gpa_to_vva(const struct vq_ctx *m, uint64_t gpa, uint64_t len)
+{
+	uint32_t i;
+	for (i = 0; i < m->nregions; i++) {
+		uint64_t g = m->regions[3 * i], sz = m->regions[3 * i + 1], hva = m->regions[3 * i + 2];
+		if (gpa >= g && gpa < g + sz) {
+			if (len > g + sz - gpa) return NULL;
+			return (void *)(uintptr_t)(gpa - g + hva);
+		}
+	}
+	return NULL;
+}
+
+/* spdk_vhost_vring_desc_get_next (vhost.c:433-453): 0 ok (possibly *desc == NULL), -1 bad index */
+static int vq_desc_get_next(const struct vq_desc **desc, const struct vq_desc *table, uint32_t table_size)
+{
+	const struct vq_desc *old = *desc;
+	if ((old->flags & VQ_F_NEXT) == 0) { *desc = NULL; return 0; }
+	if (old->next >= table_size) { *desc = NULL; return -1; }
+	*desc = &table[old->next];
+	return 0;
+}
+
+/* spdk_vhost_vring_desc_to_iov (vhost.c:461-509) appending to the task's SG list */
+static int vq_desc_to_iov(const struct vq_ctx *m, struct orc_task *t, uint16_t *iov_index, const struct vq_desc *d)
+{
+	struct oimgpu_iov out[OIMGPU_IOVS_MAX];
+	int n = oimorc_desc_to_iov(m->regions, m->nregions, d->addr, d->len, out, *iov_index), i;
+	if (n < 0) return -1;
+	for (i = 0; i < n; i++) {
+		t->iovs[*iov_index + i].base = (uint8_t *)(uintptr_t)out[i].addr;
+		t->iovs[*iov_index + i].len = out[i].len;
+	}
+	*iov_index += n;
+	return 0;
+}
+
+/* task_data_setup (vhost_scsi.c:490-624).  Returns 0 and fills t/req/resp/used_len, or -1 (invalid) */
+static int vq_task_data_setup(const struct vq_ctx *m, const struct vq_desc *ring, uint32_t ring_size, uint16_t req_idx,
+			      struct orc_task *t, const uint8_t **req, uint8_t **resp, uint32_t *used_len)
+{
+	const struct vq_desc *desc, *table;
+	uint32_t table_size, len = 0;
+	uint16_t iovcnt = 0;
+	int rc;
+
+	/* spdk_vhost_vq_get_desc (vhost.c:219-247) */
+	if (req_idx >= ring_size) return -1;
+	desc = &ring[req_idx];
+	if (desc->flags & VQ_F_INDIRECT) {
+		table_size = desc->len / sizeof(*desc);
+		table = vq_gpa_to_vva(m, desc->addr, sizeof(*desc) * (uint64_t)table_size);
+		desc = table;
+		if (desc == NULL) return -1;
+	} else {
+		table = ring;
+		table_size = ring_size;
+	}
+	/* "First descriptor must be readable" and hold a whole virtio_scsi_cmd_req (51 bytes) */
+	if ((desc->flags & VQ_F_WRITE) || desc->len < 51) return -1;
+	*req = vq_gpa_to_vva(m, desc->addr, 51);
+	if (*req == NULL) return -1;
+	vq_desc_get_next(&desc, table, table_size);
+	if (desc == NULL) return -1;	/* "contains neither payload nor response buffer" */
+	t->dxfer_dir = (desc->flags & VQ_F_WRITE) ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV;
+
+	if (t->dxfer_dir == OIMGPU_DIR_FROM_DEV) {
+		/* FROM_DEV (READ): [RD_req][WR_resp][WR_buf0]...[WR_bufN] */
+		*resp = vq_gpa_to_vva(m, desc->addr, OIMGPU_RESP_SIZE);
+		if (desc->len < OIMGPU_RESP_SIZE || *resp == NULL) return -1;
+		rc = vq_desc_get_next(&desc, table, table_size);
+		if (rc != 0) return -1;
+		if (desc == NULL) {
+			*used_len = OIMGPU_RESP_SIZE;
+			t->iovcnt = 1;
+			t->iovs[0].base = NULL;
+			t->iovs[0].len = 0;
+			t->length = t->transfer_len = 0;
+			return 0;
+		}
+		while (desc) {
+			if (!(desc->flags & VQ_F_WRITE)) return -1;
+			if (vq_desc_to_iov(m, t, &iovcnt, desc)) return -1;
+			len += desc->len;
+			rc = vq_desc_get_next(&desc, table, table_size);
+			if (rc != 0) return -1;
+		}
+		*used_len = OIMGPU_RESP_SIZE + len;
+	} else {
+		/* TO_DEV (WRITE): [RD_req][RD_buf0]...[RD_bufN][WR_resp] */
+		while (!(desc->flags & VQ_F_WRITE)) {
+			if (vq_desc_to_iov(m, t, &iovcnt, desc)) return -1;
+			len += desc->len;
+			vq_desc_get_next(&desc, table, table_size);
+			if (desc == NULL) return -1;	/* "no response descriptor" */
+		}
+		*resp = vq_gpa_to_vva(m, desc->addr, OIMGPU_RESP_SIZE);
+		if (desc->len < OIMGPU_RESP_SIZE || *resp == NULL) return -1;
+		*used_len = OIMGPU_RESP_SIZE;
+	}
+	t->iovcnt = iovcnt;
+	t->length = t->transfer_len = len;
+	return 0;
+}
+
+/* process_requestq + spdk_vhost_vq_avail_ring_get + spdk_vhost_vq_used_ring_enqueue
+ * (vhost_scsi.c:690-741, vhost.c:178-211, 397-431).  Used elements are produced in ring order (the
+ * reference's order depends on when its thread polls deferred completions, see ref_driver.c). */
+int oimorc_vq_process(void *h, uint64_t desc, uint64_t avail, uint64_t used, uint32_t size,
+		      const uint64_t *regions, uint32_t nregions, uint16_t *last_avail_idx, uint16_t *last_used_idx)
+{
+	struct oimorc *o = h;
+	const struct vq_desc *ring = (const struct vq_desc *)(uintptr_t)desc;
+	const volatile uint16_t *av = (const volatile uint16_t *)(uintptr_t)avail;	/* flags, idx, ring[] */
+	uint8_t *us = (uint8_t *)(uintptr_t)used;					/* flags, idx, {id,len}[] */
+	struct vq_ctx m = { regions, nregions };
+	uint16_t count = (uint16_t)(av[1] - *last_avail_idx), i;
+	int produced = 0;
+
+	if (size == 0 || size > OIMGPU_MAX_VQ_SIZE || (size & (size - 1))) return -EINVAL;
+	if (count > size) return 0;	/* broken queue: report nothing (vhost.c:193-198) */
+	for (i = 0; i < count; i++) {
+		uint16_t head = av[2 + ((*last_avail_idx + i) & (size - 1))];
+		struct orc_task t;
+		struct oimgpu_cpl c;
+		const uint8_t *req = NULL;
+		uint8_t *resp = NULL;
+		uint32_t used_len = 0, slot;
+
+		memset(&t, 0, sizeof(t));
+		memset(&c, 0, sizeof(c));
+		if (vq_task_data_setup(&m, ring, size, head, &t, &req, &resp, &used_len) == 0) {
+			t.cdb = req + 19;	/* virtio_scsi_cmd_req.cdb */
+			c.used_len = used_len;
+			execute_task(o, &t, req, &c);
+			/* what spdk_vhost_scsi_task_cpl / process_request write into the guest's response */
+			resp[11] = c.response;
+			if (c.response == OIMGPU_S_OK) {
+				resp[10] = c.status;
+				if (c.status != SC_GOOD) {
+					memcpy(resp + 12, c.sense, c.sense_len);
+					memcpy(resp + 0, &c.sense_len, 4);
+				}
+				memcpy(resp + 4, &c.resid, 4);
+			}
+		} else {
+			used_len = 0;	/* invalid_request(): used element with length 0, nothing else */
+		}
+		slot = (uint16_t)(*last_used_idx) & (size - 1);
+		memcpy(us + 4 + 8 * slot, &(uint32_t){ head }, 4);
+		memcpy(us + 4 + 8 * slot + 4, &used_len, 4);
+		(*last_used_idx)++;
+		__sync_synchronize();
+		memcpy(us + 2, last_used_idx, 2);
+		produced++;
+	}
+	*last_avail_idx += count;
+	return produced;
 }
 
 uint64_t oimorc_busy_ns(void *h, int reset) { (void)h; (void)reset; return 0; }	/* caller times the call */

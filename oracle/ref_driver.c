@@ -400,6 +400,71 @@ int oimref_desc_to_iov(const uint64_t *regions, uint32_t nregions, uint64_t addr
 	return idx - start_index;
 }
 
+/* Virtqueue level: run the reference's poller over a caller-built split ring living in caller
+ * memory.  desc/avail/used are host addresses of the three ring areas (what rte_vhost_get_vhost_vring
+ * reports), regions = {guest_phys_addr, size, host_user_addr} triples (the rte_vhost_memory table).
+ * Processes everything up to avail->idx in passes of <= 32 and returns the number of used elements
+ * produced; *last_avail_idx / *last_used_idx are the ring cursors, updated in place. */
+int oimref_vq_process(void *h, uint64_t desc, uint64_t avail, uint64_t used, uint32_t size,
+		      const uint64_t *regions, uint32_t nregions, uint16_t *last_avail_idx, uint16_t *last_used_idx)
+{
+	struct oimref *r = h;
+	struct spdk_vhost_session *vs = &r->svsession->vsession;
+	struct spdk_vhost_virtqueue *vq = &vs->virtqueue[VIRTIO_SCSI_REQUESTQ + 1];
+	struct rte_vhost_memory *mem, *saved_mem = vs->mem;
+	struct vring_avail *av = (struct vring_avail *)(uintptr_t)avail;
+	struct vring_used *us = (struct vring_used *)(uintptr_t)used;
+	struct timespec t0, t1;
+	uint16_t start_used = *last_used_idx, want, i;
+	int spins = 0;
+
+	if (size == 0 || size > SPDK_VHOST_MAX_VQ_SIZE || (size & (size - 1))) return -EINVAL;
+	spdk_set_thread(g_thread);
+	mem = calloc(1, sizeof(*mem) + nregions * sizeof(struct rte_vhost_mem_region));
+	mem->nregions = nregions;
+	for (i = 0; i < nregions; i++) {
+		mem->regions[i].guest_phys_addr = regions[3 * i];
+		mem->regions[i].size = regions[3 * i + 1];
+		mem->regions[i].host_user_addr = regions[3 * i + 2];
+	}
+	vs->mem = mem;
+	memset(vq, 0, sizeof(*vq));
+	vq->vring.desc = (struct vring_desc *)(uintptr_t)desc;
+	vq->vring.avail = av;
+	vq->vring.used = us;
+	vq->vring.size = size;
+	vq->vring.callfd = r->eventfd;
+	vq->vring.kickfd = -1;
+	vq->vring.last_avail_idx = *last_avail_idx;
+	vq->vring.last_used_idx = *last_used_idx;
+	vq->tasks = calloc(size, sizeof(struct spdk_vhost_scsi_task));
+	for (i = 0; i < size; i++) {
+		struct spdk_vhost_scsi_task *t = &((struct spdk_vhost_scsi_task *)vq->tasks)[i];
+		t->svsession = r->svsession;
+		t->vq = vq;
+		t->req_idx = i;
+	}
+	want = (uint16_t)(av->idx - *last_avail_idx);
+	if (want > size) want = 0;	/* "the queue is unrecoverably broken" (vhost.c:193-198) */
+
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	while ((uint16_t)(us->idx - start_used) != want && spins++ < 100000) {
+		process_requestq(r->svsession, vq);
+		spdk_thread_poll(g_thread, 0, 0);
+		spdk_vhost_vq_used_signal(vs, vq);
+	}
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	r->poller_ns += (uint64_t)(t1.tv_sec - t0.tv_sec) * 1000000000ull + (uint64_t)(t1.tv_nsec - t0.tv_nsec);
+
+	*last_avail_idx = vq->vring.last_avail_idx;
+	*last_used_idx = vq->vring.last_used_idx;
+	free(vq->tasks);
+	vq->tasks = NULL;
+	vs->mem = saved_mem;
+	free(mem);
+	return (uint16_t)(us->idx - start_used) == want ? (int)want : -EIO;
+}
+
 /* nanoseconds spent in process_requestq() + completion polling + used_signal since the last reset:
  * the reference's own work, without this driver's descriptor-chain building (which a guest does) */
 uint64_t oimref_busy_ns(void *h, int reset)
