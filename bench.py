@@ -334,15 +334,27 @@ def run_ours(args, rank, world, local):
         en = eq * ep
         t = traces.uniform_trace(en, NUM_BLOCKS, io_blocks=8, pattern="randread", seed=plan["e2e_seed"])
         host = torch.empty(t.arena_bytes, dtype=torch.uint8).pin_memory()
-        iovs = t.bind(host.data_ptr())
-        cpls = np.zeros(en, dtype=abi.cpl_dtype)
+
+        def pinned_like(a: np.ndarray) -> np.ndarray:
+            """same contents in pinned host memory (a front end builds its requests there)"""
+            buf = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+            out = buf.numpy().view(a.dtype)
+            out[:] = a
+            out_keep.append(buf)
+            return out
+        out_keep = []
+        reqs_p = pinned_like(t.reqs)
+        iovs = pinned_like(t.bind(host.data_ptr()))
+        cpls = pinned_like(np.zeros(en, dtype=abi.cpl_dtype))
         L = lib.load()
 
         def e2e_step():
-            rc = L.oimgpu_submit_and_wait(lun_e2e.h, eq, ep, t.reqs.ctypes.data, iovs.ctypes.data, len(iovs),
+            # host->device: request + SG arrays (copy engine); device->host: payload (stored by the
+            # movers into the pinned client buffers) + completion records (copy engine)
+            rc = L.oimgpu_submit_and_wait(lun_e2e.h, eq, ep, reqs_p.ctypes.data, iovs.ctypes.data, len(iovs),
                                           cpls.ctypes.data, abi.MEM_HOST)
             assert rc == 0, rc
-            return int(cpls["status"].sum())       # device->host read of the step's result
+            return int(cpls["status"].sum()) + int((cpls["used_len"] != 4096 + 108).sum())
         for _ in range(max(1, args.warmup)):
             e2e_step()
         barrier()
@@ -351,6 +363,12 @@ def run_ours(args, rank, world, local):
             assert e2e_step() == 0
         barrier()
         wall = max_over_ranks(time.perf_counter() - t0)
+        # device share of one step (explains the number; not part of it)
+        timer.start(lun_e2e)
+        L.oimgpu_submit_batch(lun_e2e.h, eq, ep, reqs_p.ctypes.data, iovs.ctypes.data, len(iovs), cpls.ctypes.data, abi.MEM_HOST)
+        timer.stop(lun_e2e)
+        lun_e2e.sync()
+        dev_ms = timer.elapsed_ms()
         got = host[:4096].numpy()
         lba0 = int.from_bytes(bytes(t.reqs["cdb"][0][2:6]), "big")
         assert (got == traces.pattern_bytes(plan["store_seed"], lba0 * BLOCK, 4096)).all()
@@ -358,8 +376,11 @@ def run_ours(args, rank, world, local):
                "h2d_bytes_per_step": int(en * 64 + len(iovs) * 16),
                "d2h_bytes_per_step": int(en * 4096 + en * 48),
                "ms_per_step": wall / args.steps * 1e3, "requests_per_step": en, "queues": eq,
-               "note": "request/SG/completion rings in mapped pinned host memory, read/written by the kernel "
-                       "over PCIe; payload stored by the kernel straight into pinned client buffers"}
+               "device_ms_per_step": dev_ms, "pcie_payload_gbs_device": en * 4096 / (dev_ms / 1e3) / 1e9,
+               "note": "host request/SG arrays in pinned memory -> copy-engine upload -> kernel on HBM-resident "
+                       "metadata; payload stored by the movers straight into pinned client buffers over PCIe; "
+                       "completion records copied back; PCIe D2H ceiling of the box 57 GB/s (cudaMemcpy), "
+                       "52.7 GB/s for SM-originated stores (tools/pcie_store_bench.cu)"}
 
     # ---- second metric: 128 KiB sequential write (runs last: it overwrites the patterned store) ----
     seq = None

@@ -223,6 +223,7 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 	bool valid = true;
 	for (uint32_t j = 0; j < cnt; j++) {
 		if (j >= OIMGPU_IOVS_MAX) { valid = false; break; }
+		if (q.iov_limit && r.iov_start + j >= q.iov_limit) { valid = false; break; }	/* index outside the SG table */
 		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
 		if (v.addr == 0) { valid = false; break; }
 		len += v.len;

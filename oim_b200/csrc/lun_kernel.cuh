@@ -105,6 +105,7 @@ struct QueueDesc {
 	uint32_t head;			/* first slot to process */
 	uint32_t count;			/* number of slots to process */
 	uint32_t mode;			/* QMODE_* */
+	uint32_t iov_limit;		/* entries in the SG table (0: not checked) */
 	uint32_t vq_size;		/* virtqueue mode: a real virtio split ring (linux/virtio_ring.h) */
 	const uint8_t *vq_desc;		/* struct vring_desc[vq_size] */
 	const uint8_t *vq_avail;	/* struct vring_avail */
