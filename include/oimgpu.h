@@ -266,6 +266,16 @@ int oimgpu_vq_attach(oimgpu_lun *lun, uint32_t q, const void *desc, const void *
 int oimgpu_vq_detach(oimgpu_lun *lun, uint32_t q, uint16_t *last_avail_idx, uint16_t *last_used_idx);
 int oimgpu_vq_kick(oimgpu_lun *lun);	/* process every attached ring up to its avail->idx; asynchronous */
 
+/* ---- persistent poller: one resident "reactor" kernel per LUN (replaces the vdev_worker poller that
+ * spdk_poller_register() keeps running on a reactor core, S/lib/vhost/vhost_scsi.c:758-772,1311-1318).
+ * The kernel polls the tail doorbell of every library ring and the avail->idx of every attached
+ * virtqueue from mapped host memory; oimgpu_kick() becomes a doorbell write, oimgpu_poll() reads the
+ * completion counter.  max_ctas == 0: one CTA per queue up to the GPU's capacity.
+ * idle_timeout_ms != 0: watchdog, the kernel leaves after that long without work. */
+int oimgpu_lun_start_poller(oimgpu_lun *lun, uint32_t max_ctas, uint32_t idle_timeout_ms);
+int oimgpu_lun_stop_poller(oimgpu_lun *lun);
+int oimgpu_lun_poller_running(oimgpu_lun *lun);
+
 /* Session-visible hot-remove state of the target (S/lib/vhost/vhost_scsi.c:1093-1100: `removed`;
  * S/lib/scsi/lun.c:171-176: `lun_removed`). */
 int oimgpu_lun_set_removed(oimgpu_lun *lun, int removed, int lun_removed);

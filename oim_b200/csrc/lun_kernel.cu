@@ -370,6 +370,19 @@ __device__ __forceinline__ void build_cpl(const oimgpu_req &r, const LaneState &
 
 /* ---- virtqueue mode: the split-ring walk of the reference's poller on one parser lane ---------- */
 
+__device__ __forceinline__ uint32_t ld_vol32(const volatile void *p)
+{
+	uint32_t r;
+	asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+	return r;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns()
+{
+	uint64_t t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
 __device__ __forceinline__ uint16_t ld_vol16(const void *p)
 {
 	uint16_t r;
@@ -535,6 +548,12 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 			st_cg16(reinterpret_cast<int4 *>(&st.cpl_ring[slot]) + v % 3,
 				reinterpret_cast<const int4 *>(&st.cpl[v / 3])[v % 3]);
 		}
+		if (st.done) {
+			/* persistent mode: make payload + records visible to the host, then bump the counter it polls */
+			__threadfence_system();
+			__syncwarp();
+			if (lane == 0 && n) *st.done = st.cpl_slot0 + n;
+		}
 		return;
 	}
 	/* virtqueue mode: spdk_vhost_scsi_task_cpl writes into the guest's response buffer
@@ -601,14 +620,59 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 		bool first = true;
 
 		const uint32_t nqueues = hdr->nqueues;
+		const bool persistent = hdr->persistent != 0;
+		uint32_t sweep_qi = blockIdx.x;
+		bool progress = false;
+		uint64_t last_progress = persistent ? globaltimer_ns() : 0;
 		for (;;) {
-			/* next queue: first one static (no atomic on the critical path), then work-stealing */
 			uint32_t qi = 0;
-			if (lane == 0) qi = first ? blockIdx.x : atomicAdd(&hdr->next, 1u);
-			qi = __shfl_sync(0xffffffffu, qi, 0);
-			first = false;
-			if (qi >= nqueues) break;
+			if (!persistent) {
+				/* next queue: first one static (no atomic on the critical path), then work-stealing */
+				if (lane == 0) qi = first ? blockIdx.x : atomicAdd(&hdr->next, 1u);
+				qi = __shfl_sync(0xffffffffu, qi, 0);
+				first = false;
+				if (qi >= nqueues) break;
+			} else {
+				if (sweep_qi >= nqueues) {
+					/* end of one sweep over this CTA's queues (spdk_thread_poll returning) */
+					sweep_qi = blockIdx.x;
+					if (progress) {
+						progress = false;
+						last_progress = globaltimer_ns();
+						continue;
+					}
+					/* idle: publish every completion still held back by the pipeline, then look at the
+					 * stop flag / watchdog */
+					while (reaped < fills) {
+						const uint32_t sidx = reaped % kStages;
+						mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
+						reap_stage(sh.stage[sidx], lane);
+						reaped++;
+					}
+					uint32_t quit = 0;
+					if (lane == 0) {
+						quit = ld_vol32(hdr->stop) != 0;
+						if (!quit && hdr->idle_timeout_ms &&
+						    globaltimer_ns() - last_progress > (uint64_t)hdr->idle_timeout_ms * 1000000ull) quit = 1;
+					}
+					if (__shfl_sync(0xffffffffu, quit, 0)) break;
+					__nanosleep(500);
+					continue;
+				}
+				qi = sweep_qi;
+				sweep_qi += gridDim.x;
+			}
 			QueueDesc q = queues[qi];
+			if (persistent && q.mode == QMODE_SLOTS) {
+				/* new slots = host doorbell (tail) - consumed cursor */
+				uint32_t cnt = 0, consumed = 0;
+				if (lane == 0) {
+					consumed = q.vq_state->last_avail;
+					cnt = ld_vol32(q.doorbell) - consumed;
+				}
+				q.count = __shfl_sync(0xffffffffu, cnt, 0);
+				q.head = __shfl_sync(0xffffffffu, consumed, 0);
+			}
 			uint32_t vq_last_avail = 0, vq_last_used = 0;
 			if (q.mode == QMODE_VRING) {
 				/* spdk_vhost_vq_avail_ring_get (vhost.c:178-211): everything up to avail->idx */
@@ -625,6 +689,10 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 				q.head = vq_last_avail;
 				q.iov_mask = 0xffffffffu;
 				q.iovs += (size_t)blockIdx.x * kPass * kIovRow;	/* this CTA's scratch SG rows */
+			}
+			if (persistent) {
+				if (q.count == 0) continue;
+				progress = true;
 			}
 			/* request slots are prefetched one pass ahead: 4 x 16 B per lane, coalesced
 			 * (vector v = k*32+lane of the pass -> request v/4, quarter v%4) */
@@ -761,7 +829,7 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 					 * fill's completions, then refill */
 					const uint32_t sidx = fills % kStages;
 					Stage &st = sh.stage[sidx];
-					if (fills >= kStages) {
+					if (fills >= kStages && reaped + kStages <= fills) {
 						mbar_wait(&sh.empty[sidx], ((fills / kStages) - 1) & 1);
 						reap_stage(st, lane);
 						reaped++;
@@ -792,6 +860,7 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 						st.vq_state = q.vq_state;
 						st.vq_size = q.vq_size;
 						st.used_base = vq_last_used + done + r0;
+						st.done = persistent ? q.done : nullptr;
 					}
 					__syncwarp();
 					if (lane == 0) mbar_arrive(&sh.full[sidx]);
@@ -800,18 +869,19 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 				}
 			}
 			if (q.mode == QMODE_VRING && lane == 0) q.vq_state->last_avail = (vq_last_avail + q.count) & 0xffff;
+			if (persistent && q.mode == QMODE_SLOTS && lane == 0) q.vq_state->last_avail = q.head + q.count;
 		}
 		/* tell the movers to stop, then publish the completions still in flight */
 		{
 			const uint32_t sidx = fills % kStages;
 			Stage &st = sh.stage[sidx];
-			if (fills >= kStages) {
+			if (fills >= kStages && reaped + kStages <= fills) {
 				mbar_wait(&sh.empty[sidx], ((fills / kStages) - 1) & 1);
 				reap_stage(st, lane);
 				reaped++;
 				__syncwarp();
 			}
-			if (lane == 0) { st.stop = 1; st.nunits = 0; st.nseg = 0; st.nwaves = 1; st.drain = 0; st.ncpl = 0; st.mode = QMODE_SLOTS; }
+			if (lane == 0) { st.stop = 1; st.nunits = 0; st.nseg = 0; st.nwaves = 1; st.drain = 0; st.ncpl = 0; st.mode = QMODE_SLOTS; st.done = nullptr; }
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&sh.full[sidx]);
 		}
@@ -820,6 +890,10 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 			mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
 			reap_stage(sh.stage[sidx], lane);
 			reaped++;
+		}
+		if (persistent && lane == 0) {
+			__threadfence_system();
+			atomicAdd_system(const_cast<uint32_t *>(hdr->exited), 1u);
 		}
 		/* flush counters: one atomic per counter per CTA */
 		st_rb = __reduce_add_sync(0xffffffffu, (uint32_t)(st_rb >> 9));

@@ -84,7 +84,12 @@ struct LunCtx {
 struct KickHeader {
 	uint32_t next;
 	uint32_t nqueues;
-	uint32_t pad[2];
+	/* persistent ("reactor") mode: the kernel stays resident, CTA b polls queues b, b+grid, ... for
+	 * new doorbell values until *stop != 0 (or nothing happened for idle_timeout_ms: watchdog) */
+	uint32_t persistent;
+	uint32_t idle_timeout_ms;
+	const volatile uint32_t *stop;		/* mapped host memory, written by the host */
+	volatile uint32_t *exited;		/* mapped host memory: CTAs that left the poll loop */
 };
 
 /* ring cursors of an attached virtqueue, device-resident so they survive across launches */
@@ -107,6 +112,9 @@ struct QueueDesc {
 	uint32_t mode;			/* QMODE_* */
 	uint32_t iov_limit;		/* entries in the SG table (0: not checked) */
 	uint32_t vq_size;		/* virtqueue mode: a real virtio split ring (linux/virtio_ring.h) */
+	/* persistent mode, slot rings: host-written tail doorbell / device-written completion count */
+	const volatile uint32_t *doorbell;
+	volatile uint32_t *done;
 	const uint8_t *vq_desc;		/* struct vring_desc[vq_size] */
 	const uint8_t *vq_avail;	/* struct vring_avail */
 	uint8_t       *vq_used;		/* struct vring_used */
@@ -153,6 +161,7 @@ struct __align__(16) Stage {
 	uint16_t vq_head[kPass];
 	uint8_t  *vq_used;
 	VqState  *vq_state;
+	volatile uint32_t *done;	/* persistent slot ring: completion counter in host memory */
 	uint32_t vq_size, used_base, mode;
 	uint32_t nseg, nunits, nwaves;
 	uint32_t drain;			/* conflicts with the previous fill: wait for it to finish */

@@ -145,6 +145,13 @@ struct oimgpu_lun {
 	size_t bs_pending = 0;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t bs_uploaded = nullptr;
+	/* persistent poller */
+	struct Door { volatile uint32_t tail; uint32_t pad0[15]; volatile uint32_t done; uint32_t pad1[15]; };
+	Door *h_door = nullptr, *d_door = nullptr;	/* mapped pinned: one doorbell/completion-count pair per queue */
+	volatile uint32_t *h_flags = nullptr;	/* mapped pinned: [0] stop, [16] exited */
+	uint32_t *d_flags = nullptr;
+	bool poller_active = false;
+	uint32_t poller_grid = 0;
 	VqState *d_vq_state = nullptr;		/* [num_queues] ring cursors */
 	oimgpu_iov *d_iov_scratch = nullptr;	/* [grid_cap][32][kIovRow] SG rows built by the parser lanes */
 };
@@ -655,6 +662,14 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 		Q.h_cpls = (oimgpu_cpl *)h;
 		Q.d_cpls = (oimgpu_cpl *)d;
 	}
+	CU_OK(cudaHostAlloc((void **)&L->h_door, sizeof(oimgpu_lun::Door) * num_queues, cudaHostAllocMapped));
+	CU_OK(cudaHostGetDevicePointer((void **)&L->d_door, L->h_door, 0));
+	memset((void *)L->h_door, 0, sizeof(oimgpu_lun::Door) * num_queues);
+	CU_OK(cudaHostAlloc((void **)&L->h_flags, 256, cudaHostAllocMapped));
+	CU_OK(cudaHostGetDevicePointer((void **)&L->d_flags, (void *)L->h_flags, 0));
+	memset((void *)L->h_flags, 0, 256);
+	CU_OK(cudaMalloc((void **)&L->d_vq_state, sizeof(VqState) * num_queues));
+	CU_OK(cudaMemset(L->d_vq_state, 0, sizeof(VqState) * num_queues));
 	int per_sm = 0;
 	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes()));
 	if (per_sm < 1) per_sm = 1;
@@ -669,7 +684,13 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 	if (!L) return -EINVAL;
 	std::lock_guard<std::mutex> lk(g.mu);
 	cudaSetDevice(L->device);
+	if (L->poller_active) {
+		L->h_flags[0] = 1;
+		L->poller_active = false;
+	}
 	cudaStreamSynchronize(L->stream);
+	cudaFreeHost((void *)L->h_door);
+	cudaFreeHost((void *)L->h_flags);
 	if (!L->queues.empty()) cudaFreeHost(L->queues[0].h_reqs);
 	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
 		cudaFreeHost(L->h_kick[k]);
@@ -769,6 +790,21 @@ extern "C" int oimgpu_submit_device(oimgpu_lun *L, uint32_t q, const oimgpu_req 
 extern "C" int oimgpu_kick(oimgpu_lun *L)
 {
 	if (!L) return -EINVAL;
+	if (L->poller_active) {
+		/* the resident kernel is polling: a kick is a doorbell write (after the slot contents) */
+		int n = 0;
+		std::atomic_thread_fence(std::memory_order_release);
+		for (uint32_t q = 0; q < L->num_queues; q++) {
+			Queue &Q = L->queues[q];
+			if (Q.dev_count) return -EBUSY;		/* caller-owned device arrays need a launch */
+			if (Q.tail != Q.kicked) {
+				L->h_door[q].tail = Q.tail;
+				Q.kicked = Q.tail;
+				n++;
+			}
+		}
+		return n;
+	}
 	CU_OK(cudaSetDevice(L->device));
 	const int slot = (int)(L->kicks % oimgpu_lun::kKickSlots);
 	if (L->kicks >= (uint64_t)oimgpu_lun::kKickSlots) CU_OK(cudaEventSynchronize(L->kick_ev[slot]));
@@ -842,6 +878,21 @@ extern "C" int oimgpu_poll(oimgpu_lun *L, uint32_t q, oimgpu_cpl *cpls, uint32_t
 	if (!L || q >= L->num_queues) return -EINVAL;
 	Queue &Q = L->queues[q];
 	if (Q.kicked == Q.reaped) return 0;
+	if (L->poller_active) {
+		uint32_t done = L->h_door[q].done;
+		if (wait) {
+			while ((int32_t)(done - Q.kicked) < 0) {
+				if (L->h_flags[16] >= L->poller_grid) return -ESHUTDOWN;	/* the poller left (watchdog) */
+				done = L->h_door[q].done;
+			}
+		}
+		std::atomic_thread_fence(std::memory_order_acquire);
+		uint32_t n = std::min(max, done - Q.reaped);
+		const uint32_t qmask = L->queue_size - 1;
+		for (uint32_t i = 0; i < n; i++) cpls[i] = Q.h_cpls[(Q.reaped + i) & qmask];
+		Q.reaped += n;
+		return (int)n;
+	}
 	if (wait) {
 		int rc = oimgpu_lun_sync(L);
 		if (rc) return rc;
@@ -874,6 +925,7 @@ extern "C" int oimgpu_submit_batch(oimgpu_lun *L, uint32_t nq, uint32_t per_q, c
 	/* Host arrays.  The SG *addresses* stay host pointers (payload is loaded/stored by the movers
 	 * straight from/to pinned client memory); the request, SG and completion *arrays* are moved by the
 	 * copy engine so that the parser never waits on a PCIe read. */
+	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	if (L->bs_pending) return -EAGAIN;
 	const size_t n = (size_t)nq * per_q;
@@ -950,6 +1002,7 @@ extern "C" int oimgpu_submit_batch(oimgpu_lun *L, uint32_t nq, uint32_t per_q, c
 /* completes a host-array batch: wait, then hand the completions to the caller's array */
 static int batch_finish(oimgpu_lun *L)
 {
+	if (L->poller_active) return -EBUSY;	/* the stream never drains while the poller is resident */
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
 	if (L->bs_pending && L->bs_user_cpls) memcpy(L->bs_user_cpls, L->bs_h_cpls, L->bs_pending * sizeof(oimgpu_cpl));
@@ -969,6 +1022,7 @@ extern "C" int oimgpu_submit_and_wait(oimgpu_lun *L, uint32_t nq, uint32_t per_q
 extern "C" int oimgpu_lun_iostat(oimgpu_lun *L, oimgpu_iostat *out)
 {
 	if (!L || !out) return -EINVAL;
+	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
 	LunCtx c;
@@ -990,6 +1044,7 @@ extern "C" int oimgpu_lun_iostat(oimgpu_lun *L, oimgpu_iostat *out)
 extern "C" int oimgpu_lun_set_removed(oimgpu_lun *L, int removed, int lun_removed)
 {
 	if (!L) return -EINVAL;
+	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
 	L->h_ctx.removed = removed != 0;
@@ -1005,6 +1060,7 @@ extern "C" int oimgpu_lun_set_removed(oimgpu_lun *L, int removed, int lun_remove
 extern "C" int oimgpu_lun_set_mem_table(oimgpu_lun *L, const oimgpu_mem_region *regions, uint32_t nregions)
 {
 	if (!L || (!regions && nregions) || nregions > (uint32_t)kMaxRegions) return -EINVAL;
+	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
 	L->h_ctx.nregions = nregions;
@@ -1024,12 +1080,9 @@ extern "C" int oimgpu_vq_attach(oimgpu_lun *L, uint32_t q, const void *desc, con
 {
 	if (!L || q >= L->num_queues || !desc || !avail || !used) return -EINVAL;
 	if (size == 0 || size > OIMGPU_MAX_VQ_SIZE || (size & (size - 1))) return -EINVAL;
+	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
-	if (!L->d_vq_state) {
-		CU_OK(cudaMalloc((void **)&L->d_vq_state, sizeof(VqState) * L->num_queues));
-		CU_OK(cudaMemset(L->d_vq_state, 0, sizeof(VqState) * L->num_queues));
-	}
 	if (!L->d_iov_scratch) {
 		CU_OK(cudaMalloc((void **)&L->d_iov_scratch, sizeof(oimgpu_iov) * (size_t)L->grid_cap * kPass * kIovRow));
 	}
@@ -1047,6 +1100,7 @@ extern "C" int oimgpu_vq_attach(oimgpu_lun *L, uint32_t q, const void *desc, con
 extern "C" int oimgpu_vq_detach(oimgpu_lun *L, uint32_t q, uint16_t *last_avail_idx, uint16_t *last_used_idx)
 {
 	if (!L || q >= L->num_queues || !L->queues[q].vq_size) return -EINVAL;
+	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
 	VqState st;
@@ -1065,12 +1119,112 @@ extern "C" int oimgpu_vq_detach(oimgpu_lun *L, uint32_t q, uint16_t *last_avail_
 extern "C" int oimgpu_vq_kick(oimgpu_lun *L)
 {
 	if (!L) return -EINVAL;
+	if (L->poller_active) return 0;	/* the resident kernel sees avail->idx by itself */
 	int n = 0;
 	for (auto &Q : L->queues) {
 		if (Q.vq_size) { Q.vq_pending = true; n++; }
 	}
 	if (!n) return 0;
 	return oimgpu_kick(L);
+}
+
+/* ---- persistent poller ("one reactor kernel per LUN") ------------------------------------------------ */
+
+/* Launch oim_lun_queue_kernel in persistent mode on the LUN's stream: it stays resident and serves the
+ * library rings of every queue (doorbell = tail index in mapped host memory) and every attached
+ * virtqueue (doorbell = the guest's avail->idx) until oimgpu_lun_stop_poller().  While it runs,
+ * oimgpu_kick() is a doorbell write and oimgpu_poll() reads the completion counter the kernel
+ * publishes; nothing is launched per request.  idle_timeout_ms != 0 arms a watchdog that lets the
+ * kernel leave after that long without work (tests use it so a lost host cannot wedge the GPU). */
+extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_t idle_timeout_ms)
+{
+	if (!L) return -EINVAL;
+	if (L->poller_active) return -EALREADY;
+	CU_OK(cudaSetDevice(L->device));
+	CU_OK(cudaStreamSynchronize(L->stream));
+	if (!L->d_iov_scratch) {
+		CU_OK(cudaMalloc((void **)&L->d_iov_scratch, sizeof(oimgpu_iov) * (size_t)L->grid_cap * kPass * kIovRow));
+	}
+	const int slot = (int)(L->kicks % oimgpu_lun::kKickSlots);
+	QueueDesc *h_desc = (QueueDesc *)(L->h_kick[slot] + sizeof(KickHeader));
+	uint32_t nd = 0;
+	std::vector<VqState> cursors(L->num_queues);
+	CU_OK(cudaMemcpy(cursors.data(), L->d_vq_state, sizeof(VqState) * L->num_queues, cudaMemcpyDeviceToHost));
+	std::vector<std::pair<uint32_t, VqState>> ring_cursor;
+	for (uint32_t q = 0; q < L->num_queues; q++) {
+		Queue &Q = L->queues[q];
+		if (Q.dev_count || Q.tail != Q.kicked) return -EBUSY;	/* drain pending launches first */
+		if (Q.vq_size) {
+			QueueDesc &D = h_desc[nd++];
+			memset(&D, 0, sizeof(D));
+			D.mode = QMODE_VRING;
+			D.iovs = L->d_iov_scratch;
+			D.vq_size = Q.vq_size;
+			D.vq_desc = Q.vq_desc;
+			D.vq_avail = Q.vq_avail;
+			D.vq_used = Q.vq_used;
+			D.vq_state = L->d_vq_state + q;
+		} else {
+			QueueDesc &D = h_desc[nd++];
+			memset(&D, 0, sizeof(D));
+			D.reqs = Q.d_reqs;
+			D.iovs = Q.d_iovs;
+			D.cpls = Q.d_cpls;
+			D.ring_mask = L->queue_size - 1;
+			D.iov_mask = L->iov_cap - 1;
+			D.doorbell = &L->d_door[q].tail;
+			D.done = &L->d_door[q].done;
+			D.vq_state = L->d_vq_state + q;
+			/* everything kicked so far was served by launches: the poller starts from there */
+			L->h_door[q].tail = Q.kicked;
+			L->h_door[q].done = Q.kicked;
+			cursors[q].last_avail = Q.kicked;
+		}
+	}
+	/* slot-ring cursors live in the same VqState array (virtqueues keep theirs) */
+	for (uint32_t q = 0; q < L->num_queues; q++) {
+		if (!L->queues[q].vq_size) CU_OK(cudaMemcpy(L->d_vq_state + q, &cursors[q], sizeof(VqState), cudaMemcpyHostToDevice));
+	}
+	uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap);
+	if (max_ctas) grid = std::min(grid, max_ctas);
+	L->h_flags[0] = 0;
+	L->h_flags[16] = 0;
+	KickHeader *kh = (KickHeader *)L->h_kick[slot];
+	memset(kh, 0, sizeof(*kh));
+	kh->next = grid;
+	kh->nqueues = nd;
+	kh->persistent = 1;
+	kh->idle_timeout_ms = idle_timeout_ms;
+	kh->stop = L->d_flags;
+	kh->exited = L->d_flags + 16;
+	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
+	oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	CU_OK(cudaGetLastError());
+	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
+	L->kicks++;
+	L->launches++;
+	L->poller_grid = grid;
+	L->poller_active = true;
+	return (int)grid;
+}
+
+extern "C" int oimgpu_lun_stop_poller(oimgpu_lun *L)
+{
+	if (!L) return -EINVAL;
+	if (!L->poller_active) return 0;
+	CU_OK(cudaSetDevice(L->device));
+	std::atomic_thread_fence(std::memory_order_seq_cst);
+	L->h_flags[0] = 1;
+	L->poller_active = false;
+	CU_OK(cudaStreamSynchronize(L->stream));
+	return 0;
+}
+
+/* 1 while the resident kernel is polling, 0 after it left (stop or watchdog) */
+extern "C" int oimgpu_lun_poller_running(oimgpu_lun *L)
+{
+	if (!L) return -EINVAL;
+	return L->poller_active && L->h_flags[16] < L->poller_grid;
 }
 
 /* ---- device-timed region helpers (bench.py times on the LUN's own stream) ------------------------- */

@@ -86,6 +86,9 @@ SYMBOLS = [
     ("oimgpu_lun_iostat", _I, [_VP, C.POINTER(IoStat)]),
     ("oimgpu_lun_stream", _VP, [_VP]),
     ("oimgpu_lun_set_removed", _I, [_VP, _I, _I]),
+    ("oimgpu_lun_start_poller", _I, [_VP, _U32, _U32]),
+    ("oimgpu_lun_stop_poller", _I, [_VP]),
+    ("oimgpu_lun_poller_running", _I, [_VP]),
     ("oimgpu_lun_set_mem_table", _I, [_VP, _VP, _U32]),
     ("oimgpu_vq_attach", _I, [_VP, _U32, _VP, _VP, _VP, _U32, C.c_uint16, C.c_uint16]),
     ("oimgpu_vq_detach", _I, [_VP, _U32, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]),
@@ -343,6 +346,16 @@ class Lun:
 
     def set_removed(self, removed: bool = True, lun_removed: bool = False) -> None:
         _chk(load().oimgpu_lun_set_removed(self.h, int(removed), int(lun_removed)), "set_removed")
+
+    # ---- persistent poller ----
+    def start_poller(self, max_ctas: int = 0, idle_timeout_ms: int = 0) -> int:
+        return _chk(load().oimgpu_lun_start_poller(self.h, max_ctas, idle_timeout_ms), "start_poller")
+
+    def stop_poller(self) -> None:
+        _chk(load().oimgpu_lun_stop_poller(self.h), "stop_poller")
+
+    def poller_running(self) -> bool:
+        return bool(_chk(load().oimgpu_lun_poller_running(self.h), "poller_running"))
 
     # ---- virtqueue mode ----
     def set_mem_table(self, regions: np.ndarray) -> None:
