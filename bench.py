@@ -50,6 +50,7 @@ def parse_args():
     p.add_argument("--no-seq", action="store_true", help="skip the 128 KiB sequential leg")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-lat", action="store_true", help="skip the single-queue qd=32 closed-loop leg")
     return p.parse_args()
 
 
@@ -382,6 +383,36 @@ def run_ours(args, rank, world, local):
                        "completion records copied back; PCIe D2H ceiling of the box 57 GB/s (cudaMemcpy), "
                        "52.7 GB/s for SM-originated stores (tools/pcie_store_bench.cu)"}
 
+    # ---- latency-bound corner: ONE request queue, qd=32, closed loop (submit 32 -> wait -> submit 32 ...) ----
+    lat = None
+    if not args.no_lat:
+        rounds = 300
+        lt = traces.uniform_trace(32 * rounds, NUM_BLOCKS, io_blocks=8, pattern="randread", seed=plan["e2e_seed"] + 7)
+        lbuf = torch.empty(lt.arena_bytes, dtype=torch.uint8).pin_memory()
+        liov = lt.bind(lbuf.data_ptr())
+        lat = {}
+        lcpl = np.zeros(32, dtype=abi.cpl_dtype)
+        Lc = lib.load()
+        for mode in ("launch_per_kick", "persistent_poller"):
+            lq = lib.Lun(plan["ctrlr"], plan["target"], num_queues=1, queue_size=64)
+            if mode == "persistent_poller":
+                lq.start_poller(idle_timeout_ms=5000)
+            try:
+                for phase in ("warm", "timed"):
+                    t0 = time.perf_counter()
+                    for r in range(rounds if phase == "timed" else 20):
+                        # one C call per round trip: 32 requests in, 32 completions out
+                        rc = Lc.oimgpu_submit_and_wait(lq.h, 1, 32, lt.reqs[r * 32:].ctypes.data, liov.ctypes.data,
+                                                       len(liov), lcpl.ctypes.data, abi.MEM_HOST)
+                        assert rc == 0 and not lcpl["status"].any()
+                    dt = time.perf_counter() - t0
+            finally:
+                if mode == "persistent_poller":
+                    lq.stop_poller()
+                lq.close()
+            lat[mode] = {"iops": 32 * rounds / dt, "us_per_round_trip": dt / rounds * 1e6}
+        lat["workload"] = "1 queue, qd=32, 4 KiB random read, closed loop of oimgpu_submit_and_wait calls, pinned client buffers"
+
     # ---- second metric: 128 KiB sequential write (runs last: it overwrites the patterned store) ----
     seq = None
     if not args.no_seq:
@@ -418,7 +449,7 @@ def run_ours(args, rank, world, local):
                          "traffic": measured_traffic("rand4k", n), "peak_source": peak_src,
                          "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
-            "seq128k": seq, "e2e": e2e, "cpu_baseline": cpu,
+            "seq128k": seq, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:

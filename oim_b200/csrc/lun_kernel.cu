@@ -932,12 +932,16 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 					const uint32_t nbytes = (uint32_t)min((uint64_t)kUnitBytes, g.len - off);
 					const uint8_t *src = g.src;
 					uint8_t *dst = g.dst;
-					if (src) move_unit(dst + off, src + off, nbytes, lane);
-					else zero_unit(dst + off, nbytes, lane);
-					if (g.mirror && nrep > 1) {
-						/* mirrored bdev: the same bytes go to every peer replica over NVLink (P2P stores) */
+					if (!(g.mirror && nrep > 1)) {
+						if (src) move_unit(dst + off, src + off, nbytes, lane);
+						else zero_unit(dst + off, nbytes, lane);
+					} else {
+						/* mirrored bdev: the same bytes go to every peer replica over NVLink (P2P stores)
+						 * in the same step; replica 1 shares the loaded registers with the local store */
 						const uint64_t soff = (uint64_t)(dst - lun->store[0]) + off;
-						for (uint32_t rep = 1; rep < nrep; rep++) {
+						if (src) move_unit(dst + off, src + off, nbytes, lane, lun->store[1] + soff);
+						else { zero_unit(dst + off, nbytes, lane); zero_unit(lun->store[1] + soff, nbytes, lane); }
+						for (uint32_t rep = 2; rep < nrep; rep++) {
 							if (src) move_unit(lun->store[rep] + soff, src + off, nbytes, lane);
 							else zero_unit(lun->store[rep] + soff, nbytes, lane);
 						}

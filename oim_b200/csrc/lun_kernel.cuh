@@ -210,8 +210,10 @@ __device__ __forceinline__ uint32_t be32(const uint8_t *p)
 }
 __device__ __forceinline__ uint64_t be64(const uint8_t *p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
 
-/* Move `n` (<= kUnitBytes) bytes with one warp.  Fast path: both sides 16-byte aligned. */
-__device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
+/* Move `n` (<= kUnitBytes) bytes with one warp.  Fast path: both sides 16-byte aligned.
+ * dst2 != nullptr (mirrored bdev, same alignment as dst): the registers are stored twice, locally
+ * and into the peer replica over NVLink - one load, two stores, no second pass. */
+__device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint32_t n, int lane, uint8_t *dst2 = nullptr)
 {
 	if ((((uintptr_t)dst | (uintptr_t)src | n) & 15) == 0) {
 		int4 r[kUnitBytes / 512];
@@ -226,7 +228,17 @@ __device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint
 			uint32_t v = lane + 32 * k;
 			if (v < nv) st_cg16(dst + (size_t)v * 16, r[k]);
 		}
+		if (dst2) {
+#pragma unroll
+			for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
+				uint32_t v = lane + 32 * k;
+				if (v < nv) st_cg16(dst2 + (size_t)v * 16, r[k]);
+			}
+		}
 		return;
+	}
+	if (dst2) {	/* unaligned: the generic path once per destination */
+		move_unit(dst2, src, n, lane);
 	}
 	/* byte-granular SG element (SURVEY.md §7 "unaligned SG elements"): peel to a 16-byte aligned
 	 * destination, then aligned 16-byte stores fed by the widest loads the source allows */

@@ -925,7 +925,34 @@ extern "C" int oimgpu_submit_batch(oimgpu_lun *L, uint32_t nq, uint32_t per_q, c
 	/* Host arrays.  The SG *addresses* stay host pointers (payload is loaded/stored by the movers
 	 * straight from/to pinned client memory); the request, SG and completion *arrays* are moved by the
 	 * copy engine so that the parser never waits on a PCIe read. */
-	if (L->poller_active) return -EBUSY;
+	if (L->poller_active) {
+		/* resident kernel: requests go through the host-visible rings, the kick is a doorbell write.
+		 * Every queue's requests index the one SG table of the call. */
+		for (uint32_t q = 0; q < nq; q++) {
+			const oimgpu_req *r = reqs + (size_t)q * per_q;
+			uint32_t lo = 0xffffffffu, hi = 0;
+			for (uint32_t i = 0; i < per_q; i++) {
+				if (r[i].iovcnt == 0) continue;
+				lo = std::min(lo, r[i].iov_start);
+				hi = std::max(hi, r[i].iov_start + r[i].iovcnt);
+			}
+			if (lo == 0xffffffffu) lo = hi = 0;
+			if (hi > niovs) return -EINVAL;
+			Queue &Q = L->queues[q];
+			if (per_q > L->queue_size - (Q.tail - Q.reaped)) return -EAGAIN;
+			if (hi - lo > L->iov_cap) return -E2BIG;
+			const uint32_t qmask = L->queue_size - 1, imask = L->iov_cap - 1;
+			for (uint32_t i = lo; i < hi; i++) Q.h_iovs[(Q.iov_tail + (i - lo)) & imask] = iovs[i];
+			for (uint32_t i = 0; i < per_q; i++) {
+				oimgpu_req t = r[i];
+				t.iov_start = t.iov_start - lo + Q.iov_tail;
+				Q.h_reqs[(Q.tail + i) & qmask] = t;
+			}
+			Q.tail += per_q;
+			Q.iov_tail += hi - lo;
+		}
+		return oimgpu_kick(L);
+	}
 	CU_OK(cudaSetDevice(L->device));
 	if (L->bs_pending) return -EAGAIN;
 	const size_t n = (size_t)nq * per_q;
@@ -1016,6 +1043,17 @@ extern "C" int oimgpu_submit_and_wait(oimgpu_lun *L, uint32_t nq, uint32_t per_q
 {
 	int rc = oimgpu_submit_batch(L, nq, per_q, reqs, iovs, niovs, cpls, mem);
 	if (rc < 0) return rc;
+	if (L->poller_active && mem == OIMGPU_MEM_HOST) {
+		for (uint32_t q = 0; q < nq; q++) {
+			uint32_t got = 0;
+			while (got < per_q) {
+				int n = oimgpu_poll(L, q, cpls + (size_t)q * per_q + got, per_q - got, 1);
+				if (n < 0) return n;
+				got += (uint32_t)n;
+			}
+		}
+		return 0;
+	}
 	return oimgpu_lun_sync(L);
 }
 
