@@ -158,8 +158,15 @@ int  oimgpu_abi_version(void);
 /* Initialise on the given CUDA device ordinals (devices==NULL: current device only).
  * Fails with -ENODEV when no CUDA device is usable: there is no CPU fallback. */
 int  oimgpu_init(const int *devices, int ndevices);
+/* Control plane only (protocol tests without a GPU): no stores are allocated, every data-path call
+ * returns -ENODEV.  Not a CPU implementation of the path. */
+int  oimgpu_init_control_only(void);
 void oimgpu_fini(void);
 int  oimgpu_device_count(void);
+/* vhost -S <dir> and -m <mask> of S/app/vhost/vhost.c:43-48: socket directory reported by
+ * get_vhost_controllers / stripped from controller names, and the application core mask controller
+ * cpumasks must be a subset of. */
+int  oimgpu_set_socket_dir(const char *dir, const char *app_core_mask);
 const char *oimgpu_version_string(void);
 
 /* ---- bdev control ----------------------------------------------------------------------- */
@@ -178,7 +185,9 @@ int oimgpu_bdev_create_rbd(const char *name, const char *pool_name, const char *
 /* R-way mirrored malloc bdev: replica r lives on devices[r]; writes fan out over NVLink. */
 int oimgpu_bdev_create_mirror(const char *name, uint64_t num_blocks, uint32_t block_size,
 			      const int *devices, int nreplicas, char *name_out, size_t name_cap);
-int oimgpu_bdev_delete(const char *name);			/* -ENODEV if unknown, -EBUSY if attached */
+int oimgpu_bdev_delete(const char *name);			/* -ENODEV if unknown; attached targets are hot-removed
+								 * (as spdk_bdev_unregister does); -EBUSY while a
+								 * data path (oimgpu_lun) is open on it */
 int oimgpu_bdev_get(const char *name, struct oimgpu_bdev_info *out);	/* -ENODEV if unknown */
 int oimgpu_bdev_list(struct oimgpu_bdev_info *out, int max);	/* returns count */
 /* test/digest helpers: raw access to the backing store of replica r (synchronous) */

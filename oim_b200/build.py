@@ -33,14 +33,34 @@ def build(force: bool = False, verbose: bool = False, defs: str | None = None, o
     if os.environ.get("OIM_LIB_PATH") and out == LIB:
         return os.environ["OIM_LIB_PATH"]           # a tuning build was selected explicitly
     if not force and not defs and out == LIB and not _stale():
+        build_daemon()
         return LIB
     cmd = [NVCC, *FLAGS, *defs.split(), "-Xptxas", "-v", "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stderr[-3000:])
+    if out == LIB:
+        build_daemon()
+    return out
+
+
+DAEMON = os.path.join(HERE, "oim-gpu-vhost")
+DAEMON_SRC = os.path.join(HERE, "daemon", "oim_gpu_vhost.cpp")
+
+
+def build_daemon(force: bool = False) -> str:
+    """the JSON-RPC daemon (drop-in for SPDK's `vhost` binary): plain C++ on top of the C ABI"""
+    if not force and os.path.exists(DAEMON) and os.path.getmtime(DAEMON) >= max(
+            os.path.getmtime(DAEMON_SRC), os.path.getmtime(LIB), os.path.getmtime(os.path.join(ROOT, "include", "oimgpu.h"))):
+        return DAEMON
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", DAEMON, DAEMON_SRC,
+           "-L", HERE, "-loimgpu", "-Wl,-rpath,$ORIGIN"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
-    if verbose:
-        print(out.stderr[-3000:])
-    return out
+        raise RuntimeError("daemon build failed:\n" + out.stdout[-3000:] + out.stderr[-3000:])
+    return DAEMON
 
 
 if __name__ == "__main__":

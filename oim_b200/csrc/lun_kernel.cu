@@ -587,11 +587,26 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 	}
 }
 
+/* mirrored bdev (config 5): the same bytes go to every replica in one step - local HBM and, by P2P
+ * stores over NVLink, the peers.  Replica 1 shares the loaded registers with the local store (one load,
+ * two stores).  Out of line so that it does not weigh on the plain mover loop's registers. */
+static __device__ __forceinline__ void mirror_unit(const LunCtx &L, uint8_t *dst, const uint8_t *src, uint64_t off,
+						uint32_t nbytes, int lane, uint32_t nrep)
+{
+	const uint64_t soff = (uint64_t)(dst - L.store[0]) + off;
+	if (src) move_unit(dst + off, src + off, nbytes, lane, L.store[1] + soff);
+	else { zero_unit(dst + off, nbytes, lane); zero_unit(L.store[1] + soff, nbytes, lane); }
+	for (uint32_t rep = 2; rep < nrep; rep++) {
+		if (src) move_unit(L.store[rep] + soff, src + off, nbytes, lane);
+		else zero_unit(L.store[rep] + soff, nbytes, lane);
+	}
+}
+
 #ifndef OIM_MIN_BLOCKS
 #define OIM_MIN_BLOCKS 2	/* 128 registers: the mover loop must stay spill-free (80-register builds lose ~25%) */
 #endif
-__global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
-oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
+template <bool kMirrored>
+__device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	CtaShared &sh = *reinterpret_cast<CtaShared *>(smem_raw);
@@ -932,19 +947,11 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 					const uint32_t nbytes = (uint32_t)min((uint64_t)kUnitBytes, g.len - off);
 					const uint8_t *src = g.src;
 					uint8_t *dst = g.dst;
-					if (!(g.mirror && nrep > 1)) {
+					if (!kMirrored || !g.mirror) {
 						if (src) move_unit(dst + off, src + off, nbytes, lane);
 						else zero_unit(dst + off, nbytes, lane);
 					} else {
-						/* mirrored bdev: the same bytes go to every peer replica over NVLink (P2P stores)
-						 * in the same step; replica 1 shares the loaded registers with the local store */
-						const uint64_t soff = (uint64_t)(dst - lun->store[0]) + off;
-						if (src) move_unit(dst + off, src + off, nbytes, lane, lun->store[1] + soff);
-						else { zero_unit(dst + off, nbytes, lane); zero_unit(lun->store[1] + soff, nbytes, lane); }
-						for (uint32_t rep = 2; rep < nrep; rep++) {
-							if (src) move_unit(lun->store[rep] + soff, src + off, nbytes, lane);
-							else zero_unit(lun->store[rep] + soff, nbytes, lane);
-						}
+						mirror_unit(*lun, dst, src, off, nbytes, lane, nrep);
 					}
 				}
 				if (nw > 1) movers_barrier();
@@ -953,6 +960,20 @@ oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 			if (lane == 0) mbar_arrive(&sh.empty[sidx]);
 		}
 	}
+}
+
+/* the plain kernel carries no mirror code at all (a call in the mover loop costs it ~25 %: the
+ * caller-saved data registers get spilled); mirrored bdevs use the second instantiation */
+__global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
+oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
+{
+	lun_queue_body<false>(lun, hdr, queues);
+}
+
+__global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
+oim_lun_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
+{
+	lun_queue_body<true>(lun, hdr, queues);
 }
 
 /* struct spdk_copy_engine.copy / .fill (S/include/spdk_internal/copy_engine.h:47-53) for

@@ -210,38 +210,10 @@ __device__ __forceinline__ uint32_t be32(const uint8_t *p)
 }
 __device__ __forceinline__ uint64_t be64(const uint8_t *p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
 
-/* Move `n` (<= kUnitBytes) bytes with one warp.  Fast path: both sides 16-byte aligned.
- * dst2 != nullptr (mirrored bdev, same alignment as dst): the registers are stored twice, locally
- * and into the peer replica over NVLink - one load, two stores, no second pass. */
-__device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint32_t n, int lane, uint8_t *dst2 = nullptr)
+/* byte-granular SG element (SURVEY.md §7 "unaligned SG elements"): peel to a 16-byte aligned
+ * destination, then aligned 16-byte stores fed by the widest loads the source allows */
+__device__ __forceinline__ void move_unit_unaligned(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
 {
-	if ((((uintptr_t)dst | (uintptr_t)src | n) & 15) == 0) {
-		int4 r[kUnitBytes / 512];
-		const uint32_t nv = n >> 4;
-#pragma unroll
-		for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
-			uint32_t v = lane + 32 * k;
-			if (v < nv) r[k] = ld_cg16(src + (size_t)v * 16);
-		}
-#pragma unroll
-		for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
-			uint32_t v = lane + 32 * k;
-			if (v < nv) st_cg16(dst + (size_t)v * 16, r[k]);
-		}
-		if (dst2) {
-#pragma unroll
-			for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
-				uint32_t v = lane + 32 * k;
-				if (v < nv) st_cg16(dst2 + (size_t)v * 16, r[k]);
-			}
-		}
-		return;
-	}
-	if (dst2) {	/* unaligned: the generic path once per destination */
-		move_unit(dst2, src, n, lane);
-	}
-	/* byte-granular SG element (SURVEY.md §7 "unaligned SG elements"): peel to a 16-byte aligned
-	 * destination, then aligned 16-byte stores fed by the widest loads the source allows */
 	uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
 	if (head > n) head = n;
 	if ((uint32_t)lane < head) dst[lane] = ld_cg8(src + lane);
@@ -270,6 +242,37 @@ __device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint
 	}
 	const uint32_t tail = n & 15;
 	if ((uint32_t)lane < tail) dst[(size_t)nv * 16 + lane] = ld_cg8(src + (size_t)nv * 16 + lane);
+}
+
+/* Move `n` (<= kUnitBytes) bytes with one warp.  Fast path: both sides 16-byte aligned.
+ * dst2 != nullptr (mirrored bdev, same alignment as dst): the registers are stored twice, locally
+ * and into the peer replica over NVLink - one load, two stores, no second pass. */
+__device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint32_t n, int lane, uint8_t *dst2 = nullptr)
+{
+	if ((((uintptr_t)dst | (uintptr_t)src | n) & 15) == 0) {
+		int4 r[kUnitBytes / 512];
+		const uint32_t nv = n >> 4;
+#pragma unroll
+		for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
+			uint32_t v = lane + 32 * k;
+			if (v < nv) r[k] = ld_cg16(src + (size_t)v * 16);
+		}
+#pragma unroll
+		for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
+			uint32_t v = lane + 32 * k;
+			if (v < nv) st_cg16(dst + (size_t)v * 16, r[k]);
+		}
+		if (dst2) {
+#pragma unroll
+			for (int k = 0; k < (int)(kUnitBytes / 512); k++) {
+				uint32_t v = lane + 32 * k;
+				if (v < nv) st_cg16(dst2 + (size_t)v * 16, r[k]);
+			}
+		}
+		return;
+	}
+	move_unit_unaligned(dst, src, n, lane);
+	if (dst2) move_unit_unaligned(dst2, src, n, lane);
 }
 
 /* mem_copy_fill with fill == 0 (copy_engine.c:128-140): zero `n` bytes; block-aligned by construction */

@@ -26,6 +26,7 @@
 
 namespace oimgpu {
 __global__ void oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
+__global__ void oim_lun_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_copy_kernel(uint8_t *dst, const uint8_t *src, uint64_t nbytes);
 __global__ void oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes);
 size_t lun_kernel_smem_bytes();
@@ -62,6 +63,7 @@ struct Bdev {
 	uint64_t num_blocks = 0;
 	uint32_t block_size = 0;
 	int claimed = 0;	/* number of SCSI targets built on it */
+	int open_luns = 0;	/* oimgpu_lun handles */
 	std::vector<int> devices;	/* replica r lives on devices[r] */
 	std::vector<uint8_t *> stores;
 };
@@ -69,14 +71,20 @@ struct Bdev {
 struct Ctrlr {
 	std::string name, cpumask;
 	std::string targets[OIMGPU_CTRLR_MAX_DEVS];	/* bdev name or "" */
+	int scsi_id[OIMGPU_CTRLR_MAX_DEVS] = {};	/* spdk_scsi_dev.id: slot in the global device table */
 };
 
 struct Registry {
 	std::mutex mu;
 	bool inited = false;
+	bool control_only = false;	/* wire-protocol testing without a GPU: no stores, no data path */
 	std::vector<Device> devices;
 	std::map<std::string, std::unique_ptr<Bdev>> bdevs;
 	std::map<std::string, std::unique_ptr<Ctrlr>> ctrlrs;
+	std::vector<std::string> bdev_order, ctrlr_order;	/* registration order, as SPDK's TAILQs list them */
+	bool scsi_slot_used[1024] = {};	/* g_spdk_scsi.dev[SPDK_SCSI_MAX_DEVS]: ids are the lowest free slot (S/lib/scsi/dev.c:49-66) */
+	std::string socket_dir;		/* vhost -S <dir>: prefix of controller socket paths (vhost.c:1185-1205) */
+	unsigned long long app_core_mask = 0x1;	/* spdk_app_get_core_mask(): default -m 0x1 */
 	int malloc_disk_count = 0;	/* bdev_malloc.c:93 */
 	int rbd_count = 0;
 	std::map<void *, size_t> registered;
@@ -253,18 +261,38 @@ extern "C" int oimgpu_init(const int *devices, int ndevices)
 	return 0;
 }
 
+/* Control plane only: bdev/controller bookkeeping for protocol tests on a machine without a GPU.
+ * No backing store is allocated and every data-path entry point fails with -ENODEV; this is NOT a
+ * CPU implementation of the path. */
+extern "C" int oimgpu_init_control_only(void)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (g.inited) return g.control_only ? 0 : -EBUSY;
+	Device d;
+	d.ordinal = 0;
+	d.sm_count = 0;
+	g.devices.push_back(d);
+	g.control_only = true;
+	g.inited = true;
+	return 0;
+}
+
 extern "C" void oimgpu_fini(void)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (!g.inited) return;
 	for (auto &kv : g.bdevs) {
-		for (size_t r = 0; r < kv.second->stores.size(); r++) {
+		for (size_t r = 0; r < kv.second->stores.size() && !g.control_only; r++) {
 			cudaSetDevice(kv.second->devices[r]);
 			cudaFree(kv.second->stores[r]);
 		}
 	}
+	g.control_only = false;
 	g.bdevs.clear();
 	g.ctrlrs.clear();
+	g.bdev_order.clear();
+	g.ctrlr_order.clear();
+	memset(g.scsi_slot_used, 0, sizeof(g.scsi_slot_used));
 	g.devices.clear();
 	g.malloc_disk_count = g.rbd_count = 0;
 	g.inited = false;
@@ -286,6 +314,10 @@ static int pick_device(int device)
 
 static int alloc_store(int ordinal, uint64_t bytes, uint8_t **out)
 {
+	if (g.control_only) {
+		*out = nullptr;
+		return 0;
+	}
 	CU_OK(cudaSetDevice(ordinal));
 	cudaError_t e = cudaMalloc((void **)out, bytes);
 	if (e != cudaSuccess) {
@@ -331,6 +363,7 @@ static int create_bdev_locked(const char *name, const char *uuid, uint64_t num_b
 	}
 	copy_str(name_out, name_cap, nm);
 	g.bdevs[nm] = std::move(b);
+	g.bdev_order.push_back(nm);
 	return 0;
 }
 
@@ -396,8 +429,18 @@ extern "C" int oimgpu_bdev_delete(const char *name)
 	if (!g.inited) return -ENODEV;
 	auto it = g.bdevs.find(name ? name : "");
 	if (it == g.bdevs.end()) return -ENODEV;
-	if (it->second->claimed) return -EBUSY;
-	for (size_t r = 0; r < it->second->stores.size(); r++) {
+	if (it->second->open_luns) return -EBUSY;	/* a data path is open on it */
+	/* spdk_bdev_unregister hot-removes the SCSI LUNs built on the bdev (lun.c:213-260): the targets go */
+	for (auto &kv : g.ctrlrs) {
+		for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+			if (kv.second->targets[t] == it->first) {
+				g.scsi_slot_used[kv.second->scsi_id[t]] = false;
+				kv.second->targets[t].clear();
+			}
+		}
+	}
+	g.bdev_order.erase(std::remove(g.bdev_order.begin(), g.bdev_order.end(), it->first), g.bdev_order.end());
+	for (size_t r = 0; r < it->second->stores.size() && !g.control_only; r++) {
 		cudaSetDevice(it->second->devices[r]);
 		cudaFree(it->second->stores[r]);
 		g.devices[find_device_slot(it->second->devices[r])].bytes_allocated -=
@@ -415,7 +458,7 @@ static void fill_bdev_info(const Bdev &b, oimgpu_bdev_info *o)
 	copy_str(o->uuid, sizeof(o->uuid), b.uuid);
 	o->num_blocks = b.num_blocks;
 	o->block_size = b.block_size;
-	o->claimed = b.claimed != 0;
+	o->claimed = 0;	/* SCSI LUNs open the bdev without claiming it (lun.c:342): get_bdevs says false */
 	o->device = b.devices[0];
 	o->replicas = (uint32_t)b.stores.size();
 	o->device_ptr = (uint64_t)(uintptr_t)b.stores[0];
@@ -435,8 +478,8 @@ extern "C" int oimgpu_bdev_list(oimgpu_bdev_info *out, int max)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
 	int n = 0;
-	for (auto &kv : g.bdevs) {
-		if (out && n < max) fill_bdev_info(*kv.second, &out[n]);
+	for (auto &nm : g.bdev_order) {
+		if (out && n < max) fill_bdev_info(*g.bdevs[nm], &out[n]);
 		n++;
 	}
 	return n;
@@ -445,7 +488,7 @@ extern "C" int oimgpu_bdev_list(oimgpu_bdev_info *out, int max)
 static int raw_access(const char *name, int replica, uint64_t offset, void *host, uint64_t len, bool write)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
-	if (!g.inited) return -ENODEV;
+	if (!g.inited || g.control_only) return -ENODEV;
 	auto it = g.bdevs.find(name ? name : "");
 	if (it == g.bdevs.end()) return -ENODEV;
 	Bdev &b = *it->second;
@@ -476,23 +519,47 @@ extern "C" int oimgpu_bdev_write_raw(const char *name, int replica, uint64_t off
 static std::string ctrlr_key(const char *ctrlr)
 {
 	std::string s = ctrlr ? ctrlr : "";
-	size_t p = s.find_last_of('/');
-	return p == std::string::npos ? s : s.substr(p + 1);
+	if (!g.socket_dir.empty() && s.compare(0, g.socket_dir.size(), g.socket_dir) == 0) return s.substr(g.socket_dir.size());
+	if (g.socket_dir.empty()) {
+		/* no -S directory configured: accept a path and keep its last component */
+		size_t p = s.find_last_of('/');
+		if (p != std::string::npos) return s.substr(p + 1);
+	}
+	return s;
+}
+
+/* vhost -S <dir> (S/lib/vhost/vhost.c:1185-1205): controller sockets live at <dir>/<name> */
+extern "C" int oimgpu_set_socket_dir(const char *dir, const char *app_core_mask)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	g.socket_dir = dir ? dir : "";
+	if (!g.socket_dir.empty() && g.socket_dir.back() != '/') g.socket_dir += '/';
+	if (app_core_mask && app_core_mask[0]) {
+		char *end = nullptr;
+		unsigned long long v = strtoull(app_core_mask, &end, 16);
+		if (end == app_core_mask || *end || v == 0) return -EINVAL;
+		g.app_core_mask = v;
+	}
+	return 0;
 }
 
 extern "C" int oimgpu_vhost_scsi_ctrlr_create(const char *ctrlr, const char *cpumask)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (!g.inited) return -ENODEV;
-	std::string key = ctrlr_key(ctrlr);
+	/* spdk_vhost_dev_register takes the name verbatim (only lookups strip the socket directory,
+	 * spdk_vhost_dev_find, vhost.c:611-628) */
+	std::string key = ctrlr ? ctrlr : "";
 	if (key.empty()) return -EINVAL;
-	if (g.ctrlrs.count(key)) return -EEXIST;
+	if (g.ctrlrs.count(ctrlr_key(ctrlr)) || g.ctrlrs.count(key)) return -EEXIST;
 	std::string mask = "0x1";
 	if (cpumask && cpumask[0]) {
 		/* spdk_vhost_parse_core_mask: a hex mask that must select at least one core (vhost.c:560-590) */
 		char *end = nullptr;
 		unsigned long long v = strtoull(cpumask, &end, 16);
-		if (end == cpumask || *end != 0 || v == 0) return -EINVAL;
+		if (end == cpumask || *end != 0) return -EINVAL;
+		v &= g.app_core_mask;		/* spdk_app_parse_core_mask keeps only the application's cores ... */
+		if (v == 0) return -EINVAL;	/* ... "no cpu is selected among reactor mask" (vhost.c:560-590) */
 		char buf[24];
 		snprintf(buf, sizeof(buf), "0x%llx", v);
 		mask = buf;
@@ -501,6 +568,7 @@ extern "C" int oimgpu_vhost_scsi_ctrlr_create(const char *ctrlr, const char *cpu
 	c->name = key;
 	c->cpumask = mask;
 	g.ctrlrs[key] = std::move(c);
+	g.ctrlr_order.push_back(key);
 	return 0;
 }
 
@@ -524,6 +592,11 @@ extern "C" int oimgpu_vhost_scsi_add_lun(const char *ctrlr, int scsi_target_num,
 	if (!c.targets[scsi_target_num].empty()) return -EEXIST;
 	auto b = g.bdevs.find(bdev_name);
 	if (b == g.bdevs.end()) return -EINVAL;	/* spdk_scsi_dev_construct failed */
+	int slot = 0;
+	while (slot < 1024 && g.scsi_slot_used[slot]) slot++;
+	if (slot == 1024) return -EINVAL;	/* spdk_scsi_dev_construct: no free device slot */
+	g.scsi_slot_used[slot] = true;
+	c.scsi_id[scsi_target_num] = slot;
 	c.targets[scsi_target_num] = bdev_name;
 	b->second->claimed++;
 	return scsi_target_num;
@@ -540,6 +613,7 @@ extern "C" int oimgpu_vhost_scsi_remove_target(const char *ctrlr, int scsi_targe
 	if (c.targets[scsi_target_num].empty()) return -ENODEV;
 	auto b = g.bdevs.find(c.targets[scsi_target_num]);
 	if (b != g.bdevs.end() && b->second->claimed > 0) b->second->claimed--;
+	g.scsi_slot_used[c.scsi_id[scsi_target_num]] = false;
 	c.targets[scsi_target_num].clear();
 	return 0;
 }
@@ -553,6 +627,7 @@ extern "C" int oimgpu_vhost_ctrlr_remove(const char *ctrlr)
 	for (auto &t : it->second->targets) {
 		if (!t.empty()) return -EBUSY;	/* vhost_scsi.c:837-842 */
 	}
+	g.ctrlr_order.erase(std::remove(g.ctrlr_order.begin(), g.ctrlr_order.end(), it->first), g.ctrlr_order.end());
 	g.ctrlrs.erase(it);
 	return 0;
 }
@@ -562,13 +637,14 @@ static void fill_ctrlr_info(const Ctrlr &c, oimgpu_ctrlr_info *o)
 	memset(o, 0, sizeof(*o));
 	copy_str(o->ctrlr, sizeof(o->ctrlr), c.name);
 	copy_str(o->cpumask, sizeof(o->cpumask), c.cpumask);
+	copy_str(o->socket, sizeof(o->socket), g.socket_dir + c.name);
 	o->delay_base_us = 0;
 	o->iops_threshold = 60000;	/* SPDK_VHOST_VQ_IOPS_COALESCING_THRESHOLD */
 	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
 		if (c.targets[t].empty()) continue;
 		oimgpu_target_info &ti = o->targets[o->ntargets++];
 		ti.scsi_dev_num = t;
-		ti.id = t;
+		ti.id = c.scsi_id[t];
 		snprintf(ti.target_name, sizeof(ti.target_name), "Target %d", t);
 		ti.lun_id = 0;
 		copy_str(ti.bdev_name, sizeof(ti.bdev_name), c.targets[t]);
@@ -589,8 +665,8 @@ extern "C" int oimgpu_vhost_ctrlr_list(oimgpu_ctrlr_info *out, int max)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
 	int n = 0;
-	for (auto &kv : g.ctrlrs) {
-		if (out && n < max) fill_ctrlr_info(*kv.second, &out[n]);
+	for (auto &nm : g.ctrlr_order) {
+		if (out && n < max) fill_ctrlr_info(*g.ctrlrs[nm], &out[n]);
 		n++;
 	}
 	return n;
@@ -602,7 +678,7 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 			       uint32_t queue_size, oimgpu_lun **out)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
-	if (!g.inited) return -ENODEV;
+	if (!g.inited || g.control_only) return -ENODEV;
 	if (!out || num_queues == 0 || queue_size == 0 || (queue_size & (queue_size - 1)) ||
 	    queue_size > OIMGPU_MAX_VQ_SIZE) return -EINVAL;
 	auto it = g.ctrlrs.find(ctrlr_key(ctrlr));
@@ -675,6 +751,7 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	if (per_sm < 1) per_sm = 1;
 	L->grid_cap = L->sm_count * per_sm;
 	g.open_luns++;
+	b.open_luns++;
 	*out = L.release();
 	return 0;
 }
@@ -709,6 +786,10 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 	cudaEventDestroy(L->done);
 	cudaStreamDestroy(L->stream);
 	g.open_luns--;
+	{
+		auto bi = g.bdevs.find(L->bdev);
+		if (bi != g.bdevs.end() && bi->second->open_luns > 0) bi->second->open_luns--;
+	}
 	delete L;
 	return 0;
 }
@@ -858,7 +939,8 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
 	L->kicks++;
-	oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	if (L->h_ctx.nreplicas > 1) oim_lun_queue_mirror_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	else oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->done, L->stream));
 	L->launches++;
@@ -1236,7 +1318,8 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 	kh->stop = L->d_flags;
 	kh->exited = L->d_flags + 16;
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
-	oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	if (L->h_ctx.nreplicas > 1) oim_lun_queue_mirror_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	else oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
 	L->kicks++;

@@ -54,8 +54,10 @@ _VP, _U32, _U64, _I = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
 SYMBOLS = [
     ("oimgpu_abi_version", _I, []),
     ("oimgpu_init", _I, [C.POINTER(C.c_int), _I]),
+    ("oimgpu_init_control_only", _I, []),
     ("oimgpu_fini", None, []),
     ("oimgpu_device_count", _I, []),
+    ("oimgpu_set_socket_dir", _I, [C.c_char_p, C.c_char_p]),
     ("oimgpu_version_string", C.c_char_p, []),
     ("oimgpu_bdev_create_malloc", _I, [C.c_char_p, C.c_char_p, _U64, _U32, _I, C.c_char_p, C.c_size_t]),
     ("oimgpu_bdev_create_rbd", _I, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _U32, _U64, _I, C.c_char_p, C.c_size_t]),

@@ -20,6 +20,7 @@
 #include "spdk/bdev_module.h"
 #include "spdk/copy_engine.h"
 #include "bdev_malloc.h"
+#include "spdk/rpc.h"
 #include "oimgpu.h"
 
 /* ------------------------------------------------------------------------------------------
@@ -46,6 +47,10 @@ int spdk_vhost_nvme_set_bar_mr(int vid, void *bar, uint64_t sz) { return 0; }
 int spdk_vhost_nvme_get_cap(int vid, uint64_t *cap) { return 0; }
 int spdk_vhost_nvme_controller_construct(void) { return 0; }
 int spdk_vhost_blk_controller_construct(void) { return 0; }
+/* vhost-blk / vhost-nvme are never configured by OIM: their RPC handlers link but refuse */
+int spdk_vhost_blk_construct(const char *n, const char *m, const char *d, bool ro) { return -ENOTSUP; }
+int spdk_vhost_nvme_dev_construct(const char *n, const char *m, uint32_t q) { return -ENOTSUP; }
+int spdk_vhost_nvme_dev_add_ns(struct spdk_vhost_dev *v, const char *b) { return -ENOTSUP; }
 struct spdk_event *spdk_event_allocate(uint32_t lcore, spdk_event_fn fn, void *a1, void *a2) { return NULL; }
 void spdk_event_call(struct spdk_event *e) {}
 int spdk_mem_register(void *vaddr, size_t len) { return 0; }
@@ -67,7 +72,12 @@ struct spdk_cpuset *spdk_app_get_core_mask(void)
 }
 int spdk_app_parse_core_mask(const char *mask, struct spdk_cpuset *cpumask)
 {
-	return spdk_cpuset_parse(cpumask, mask);
+	/* as S/lib/event/app.c and S/test/unit/lib/vhost/vhost.c/vhost_ut.c:58-72: parse, then keep only
+	 * the cores of the application mask */
+	int ret = spdk_cpuset_parse(cpumask, mask);
+	if (ret < 0) return ret;
+	spdk_cpuset_and(cpumask, spdk_app_get_core_mask());
+	return 0;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -463,6 +473,34 @@ int oimref_vq_process(void *h, uint64_t desc, uint64_t avail, uint64_t used, uin
 	vs->mem = saved_mem;
 	free(mem);
 	return (uint16_t)(us->idx - start_used) == want ? (int)want : -EIO;
+}
+
+/* ---- the reference's own JSON-RPC server (S/lib/rpc, S/lib/jsonrpc) with its registered handlers:
+ * get_bdevs / construct_malloc_bdev / delete_bdev (bdev_rpc.c, bdev_malloc_rpc.c) and the vhost-scsi
+ * methods (vhost_rpc.c).  Used to pin the wire behaviour of our daemon (tests/test_rpc_daemon.py). */
+int oimref_rpc_start(const char *sock_path, const char *vhost_socket_dir)
+{
+	if (ref_global_init() != 0) return -1;
+	if (vhost_socket_dir && spdk_vhost_set_socket_path(vhost_socket_dir) != 0) return -2;
+	if (spdk_rpc_listen(sock_path) != 0) return -3;
+	spdk_rpc_set_state(SPDK_RPC_RUNTIME);
+	return 0;
+}
+
+void oimref_rpc_poll(int iterations)
+{
+	int i;
+	spdk_set_thread(g_thread);
+	for (i = 0; i < iterations; i++) {
+		spdk_rpc_accept();
+		spdk_thread_poll(g_thread, 0, 0);
+	}
+}
+
+void oimref_rpc_stop(void)
+{
+	spdk_set_thread(g_thread);
+	spdk_rpc_close();
 }
 
 /* nanoseconds spent in process_requestq() + completion polling + used_signal since the last reset:

@@ -285,10 +285,15 @@ def test_cuda_control_plane_errors(gpu):
     with pytest.raises(gpu.OimGpuError) as e:
         gpu.add_vhost_scsi_lun("nope", 0, name)
     assert e.value.rc == -errno.ENODEV
-    gpu.construct_vhost_scsi_controller("/some/dir/cp.ctl")   # socket-dir prefix is stripped (vhost.c:611-628)
+    gpu.load().oimgpu_set_socket_dir(b"/some/dir", None)
+    gpu.construct_vhost_scsi_controller("cp.ctl")
     with pytest.raises(gpu.OimGpuError) as e:
         gpu.construct_vhost_scsi_controller("cp.ctl")
     assert e.value.rc == -errno.EEXIST
+    assert gpu.get_vhost_controllers("/some/dir/cp.ctl")[0]["ctrlr"] == "cp.ctl"   # lookups strip the socket dir (vhost.c:611-628)
+    with pytest.raises(gpu.OimGpuError) as e:
+        gpu.construct_vhost_scsi_controller("cp2.ctl", cpumask="0x2")     # no core left inside the app mask 0x1
+    assert e.value.rc == -errno.EINVAL
     assert gpu.add_vhost_scsi_lun("cp.ctl", 3, name) == 3
     with pytest.raises(gpu.OimGpuError) as e:
         gpu.add_vhost_scsi_lun("cp.ctl", 3, name)
@@ -300,17 +305,22 @@ def test_cuda_control_plane_errors(gpu):
         gpu.add_vhost_scsi_lun("cp.ctl", 4, "missing-bdev")
     assert e.value.rc == -errno.EINVAL
     c = gpu.get_vhost_controllers("cp.ctl")[0]
-    assert c["cpumask"] == "0x1" and c["backend_specific"]["scsi"][0]["target_name"] == "Target 3"
+    assert c["cpumask"] == "0x1" and c["socket"] == "/some/dir/cp.ctl"
+    assert c["backend_specific"]["scsi"][0]["target_name"] == "Target 3"
     assert c["backend_specific"]["scsi"][0]["luns"] == [{"id": 0, "bdev_name": name}]
+    assert not gpu.get_bdevs(name)[0]["claimed"]          # SCSI LUNs open without claiming (lun.c:342)
     with pytest.raises(gpu.OimGpuError) as e:
         gpu.remove_vhost_controller("cp.ctl")             # still has a target -> EBUSY (vhost_scsi.c:837-842)
     assert e.value.rc == -errno.EBUSY
-    with pytest.raises(gpu.OimGpuError) as e:
-        gpu.delete_bdev(name)
-    assert e.value.rc == -errno.EBUSY
-    gpu.remove_vhost_scsi_target("cp.ctl", 3)
+    with gpu.Lun("cp.ctl", 3) as lun:
+        assert lun.device == 0
+        with pytest.raises(gpu.OimGpuError) as e:
+            gpu.delete_bdev(name)                         # a data path is open on it
+        assert e.value.rc == -errno.EBUSY
+    gpu.delete_bdev(name)                                 # hot-removes the target, as spdk_bdev_unregister does
+    assert gpu.get_vhost_controllers("cp.ctl")[0]["backend_specific"]["scsi"] == []
     gpu.remove_vhost_controller("cp.ctl")
-    gpu.delete_bdev(name)
+    gpu.load().oimgpu_set_socket_dir(b"", None)
 
 
 def test_cuda_copy_engine_level(gpu):
