@@ -50,6 +50,8 @@ def parse_args():
     p.add_argument("--no-seq", action="store_true", help="skip the 128 KiB sequential leg")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-vq", action="store_true", help="skip the virtqueue-mode leg")
+    p.add_argument("--no-mixed", action="store_true", help="skip the 70/30 mixed leg (config 4 shape)")
     p.add_argument("--no-lat", action="store_true", help="skip the single-queue qd=32 closed-loop leg")
     return p.parse_args()
 
@@ -383,6 +385,89 @@ def run_ours(args, rank, world, local):
                        "completion records copied back; PCIe D2H ceiling of the box 57 GB/s (cudaMemcpy), "
                        "52.7 GB/s for SM-originated stores (tools/pcie_store_bench.cu)"}
 
+    # ---- virtqueue mode: the kernel walks real virtio split rings itself (a19-a22 on the device) ----
+    vq = None
+    if not args.no_vq:
+        from oim_b200 import vring
+        vnq, vper, vring_size = 1024, 256, 1024
+        g = vring.build_uniform_queues(vnq, vper, NUM_BLOCKS, ring_size=vring_size, seed=plan["trace_seed"] + 5)
+        guest = torch.empty(g.total_bytes(), dtype=torch.uint8, device="cuda")
+        guest[:g.data_off] = torch.from_numpy(g.arena).cuda()
+        guest[g.data_off:].zero_()
+        gbase = guest.data_ptr()
+        vlun = lib.Lun(plan["ctrlr"], plan["target"], num_queues=vnq, queue_size=32)
+        vlun.set_mem_table(np.array([g.gpa_base, g.total_bytes(), gbase], dtype=np.uint64))
+        for q in range(vnq):
+            qb = gbase + q * g.q_stride
+            vlun.vq_attach(q, qb + g.desc_off, qb + g.avail_off, qb + g.used_off, vring_size, 0, 0)
+        # the guests' avail->idx fields, one u16 per queue, as a strided view
+        avail_idx = guest[:g.data_off].view(torch.int16).view(vnq, g.q_stride // 2)[:, (g.avail_off + 2) // 2]
+        used_idx = guest[:g.data_off].view(torch.int16).view(vnq, g.q_stride // 2)[:, (g.used_off + 2) // 2]
+
+        def vstep():
+            avail_idx.add_(vper)                     # every guest publishes vper more heads ...
+            torch.cuda.current_stream().synchronize()
+            vlun.vq_kick()                           # ... and kicks
+        for _ in range(args.warmup):
+            vstep()
+        vlun.sync()
+        barrier()
+        vt = 0.0
+        for _ in range(args.steps):
+            avail_idx.add_(vper)
+            torch.cuda.current_stream().synchronize()
+            timer.start(vlun)
+            vlun.vq_kick()
+            timer.stop(vlun)
+            vlun.sync()
+            vt += timer.elapsed_ms()
+        barrier()
+        vms = max_over_ranks(vt)
+        want_used = (vper * (args.steps + args.warmup)) & 0xFFFF
+        assert int((used_idx.to(torch.int32) & 0xFFFF).min()) == want_used and int((used_idx.to(torch.int32) & 0xFFFF).max()) == want_used
+        i = int(g.lba[3, 7])
+        got = guest[g.data_off + (3 * vper + 7) * 4096:g.data_off + (3 * vper + 7) * 4096 + 4096].cpu().numpy()
+        assert (got == traces.pattern_bytes(plan["store_seed"], i * BLOCK, 4096)).all(), "virtqueue payload mismatch"
+        viops = aggregate(vnq * vper, args.steps, world, vms)
+        vq = {"metric": "4KiB rand-read IOPS through guest virtio split rings (3-descriptor chains, ring walk, "
+                        "GPA->VA translation, response + used ring written by the kernel)",
+              "value": viops, "unit": "IOPS", "hbm_frac": 2 * 4096 * viops / world / 1e9 / peak,
+              "queues": vnq, "requests_per_kick": vnq * vper}
+        vlun.close()
+        del guest
+        torch.cuda.empty_cache()
+
+    # ---- config 4 shape: mixed 70/30 random read/write, qd=128 per queue (bdevperf -M 70 -q 128) ----
+    mixed = None
+    if not args.no_mixed:
+        mq, mp = 1024, 1024                      # 2^20 requests per step; queue q stays inside LBA window q
+        mt = traces.partitioned_queues(mq, mp, NUM_BLOCKS, pattern="randrw", read_pct=70, io_blocks=8, seed=plan["trace_seed"] + 99)
+        marena = torch.empty(mt.arena_bytes, dtype=torch.uint8, device="cuda")
+        marena.view(torch.int64)[:] = 0x5A5A5A5A5A5A5A5A
+        m_reqs = torch.from_numpy(mt.reqs.view(np.uint8)).cuda()
+        m_iovs = torch.from_numpy(mt.bind(marena.data_ptr()).view(np.uint8)).cuda()
+        m_cpls = torch.zeros(len(mt.reqs) * 48, dtype=torch.uint8, device="cuda")
+        for _ in range(args.warmup):
+            lun.submit_batch(mq, mp, m_reqs.data_ptr(), m_iovs.data_ptr(), len(mt.iovs), m_cpls.data_ptr(), abi.MEM_DEVICE)
+        lun.sync()
+        barrier()
+        timer.start(lun)
+        for _ in range(args.steps):
+            lun.submit_batch(mq, mp, m_reqs.data_ptr(), m_iovs.data_ptr(), len(mt.iovs), m_cpls.data_ptr(), abi.MEM_DEVICE)
+        timer.stop(lun)
+        lun.sync()
+        barrier()
+        mms = max_over_ranks(timer.elapsed_ms())
+        mc = np.frombuffer(m_cpls.cpu().numpy().tobytes(), dtype=abi.cpl_dtype)
+        assert not mc["status"].any()
+        miops = aggregate(len(mt.reqs), args.steps, world, mms)
+        mixed = {"metric": "4KiB 70/30 rand r/w IOPS (qd=128 per queue: 4 passes of 32 in flight per queue, 1024 queues, "
+                           "queue q confined to LBA window q)", "value": miops, "unit": "IOPS",
+                 "hbm_frac": 2 * 4096 * miops / world / 1e9 / peak, "requests_per_step": len(mt.reqs),
+                 "reads": mt.meta["reads"]}
+        del marena, m_reqs, m_iovs, m_cpls
+        torch.cuda.empty_cache()
+
     # ---- latency-bound corner: ONE request queue, qd=32, closed loop (submit 32 -> wait -> submit 32 ...) ----
     lat = None
     if not args.no_lat:
@@ -449,7 +534,7 @@ def run_ours(args, rank, world, local):
                          "traffic": measured_traffic("rand4k", n), "peak_source": peak_src,
                          "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
-            "seq128k": seq, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
+            "seq128k": seq, "virtqueue": vq, "mixed_70_30": mixed, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:

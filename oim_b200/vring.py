@@ -252,3 +252,77 @@ def requests_from_trace(t: traces.Trace, arena_init: np.ndarray) -> list[dict]:
         out.append({"cdb": r["cdb"].copy(), "dir": int(r["dir"]), "lun": r["lun"].copy(), "tag": int(r["tag"]),
                     "sg": sg[:130], "payload": payload})
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Uniform multi-queue guest image for throughput measurements (bench.py `virtqueue` leg)
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class UniformGuest:
+    arena: np.ndarray            # metadata part of guest memory (rings, headers, responses); payload follows it
+    nq: int
+    per_q: int
+    ring_size: int
+    q_stride: int                # bytes of metadata per queue
+    desc_off: int                # offsets inside one queue's metadata block
+    avail_off: int
+    used_off: int
+    data_off: int                # arena offset where the payload area starts (not materialised on the host)
+    data_bytes: int
+    gpa_base: int
+
+    def total_bytes(self) -> int:
+        return self.data_off + self.data_bytes
+
+
+def build_uniform_queues(nq: int, per_q: int, num_blocks: int, *, io_blocks: int = 8, ring_size: int = 1024,
+                         seed: int = 1, target: int = 0, gpa_base: int = R2_GPA) -> UniformGuest:
+    """nq virtqueues, each holding per_q READ(10) requests of io_blocks as 3-descriptor direct chains
+    [RO req 51 B][WR resp 108 B][WR data], random LBAs over the whole device (reads only: no ordering
+    question).  The avail ring is pre-filled with the heads repeated ring_size/per_q times, so bumping
+    avail->idx by per_q re-publishes the same chains (what a guest re-using its buffers does)."""
+    assert 3 * per_q <= ring_size and ring_size % per_q == 0
+    io_bytes = io_blocks * 512
+    desc_off = 0
+    avail_off = 16 * ring_size
+    used_off = -(-(avail_off + 6 + 2 * ring_size) // 8) * 8
+    hdr_off = -(-(used_off + 6 + 8 * ring_size) // 64) * 64
+    resp_off = hdr_off + 64 * per_q
+    q_stride = -(-(resp_off + 128 * per_q) // 4096) * 4096
+    data_off = nq * q_stride
+    data_bytes = nq * per_q * io_bytes
+    arena = np.zeros(data_off, dtype=np.uint8)
+    meta = arena.reshape(nq, q_stride)
+    qbase = (np.arange(nq, dtype=np.uint64) * np.uint64(q_stride))[:, None] + np.uint64(gpa_base)      # [nq,1] GPA of a queue block
+    k = np.arange(per_q, dtype=np.uint64)[None, :]
+    # descriptors: chain i uses ring slots 3i, 3i+1, 3i+2
+    d = np.zeros((nq, ring_size), dtype=desc_dtype)
+    d["addr"][:, 0:3 * per_q:3] = qbase + np.uint64(hdr_off) + k * np.uint64(64)
+    d["len"][:, 0:3 * per_q:3] = 51
+    d["flags"][:, 0:3 * per_q:3] = F_NEXT
+    d["next"][:, 0:3 * per_q:3] = (3 * k + 1).astype(np.uint16)
+    d["addr"][:, 1:3 * per_q:3] = qbase + np.uint64(resp_off) + k * np.uint64(128)
+    d["len"][:, 1:3 * per_q:3] = 108
+    d["flags"][:, 1:3 * per_q:3] = F_NEXT | F_WRITE
+    d["next"][:, 1:3 * per_q:3] = (3 * k + 2).astype(np.uint16)
+    qi = np.arange(nq, dtype=np.uint64)[:, None]
+    d["addr"][:, 2:3 * per_q:3] = np.uint64(gpa_base + data_off) + (qi * np.uint64(per_q) + k) * np.uint64(io_bytes)
+    d["len"][:, 2:3 * per_q:3] = io_bytes
+    d["flags"][:, 2:3 * per_q:3] = F_WRITE
+    meta[:, desc_off:desc_off + 16 * ring_size] = d.view(np.uint8).reshape(nq, -1)
+    # avail ring: heads 0,3,6,... repeated
+    heads = np.tile((3 * np.arange(per_q)).astype("<u2"), ring_size // per_q)
+    meta[:, avail_off + 4:avail_off + 4 + 2 * ring_size] = heads.view(np.uint8)[None, :]
+    # request headers: virtio_scsi_cmd_req with a READ(10) at a random LBA
+    rnd = traces.splitmix64_stream(seed, nq * per_q).reshape(nq, per_q)
+    lba = (rnd % np.uint64(num_blocks // io_blocks)) * np.uint64(io_blocks)
+    hdr = np.zeros((nq, per_q, 64), dtype=np.uint8)
+    hdr[:, :, 0:8] = abi.virtio_lun(target)
+    hdr[:, :, 19] = abi.READ_10
+    hdr[:, :, 21:25] = lba.astype(">u4").view(np.uint8).reshape(nq, per_q, 4)
+    hdr[:, :, 26:28] = np.array([io_blocks >> 8, io_blocks & 0xFF], dtype=np.uint8)
+    meta[:, hdr_off:hdr_off + 64 * per_q] = hdr.reshape(nq, -1)
+    g = UniformGuest(arena, nq, per_q, ring_size, q_stride, desc_off, avail_off, used_off, data_off, data_bytes, gpa_base)
+    g.lba = lba
+    return g
