@@ -228,12 +228,6 @@ def device_pattern_fill(lun, store_ptr: int, nbytes: int, seed: int, torch):
         done += n
 
 
-def queue_major(t: traces.Trace, nq: int, per_q: int):
-    """per-queue views of a queue-major trace: request q*per_q.. belong to queue q"""
-    k = len(t.iovs) // (nq * per_q)
-    return k
-
-
 def run_ours(args, rank, world, local):
     import torch
     torch.cuda.set_device(local)

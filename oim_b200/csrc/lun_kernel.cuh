@@ -69,7 +69,6 @@ struct LunCtx {
 	uint32_t block_size;
 	uint32_t block_shift;		/* log2(block_size), or 0xffffffff when not a power of two */
 	uint8_t  target;		/* SCSI target number of this LUN inside its controller */
-	uint8_t  present[OIMGPU_CTRLR_MAX_DEVS];	/* which target slots of the controller are occupied */
 	uint8_t  removed;		/* session saw a hot-remove of this target */
 	uint8_t  lun_removed;
 	/* guest memory table for virtqueue mode: struct rte_vhost_memory (rte_vhost.h:52-66) with
