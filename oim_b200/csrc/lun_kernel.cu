@@ -207,6 +207,8 @@ __device__ __noinline__ void scsi_control(const LunCtx &L, const QueueDesc &q, c
 	}
 }
 
+__device__ void scsi_primary(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, uint32_t cnt, uint32_t len, LaneState &s);
+
 __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, LaneState &s)
 {
 	const uint32_t cnt = r.iovcnt;
@@ -307,6 +309,9 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 		break;
 	case 0x00: case 0x1b:	/* TEST UNIT READY / START STOP UNIT */
 		break;
+	case 0x12: case 0xa0: case 0x15: case 0x55: case 0x1a: case 0x5a:
+		scsi_primary(L, q, r, cnt, len, s);
+		break;
 	default:
 		set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
 		break;
@@ -366,6 +371,290 @@ __device__ __forceinline__ void build_cpl(const oimgpu_req &r, const LaneState &
 	}
 	int4 *o = reinterpret_cast<int4 *>(out);
 	o[0] = cz[0]; o[1] = cz[1]; o[2] = cz[2];
+}
+
+/* ---- SPC primary commands a guest needs to attach the disk (scsi_bdev.c:188-1265, 1827-2077):
+ *      INQUIRY (standard + VPD pages), REPORT LUNS, MODE SENSE 6/10, MODE SELECT 6/10.
+ *      Responses are built in the lane's shared-memory scratch and scattered into the SG list. ------ */
+
+__device__ __forceinline__ void d_be16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; }
+__device__ __forceinline__ void d_be32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+__device__ __forceinline__ void d_be64(uint8_t *p, uint64_t v) { d_be32(p, (uint32_t)(v >> 32)); d_be32(p + 4, (uint32_t)v); }
+__device__ __forceinline__ int d_strlen(const char *s) { int n = 0; while (s[n]) n++; return n; }
+
+/* spdk_strcpy_pad (S/lib/util/string.c:220-231) */
+__device__ __forceinline__ void d_strcpy_pad(uint8_t *dst, const char *src, int size, uint8_t pad)
+{
+	int i = 0;
+	for (; i < size && src[i]; i++) dst[i] = (uint8_t)src[i];
+	for (; i < size; i++) dst[i] = pad;
+}
+
+/* spdk_bdev_scsi_inquiry (scsi_bdev.c:188-805).  Its alloc_len argument is the size of the staging
+ * buffer (>= 4096, scsi_bdev.c:1847-1850), so the short-allocation branches never trigger.
+ * Returns the response length in `data` or -1 with the status set. */
+__device__ __noinline__ int scsi_inquiry(const LunCtx &L, const uint8_t *cdb, uint8_t *data, LaneState &s)
+{
+	const int pc = cdb[2], evpd = cdb[1] & 1;
+	int hlen = 0, len = 0;
+	for (int k = 0; k < 256; k++) data[k] = 0;
+	if (!evpd && pc) {
+		set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD);
+		return -1;
+	}
+	if (!evpd) {
+		/* standard INQUIRY data: all 96 bytes */
+		data[2] = 0x05;			/* SPC-3 */
+		data[3] = 2 | 1 << 4;		/* response format 2, HISUP */
+		data[6] = 0x10;			/* MULTIP */
+		data[7] = 0x2;			/* CMDQUE */
+		d_strcpy_pad(&data[8], "INTEL", 8, ' ');
+		d_strcpy_pad(&data[16], L.product_name, 16, ' ');
+		d_strcpy_pad(&data[32], "0001", 4, ' ');
+		for (int k = 36; k < 56; k++) data[k] = 0x20;
+		d_be16(&data[58], 0x0960); d_be16(&data[60], 0x0300); d_be16(&data[62], 0x0320); d_be16(&data[64], 0x0040);
+		data[4] = 96 - 5;		/* additional length */
+		return 96;
+	}
+	uint8_t *params = data + 4;
+	data[1] = (uint8_t)pc;
+	hlen = 4;
+	switch (pc) {
+	case 0x00: {
+		const uint8_t pages[10] = { 0x00, 0x80, 0x83, 0x85, 0x86, 0x87, 0x88, 0xb0, 0xb1, 0xb2 };
+		for (int k = 0; k < 10; k++) params[k] = pages[k];
+		len = 10;
+		break;
+	}
+	case 0x80:
+		len = d_strlen(L.bdev_name) + 1;
+		if (len > 32) len = 32;
+		for (int k = 0; k < len - 1; k++) params[k] = (uint8_t)L.bdev_name[k];
+		params[len - 1] = 0;
+		break;
+	case 0x83: {
+		uint8_t *buf = params;
+		int dl;
+#define DESIG(code_set, type, assoc, dlen) do { buf[0] = (uint8_t)((code_set) | L.protocol_id << 4); \
+		buf[1] = (uint8_t)((type) | (assoc) << 4 | 1 << 7); buf[2] = 0; buf[3] = (uint8_t)(dlen); } while (0)
+		DESIG(1, 3, 0, 8);
+		{	/* spdk_bdev_scsi_set_naa_ieee_extended (scsi_bdev.c:78-103) */
+			uint8_t *nb = buf + 4;
+			int count = 0;
+			for (int i = 0; i < 16 && L.bdev_name[i]; i++) {
+				int ch = L.bdev_name[i], value;
+				if (ch >= '0' && ch <= '9') value = ch - '0';
+				else {
+					if (ch >= 'A' && ch <= 'Z') ch += 32;
+					value = (ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : ch;
+				}
+				if (i % 2) nb[count++] |= (uint8_t)(value << 4);
+				else nb[count] = (uint8_t)value;
+			}
+			uint64_t v = 0;
+			for (int k = 7; k >= 0; k--) v = v << 8 | nb[k];	/* little-endian load */
+			v &= 0x0fff000000ffffffull;
+			v |= 0x2000000347000000ull;
+			d_be64(nb, v);
+		}
+		len = 12; buf += 12;
+		DESIG(2, 1, 0, 56);
+		d_strcpy_pad(buf + 4, "INTEL", 8, ' ');
+		d_strcpy_pad(buf + 12, L.product_name, 16, ' ');
+		d_strcpy_pad(buf + 28, L.bdev_name, 32, ' ');
+		len += 60; buf += 60;
+		dl = d_strlen(L.dev_name);
+		for (int k = 0; k < dl; k++) buf[4 + k] = (uint8_t)L.dev_name[k];
+		do { buf[4 + dl++] = 0; } while (dl & 3);
+		DESIG(3, 8, 2, dl);
+		len += 4 + dl; buf += 4 + dl;
+		dl = d_strlen(L.port_name);
+		for (int k = 0; k < dl; k++) buf[4 + k] = (uint8_t)L.port_name[k];
+		DESIG(3, 8, 1, dl);
+		len += 4 + dl; buf += 4 + dl;
+		DESIG(1, 4, 1, 4);
+		d_be16(buf + 6, L.port_index);
+		len += 8; buf += 8;
+		DESIG(1, 5, 1, 4);
+		len += 8; buf += 8;
+		DESIG(1, 6, 0, 4);
+		d_be16(buf + 6, (uint32_t)L.scsi_dev_id);
+		len += 8;
+#undef DESIG
+		break;
+	}
+	case 0x86:
+		data[1] = 0;			/* the reference's memset wipes the page code (scsi_bdev.c:420) */
+		data[5] = 0x04 | 0x01;
+		len = 60;
+		break;
+	case 0x85:
+		len = 0;
+		break;
+	case 0x87:
+		params[0] = 0x3f; params[1] = 0xff;
+		len = 4;
+		break;
+	case 0x88: {
+		const int plen = d_strlen(L.port_name);
+		d_be16(params + 2, L.port_index);
+		params[14] = 0x05 << 4 | 0x03;
+		params[15] = 0x80 | 1 << 4 | 8;
+		params[17] = (uint8_t)plen;
+		for (int k = 0; k < plen; k++) params[18 + k] = (uint8_t)L.port_name[k];
+		d_be16(params + 12, 4 + plen);
+		len = 12 + 4 + plen;		/* 14-byte descriptor counted as 12: name cut by 2 (scsi_bdev.c:503-540) */
+		break;
+	}
+	case 0xb0: {
+		uint32_t blocks = (1024u * 1024u) / L.block_size;
+		data[5] = (uint8_t)(blocks > 0xff ? 0xff : blocks);
+		d_be16(&data[6], L.block_size < 4096 ? 4096 / L.block_size : 1);
+		blocks = OIMGPU_MAX_XFER_BYTES / L.block_size;
+		d_be32(&data[8], blocks);
+		d_be32(&data[12], blocks);
+		d_be32(&data[20], 4194304);
+		d_be32(&data[24], OIMGPU_MAX_UNMAP_DESC);
+		d_be64(&data[36], 512);
+		len = 60;
+		break;
+	}
+	case 0xb1:
+		d_be16(&data[4], 1);
+		data[7] = 0x02 << 4;
+		len = 60;
+		break;
+	case 0xb2:
+		data[5] = 1 << 7;
+		data[6] = 0x02;
+		len = 7;
+		break;
+	default:
+		s.data_transferred = 0;
+		set_check(s, SK_NO_SENSE, ASC_NONE);
+		return -1;
+	}
+	d_be16(&data[2], (uint32_t)len);
+	return hlen + len;
+}
+
+/* mode_sense_page_init + spdk_bdev_scsi_mode_sense_page for one (page, subpage) without recursion
+ * (scsi_bdev.c:807-1100); cp == nullptr only sizes */
+__device__ __forceinline__ int mode_page_one(int pc, int page, int subpage, uint8_t *cp)
+{
+	int plen;
+	switch (page) {
+	case 0x01: case 0x07: case 0x1a: case 0x1c: plen = 0x0a + 2; break;
+	case 0x02: plen = 0x0e + 2; break;
+	case 0x08: plen = 0x12 + 2; break;
+	case 0x10: plen = 0x16 + 2; break;
+	case 0x0a:
+		if (subpage == 0x01) {
+			plen = 0x1c + 4;
+			if (cp) { for (int k = 0; k < plen; k++) cp[k] = 0; cp[0] = (uint8_t)(page | 0x40); cp[1] = 1; d_be16(&cp[2], plen - 4); }
+			return plen;
+		}
+		plen = 0x0a + 2;
+		break;
+	default:
+		return 0;
+	}
+	if (subpage != 0) return 0;
+	if (cp) {
+		for (int k = 0; k < plen; k++) cp[k] = 0;
+		cp[0] = (uint8_t)page; cp[1] = (uint8_t)(plen - 2);
+		if (page == 0x08 && pc != 0x01) cp[2] |= 0x4 | 0x1;	/* WCE | RCD */
+	}
+	return plen;
+}
+
+__device__ __forceinline__ int mode_pages(int pc, int page, int subpage, uint8_t *cp)
+{
+	int len = 0;
+	if (page == 0x0a && subpage == 0xff) {
+		len += mode_page_one(pc, 0x0a, 0x00, cp ? cp + len : nullptr);
+		len += mode_page_one(pc, 0x0a, 0x01, cp ? cp + len : nullptr);
+		return len;
+	}
+	if (page == 0x3f) {
+		if (subpage == 0x00 || subpage == 0xff) {
+			for (int i = 0; i < 0x3e; i++) len += mode_page_one(pc, i, 0x00, cp ? cp + len : nullptr);
+		}
+		if (subpage == 0xff) {
+			/* the second round asks every page for subpage 0xff: only page 0x0a answers (00h + 01h) */
+			len += mode_page_one(pc, 0x0a, 0x00, cp ? cp + len : nullptr);
+			len += mode_page_one(pc, 0x0a, 0x01, cp ? cp + len : nullptr);
+		}
+		return len;
+	}
+	return mode_page_one(pc, page, subpage, cp);
+}
+
+/* spdk_bdev_scsi_process_primary (scsi_bdev.c:1827-2077) for INQUIRY / REPORT LUNS / MODE SENSE / MODE SELECT */
+__device__ __noinline__ void scsi_primary(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, uint32_t cnt,
+					  uint32_t len, LaneState &s)
+{
+	const uint8_t *cdb = r.cdb;
+	uint8_t *data = s.scratch;
+	int rc = 0, data_len = -1, alloc_len = -1;
+
+	switch (cdb[0]) {
+	case 0x12:
+		alloc_len = be16(&cdb[3]);
+		rc = scsi_inquiry(L, cdb, data, s);
+		data_len = rc;
+		break;
+	case 0xa0:
+		alloc_len = (int)be32(&cdb[6]);
+		if (alloc_len < 16) { set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD); rc = -1; break; }
+		if (cdb[2] > 0x02) { set_check(s, SK_NO_SENSE, ASC_NONE); rc = -1; break; }
+		for (int k = 0; k < 16; k++) data[k] = 0;
+		d_be32(data, 8);		/* one LUN, id 0, flat addressing (scsi_bdev.c:105-172) */
+		rc = data_len = 16;
+		break;
+	case 0x15: case 0x55: {
+		const int md = cdb[0] == 0x15 ? 4 : 8;
+		const int pllen = cdb[0] == 0x15 ? cdb[4] : be16(&cdb[7]);
+		if (pllen == 0) break;
+		if (pllen < md || (int)len < md) { set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD); rc = -1; break; }
+		/* spdk_bdev_scsi_mode_select_page walks the pages and applies nothing (scsi_bdev.c:1176-1265) */
+		rc = pllen;
+		data_len = 0;
+		break;
+	}
+	case 0x1a: case 0x5a: {
+		int md, llba = 0;
+		if (cdb[0] == 0x1a) { alloc_len = cdb[4]; md = 6; }
+		else { alloc_len = be16(&cdb[7]); llba = !!(cdb[1] & 0x10); md = 10; }
+		const int dbd = !!(cdb[1] & 0x8), pc = (cdb[2] & 0xc0) >> 6, page = cdb[2] & 0x3f, subpage = cdb[3];
+		if (pc == 3) { set_check(s, SK_ILLEGAL_REQUEST, 0x39); rc = -1; break; }	/* SAVING PARAMETERS NOT SUPPORTED */
+		const int hlen = md == 6 ? 4 : 8;
+		const int blen = dbd ? 0 : (md == 6 ? 8 : (llba ? 16 : 8));
+		for (int k = 0; k < 256; k++) data[k] = 0;
+		const int plen = mode_pages(pc, page, subpage, data + hlen + blen);
+		const int total = hlen + blen + plen;
+		if (hlen == 4) { data[0] = (uint8_t)(total - 1); data[3] = (uint8_t)blen; }
+		else { d_be16(&data[0], total - 2); data[4] = llba ? 1 : 0; d_be16(&data[6], blen); }
+		if (blen == 16) { d_be64(&data[hlen], L.num_blocks); d_be32(&data[hlen + 12], L.block_size); }
+		else if (blen == 8) {
+			d_be32(&data[hlen], L.num_blocks > 0xffffffffULL ? 0xffffffffu : (uint32_t)L.num_blocks);
+			d_be32(&data[hlen + 4], L.block_size);
+		}
+		rc = data_len = total;
+		break;
+	}
+	default:
+		return;
+	}
+	if (rc >= 0 && data_len > 0) {
+		/* the scatter may fail (SG list shorter than the data) without changing the outcome (scsi_bdev.c:2060-2069) */
+		scatter_small(q, r, cnt, len, data, alloc_len < data_len ? alloc_len : data_len, s);
+		rc = data_len < alloc_len ? data_len : alloc_len;
+	}
+	if (rc >= 0) {
+		s.data_transferred = rc;
+		s.status = SC_GOOD;
+	}
 }
 
 /* ---- virtqueue mode: the split-ring walk of the reference's poller on one parser lane ---------- */

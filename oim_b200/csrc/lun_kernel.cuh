@@ -75,6 +75,12 @@ struct LunCtx {
 	 * host_user_addr replaced by a device-accessible address */
 	uint32_t nregions;
 	struct { uint64_t gpa, size, addr; } region[kMaxRegions];
+	/* what INQUIRY embeds (S/lib/scsi/scsi_bdev.c:188-805): bdev name / product, SCSI device name and id,
+	 * target port name and index, protocol identifier */
+	char     bdev_name[64], product_name[32], dev_name[16], port_name[16];
+	int32_t  scsi_dev_id;
+	uint16_t port_index;
+	uint8_t  protocol_id;
 	unsigned long long stats[8];	/* read ops, write ops, unmap ops, other, bytes r/w/unmapped, errors */
 };
 
@@ -146,7 +152,8 @@ struct LaneState {
 	uint8_t  response;
 	uint8_t  resp_valid;
 	uint8_t  hazard;		/* 0 none, 1 reads store, 2 writes store, 3 barrier (multi-range writer) */
-	uint8_t  scratch[40];		/* small control payloads (READ CAPACITY, INQUIRY, REQUEST SENSE) */
+	uint8_t  scratch[256];		/* control payloads: READ CAPACITY, REQUEST SENSE, INQUIRY pages (<= 125 B),
+					 * MODE SENSE (<= 188 B), REPORT LUNS */
 };
 
 /* one pipeline stage: what the movers need for (part of) one pass + its completion records */

@@ -710,6 +710,15 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	L->h_ctx.block_size = b.block_size;
 	L->h_ctx.block_shift = (b.block_size & (b.block_size - 1)) ? 0xffffffffu : (uint32_t)__builtin_ctz(b.block_size);
 	L->h_ctx.target = (uint8_t)scsi_target_num;
+	/* identity strings INQUIRY reports: spdk_scsi_dev_construct("Target N", ...) + port 0 "vhost", SAS
+	 * (vhost_scsi.c:1004-1013); the device id is the slot add_vhost_scsi_lun took in the global table */
+	snprintf(L->h_ctx.bdev_name, sizeof(L->h_ctx.bdev_name), "%s", b.name.c_str());
+	snprintf(L->h_ctx.product_name, sizeof(L->h_ctx.product_name), "%s", b.product.c_str());
+	snprintf(L->h_ctx.dev_name, sizeof(L->h_ctx.dev_name), "Target %d", scsi_target_num);
+	snprintf(L->h_ctx.port_name, sizeof(L->h_ctx.port_name), "vhost");
+	L->h_ctx.scsi_dev_id = it->second->scsi_id[scsi_target_num];
+	L->h_ctx.port_index = 0;
+	L->h_ctx.protocol_id = 0x06;
 	CU_OK(cudaMalloc((void **)&L->d_ctx, sizeof(LunCtx)));
 	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, sizeof(LunCtx), cudaMemcpyHostToDevice));
 

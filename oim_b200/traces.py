@@ -395,3 +395,98 @@ def fill_arena(arena: np.ndarray, trace: Trace, seed: int = 0x5EED) -> None:
     arena[:] = pattern_bytes(seed, 0, arena.size)
     for off, data in trace.meta.get("param_payloads", []):
         arena[off:off + len(data)] = data
+
+
+def primary_trace(n: int, *, seed: int = 1, target: int = 0, arena_bytes: int = 4 << 20) -> Trace:
+    """SPC primary commands a guest issues while attaching a disk (S/lib/scsi/scsi_bdev.c:1827-2077):
+    INQUIRY (standard + every VPD page, good and bad allocation lengths), REPORT LUNS, MODE SENSE 6/10
+    over all page / subpage / page-control combinations, MODE SELECT 6/10, with SG lists that are
+    larger, equal and smaller than the allocation length."""
+    rng = np.random.default_rng(seed)
+    b = abi.Batch(target)
+    cur = [64]
+
+    def alloc(nbytes, align=1):
+        o = -(-cur[0] // align) * align
+        if o + nbytes > arena_bytes - 64:
+            o = 64
+        cur[0] = o + nbytes
+        return o
+
+    def sg(total):
+        if total == 0:
+            return [] if rng.integers(0, 2) else [(alloc(0), 0)]
+        k = int(rng.integers(1, 4))
+        cuts = sorted(set(int(x) for x in rng.integers(1, total + 1, size=k - 1))) if k > 1 and total > 1 else []
+        edges = [0] + [c for c in cuts if 0 < c < total] + [total]
+        return [(alloc(z - a + 8) + int(rng.integers(0, 8)), z - a) for a, z in zip(edges[:-1], edges[1:])]
+
+    def payload_len(alloc_len):
+        return int(rng.choice([alloc_len, alloc_len, max(0, alloc_len - int(rng.integers(1, 9))), alloc_len + 13, 4096]))
+
+    payloads = []
+    for _ in range(n):
+        c = np.zeros(abi.CDB_SIZE, dtype=np.uint8)
+        kind = int(rng.integers(0, 10))
+        if kind < 4:                                     # INQUIRY
+            c[0] = 0x12
+            al = int(rng.choice([0, 5, 35, 36, 40, 55, 56, 57, 58, 59, 60, 62, 64, 66, 67, 74, 96, 128, 255, 618, 619, 1024, 4096, 8192]))
+            c[3:5] = [al >> 8, al & 0xFF]
+            if rng.integers(0, 3):
+                c[1] = 1
+                c[2] = int(rng.choice([0x00, 0x80, 0x83, 0x85, 0x86, 0x87, 0x88, 0xB0, 0xB1, 0xB2, 0x84, 0xC5, 0x01]))
+            elif rng.integers(0, 6) == 0:
+                c[2] = 0x80                              # page code without EVPD
+            b.add(c, abi.DIR_FROM_DEV, sg(payload_len(al)))
+        elif kind < 5:                                   # REPORT LUNS
+            c[0] = 0xA0
+            c[2] = int(rng.choice([0, 1, 2, 3, 0x11]))
+            al = int(rng.choice([0, 8, 15, 16, 24, 4096, 70000]))
+            c[6:10] = list(al.to_bytes(4, "big"))
+            b.add(c, abi.DIR_FROM_DEV, sg(min(payload_len(al), 8192)))
+        elif kind < 8:                                   # MODE SENSE 6 / 10
+            six = bool(rng.integers(0, 2))
+            c[0] = 0x1A if six else 0x5A
+            c[1] = (0x08 if rng.integers(0, 2) else 0) | (0x10 if rng.integers(0, 2) else 0)
+            pc = int(rng.choice([0, 0, 1, 2, 3]))
+            page = int(rng.choice([0x00, 0x01, 0x02, 0x03, 0x07, 0x08, 0x0A, 0x10, 0x1A, 0x1C, 0x20, 0x3E, 0x3F]))
+            c[2] = pc << 6 | page
+            c[3] = int(rng.choice([0x00, 0x00, 0x01, 0x02, 0xFF]))
+            al = int(rng.choice([0, 4, 8, 12, 24, 36, 64, 192, 255])) if six else int(rng.choice([0, 8, 16, 24, 64, 200, 512, 4096]))
+            if six:
+                c[4] = al
+            else:
+                c[7:9] = [al >> 8, al & 0xFF]
+            b.add(c, abi.DIR_FROM_DEV, sg(payload_len(al)))
+        else:                                            # MODE SELECT 6 / 10
+            six = bool(rng.integers(0, 2))
+            c[0] = 0x15 if six else 0x55
+            c[1] = 0x10 if rng.integers(0, 2) else 0     # PF
+            md = 4 if six else 8
+            pllen = int(rng.choice([0, 2, md, md + 2, md + 8 + 20, 64]))
+            if six:
+                c[4] = pllen
+            else:
+                c[7:9] = [pllen >> 8, pllen & 0xFF]
+            body = np.zeros(max(pllen, 1), dtype=np.uint8)
+            if pllen >= md + 8 + 20 and rng.integers(0, 2):
+                if six:
+                    body[3] = 8                          # block descriptor length
+                else:
+                    body[6:8] = [0, 8]
+                body[md + 8] = 0x08                      # caching page
+                body[md + 8 + 1] = 0x12
+            dlen = int(rng.choice([pllen, pllen, max(0, pllen - 3), pllen + 5])) if pllen else int(rng.choice([0, 8]))
+            iov = sg(dlen)
+            b.add(c, abi.DIR_TO_DEV, iov)
+            pos = 0
+            for a, l in iov:
+                seg = np.zeros(l, dtype=np.uint8)
+                take = body[pos:pos + l]
+                seg[:len(take)] = take
+                payloads.append((a, seg))
+                pos += l
+    reqs, iovs = b.arrays()
+    t = Trace(reqs, iovs, arena_bytes, f"primary-{seed}", {"n": n})
+    t.meta["param_payloads"] = payloads
+    return t

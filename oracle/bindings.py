@@ -35,7 +35,8 @@ class _Oracle:
     prefix = ""
     path = ""
 
-    def __init__(self, num_blocks: int, block_size: int = 512, target: int = 0):
+    def __init__(self, num_blocks: int, block_size: int = 512, target: int = 0, name: str | None = None,
+                 scsi_dev_id: int | None = None):
         if not os.path.exists(self.path):
             raise FileNotFoundError(self.path)
         self.lib = C.CDLL(self.path)
@@ -56,9 +57,23 @@ class _Oracle:
         self._busy = getattr(self.lib, p + "_busy_ns")
         self._busy.restype = C.c_uint64
         self._busy.argtypes = [C.c_void_p, C.c_int]
-        self.h = self._create(num_blocks, block_size, target)
+        if name is None:
+            self.h = self._create(num_blocks, block_size, target)
+        else:
+            cn = getattr(self.lib, p + "_create_named")
+            cn.restype = C.c_void_p
+            cn.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_int]
+            self.h = cn(name.encode(), num_blocks, block_size, target)
         if not self.h:
             raise RuntimeError(f"{p}_create failed")
+        gid = getattr(self.lib, p + "_scsi_dev_id")
+        gid.restype = C.c_int
+        gid.argtypes = [C.c_void_p, C.c_int]
+        if scsi_dev_id is not None and hasattr(self.lib, p + "_set_identity"):
+            si = getattr(self.lib, p + "_set_identity")
+            si.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+            si(self.h, (name or "Malloc0").encode(), scsi_dev_id)
+        self.scsi_dev_id = gid(self.h, target)
         self.num_blocks, self.block_size, self.target = num_blocks, block_size, target
         addr = self._store(self.h)
         buf = (C.c_uint8 * (num_blocks * block_size)).from_address(addr)

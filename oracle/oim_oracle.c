@@ -17,6 +17,7 @@
  */
 #include <errno.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdbool.h>
@@ -45,6 +46,10 @@ struct orc_bdev {
 	uint8_t  *buf;		/* malloc_buf: num_blocks*block_size zero-filled bytes */
 	uint64_t blockcnt;
 	uint32_t blocklen;
+	/* what INQUIRY embeds: spdk_bdev name/product_name, spdk_scsi_dev name/id, port name/index,
+	 * protocol identifier (vhost-scsi: SAS, vhost_scsi.c:1004-1013) */
+	char name[64], product_name[32], dev_name[16], port_name[16];
+	int  dev_id, port_index, protocol_id;
 };
 
 /* per-session target state (struct spdk_scsi_dev_vhost_state, vhost_scsi.c:66-71) */
@@ -383,16 +388,372 @@ static int scsi_process_block(struct orc_bdev *b, struct orc_task *t)
 	return TASK_COMPLETE;
 }
 
-/* spdk_bdev_scsi_process_primary (scsi_bdev.c:1827-2077): the commands that need no page tables.
- * INQUIRY / MODE SENSE / MODE SELECT / REPORT LUNS are SURVEY.md §8(f) rank 1 ("next"). */
+static inline void to_be16(uint8_t *p, uint16_t v) { p[0] = v >> 8; p[1] = (uint8_t)v; }
+
+/* spdk_strcpy_pad (S/lib/util/string.c:220-231) */
+static void strcpy_pad(uint8_t *dst, const char *src, size_t size, int pad)
+{
+	size_t len = strlen(src);
+	if (len < size) { memcpy(dst, src, len); memset(dst + len, pad, size - len); }
+	else memcpy(dst, src, size);
+}
+
+/* spdk_bdev_scsi_set_naa_ieee_extended (scsi_bdev.c:78-103): nibbles of the first 16 name characters,
+ * non-hex characters taken at face value and truncated to a byte */
+static void set_naa_ieee_extended(const char *name, uint8_t *buf)
+{
+	int i, count = 0;
+	uint64_t v = 0;
+	for (i = 0; i < 16 && name[i] != '\0'; i++) {
+		int ch = name[i], value;
+		if (ch >= '0' && ch <= '9') value = ch - '0';
+		else {
+			ch = (ch >= 'A' && ch <= 'Z') ? ch + 32 : ch;
+			value = (ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : ch;
+		}
+		if (i % 2) buf[count++] |= (uint8_t)(value << 4);
+		else buf[count] = (uint8_t)value;
+	}
+	memcpy(&v, buf, 8);		/* host (little-endian) load, as *(uint64_t *)buf */
+	v &= 0x0fff000000ffffffull;
+	v |= 0x2000000347000000ull;	/* NAA 2, IEEE company id 00 03 47 (Intel) */
+	to_be64(buf, v);
+}
+
+/* spdk_bdev_scsi_inquiry (scsi_bdev.c:188-805).  data: zeroed buffer of max(4096, alloc_len).
+ * Returns the response length or -1 with the task status set. */
+static int scsi_inquiry(const struct orc_bdev *b, struct orc_task *t, const uint8_t *cdb, uint8_t *data, uint16_t alloc_len)
+{
+	const int pc = cdb[2], evpd = cdb[1] & 1;
+	int hlen = 0, len = 0, i;
+
+	if (alloc_len < 0x24) goto inq_error;
+	if (!evpd && pc) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD, ASCQ_NONE);
+		return -1;
+	}
+	if (evpd) {
+		uint8_t *params = data + 4;
+		data[0] = 0;		/* peripheral qualifier 0 (connected) | device type 0 (disk) */
+		data[1] = pc;
+		switch (pc) {
+		case 0x00: {		/* supported VPD pages */
+			static const uint8_t pages[] = { 0x00, 0x80, 0x83, 0x85, 0x86, 0x87, 0x88, 0xb0, 0xb1, 0xb2 };
+			hlen = 4;
+			memcpy(params, pages, sizeof(pages));
+			len = sizeof(pages);	/* Malloc supports UNMAP: page 0xb2 is listed */
+			to_be16(&data[2], len);
+			break;
+		}
+		case 0x80:		/* unit serial number = bdev name, at most 31 characters + NUL */
+			hlen = 4;
+			len = (int)strlen(b->name) + 1;
+			if (len > 32) len = 32;
+			memcpy(params, b->name, len - 1);
+			params[len - 1] = 0;
+			to_be16(&data[2], len);
+			break;
+		case 0x83: {		/* device identification */
+			uint8_t *buf = params;
+			int dl;
+			hlen = 4;
+			/* worst-case size check made before anything is built (scsi_bdev.c:284-299) */
+			len = (4 + 8) + (4 + 8 + 16 + 32) + (4 + 255 + 1) + (4 + 255) + (4 + 4) * 3;
+			if (4 + len > alloc_len) {
+				task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD, ASCQ_NONE);
+				return -1;
+			}
+#define DESIG(code_set, type, assoc, dlen) do { buf[0] = (code_set) | b->protocol_id << 4; \
+		buf[1] = (type) | (assoc) << 4 | 1 << 7; buf[2] = 0; buf[3] = (dlen); } while (0)
+			DESIG(1, 3, 0, 8);				/* NAA, logical unit */
+			set_naa_ieee_extended(b->name, buf + 4);
+			len = 4 + 8; buf += 4 + 8;
+			DESIG(2, 1, 0, 8 + 16 + 32);			/* T10 vendor id, logical unit */
+			strcpy_pad(buf + 4, "INTEL", 8, ' ');
+			strcpy_pad(buf + 12, b->product_name, 16, ' ');
+			strcpy_pad(buf + 28, b->name, 32, ' ');
+			len += 4 + 56; buf += 4 + 56;
+			dl = (int)strlen(b->dev_name);			/* spdk_bdev_scsi_pad_scsi_name: NUL-pad to x4 */
+			memcpy(buf + 4, b->dev_name, dl);
+			do { buf[4 + dl++] = 0; } while (dl & 3);
+			DESIG(3, 8, 2, dl);				/* SCSI name, target device */
+			len += 4 + dl; buf += 4 + dl;
+			dl = (int)strlen(b->port_name);
+			memcpy(buf + 4, b->port_name, dl);
+			DESIG(3, 8, 1, dl);				/* SCSI name, target port */
+			len += 4 + dl; buf += 4 + dl;
+			DESIG(1, 4, 1, 4);				/* relative target port */
+			to_be16(buf + 6, b->port_index);
+			len += 8; buf += 8;
+			DESIG(1, 5, 1, 4);				/* target port group */
+			len += 8; buf += 8;
+			DESIG(1, 6, 0, 4);				/* logical unit group = device id */
+			to_be16(buf + 6, b->dev_id);
+			len += 8;
+#undef DESIG
+			to_be16(&data[2], len);
+			break;
+		}
+		case 0x86:		/* extended inquiry: the memset wipes the page code too (scsi_bdev.c:420) */
+			memset(data, 0, 64);
+			hlen = 4;
+			data[5] = 0x04 | 0x01;	/* HEADSUP | SIMPSUP */
+			len = 64 - hlen;
+			to_be16(&data[2], len);
+			break;
+		case 0x85:		/* management network addresses: empty */
+			hlen = 4;
+			to_be16(&data[2], len);
+			break;
+		case 0x87:		/* mode page policy: all pages / subpages shared */
+			hlen = 4;
+			params[0] = 0x3f; params[1] = 0xff; params[2] = 0; params[3] = 0;
+			len += 4;
+			to_be16(&data[2], len);
+			break;
+		case 0x88: {		/* SCSI ports: one used port.  struct spdk_scsi_port_desc is 14 bytes but only
+					 * 12 are counted, so the reported length cuts the name short by 2 (scsi_bdev.c:503-540) */
+			uint8_t *sd = params;
+			int plen = (int)strlen(b->port_name);
+			hlen = 4;
+			to_be16(sd + 2, b->port_index);
+			len += 12;
+			sd[14] = 0x05 << 4 | 0x03;	/* iSCSI | UTF-8 */
+			sd[15] = 0x80 | 1 << 4 | 8;	/* PIV | target port | SCSI name */
+			sd[16] = 0;
+			sd[17] = plen;
+			memcpy(sd + 18, b->port_name, plen);
+			to_be16(sd + 12, 4 + plen);
+			len += 4 + plen;
+			to_be16(&data[2], len);
+			break;
+		}
+		case 0xb0: {		/* block limits */
+			uint32_t blocks = (1024u * 1024u) / b->blocklen;
+			memset(&data[4], 0, 60);
+			hlen = 4;
+			data[5] = blocks > 0xff ? 0xff : blocks;
+			to_be16(&data[6], b->blocklen < 4096 ? 4096 / b->blocklen : 1);
+			blocks = OIMGPU_MAX_XFER_BYTES / b->blocklen;
+			to_be32(&data[8], blocks);
+			to_be32(&data[12], blocks);
+			to_be32(&data[20], 4194304);	/* maximum unmap LBA count */
+			to_be32(&data[24], OIMGPU_MAX_UNMAP_DESC);
+			to_be64(&data[36], 512);	/* maximum write same length */
+			len = 64 - hlen;
+			to_be16(&data[2], len);
+			break;
+		}
+		case 0xb1:		/* block device characteristics: non-rotating, 3.5" */
+			hlen = 4;
+			len = 64 - hlen;
+			to_be16(&data[4], 1);
+			data[6] = 0;
+			data[7] = 0x02 << 4;
+			memset(&data[8], 0, 64 - 8);
+			to_be16(&data[2], len);
+			break;
+		case 0xb2:		/* logical block provisioning: LBPU, thin */
+			hlen = 4;
+			len = 7;
+			data[4] = 0;
+			data[5] |= 1 << 7;
+			data[6] = 0x02;
+			to_be16(&data[2], len);
+			break;
+		default:
+			goto inq_error;
+		}
+	} else {
+		/* standard INQUIRY data (struct spdk_scsi_cdb_inquiry_data) */
+		data[0] = 0;
+		data[1] = 0;
+		data[2] = 0x05;		/* SPC-3 */
+		data[3] = 2 | 1 << 4;	/* response format 2, HISUP */
+		hlen = 5;
+		data[5] = 0;
+		data[6] = 0x10;		/* MULTIP */
+		data[7] = 0x2;		/* CMDQUE */
+		strcpy_pad(&data[8], "INTEL", 8, ' ');
+		strcpy_pad(&data[16], b->product_name, 16, ' ');
+		strcpy_pad(&data[32], "0001", 4, ' ');
+		len = 36 - 5;
+		if (alloc_len >= 56) { memset(&data[36], 0x20, 20); len += 20; }
+		if (alloc_len >= 57) { data[56] = 0; len += 1; }
+		if (alloc_len >= 58) { data[57] = 0; len += 1; }
+		if (alloc_len >= 58 + 2) { to_be16(&data[58], 0x0960); len += 2; }
+		if (alloc_len >= 58 + 4) { to_be16(&data[60], 0x0300); len += 2; }
+		if (alloc_len >= 58 + 6) { to_be16(&data[62], 0x0320); len += 2; }
+		if (alloc_len >= 58 + 8) { to_be16(&data[64], 0x0040); len += 2; }
+		if (alloc_len > 58 + 8) {
+			i = alloc_len - (58 + 8);
+			if (i > 30) i = 30;
+			memset(&data[66], 0, i);
+			len += i;
+		}
+		data[4] = len;		/* additional length */
+	}
+	return hlen + len;
+
+inq_error:
+	t->data_transferred = 0;
+	task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, ASC_NONE, ASCQ_NONE);
+	return -1;
+}
+
+/* mode_sense_page_init + spdk_bdev_scsi_mode_sense_page (scsi_bdev.c:807-1100); cp may be NULL */
+static void mode_page_init(uint8_t *buf, int len, int page, int subpage)
+{
+	if (!buf) return;
+	memset(buf, 0, len);
+	if (subpage != 0) { buf[0] = page | 0x40; buf[1] = subpage; to_be16(&buf[2], len - 4); }
+	else { buf[0] = page; buf[1] = len - 2; }
+}
+
+static int scsi_mode_sense_page(struct orc_task *t, int pc, int page, int subpage, uint8_t *cp)
+{
+	int len = 0, plen = 0, i;
+
+	if (pc == 3) {
+		task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, 0x39 /* SAVING PARAMETERS NOT SUPPORTED */, ASCQ_NONE);
+		return -1;
+	}
+	switch (page) {
+	case 0x01: case 0x07: case 0x1a: case 0x1c: plen = 0x0a + 2; break;	/* error recovery, verify, power, IEC */
+	case 0x02: plen = 0x0e + 2; break;					/* disconnect-reconnect */
+	case 0x08: plen = 0x12 + 2; break;					/* caching */
+	case 0x10: plen = 0x16 + 2; break;					/* XOR control */
+	case 0x0a:
+		if (subpage == 0x00) { plen = 0x0a + 2; break; }
+		if (subpage == 0x01) { mode_page_init(cp, 0x1c + 4, page, subpage); return 0x1c + 4; }
+		if (subpage == 0xff) {
+			len += scsi_mode_sense_page(t, pc, page, 0x00, cp ? &cp[len] : NULL);
+			len += scsi_mode_sense_page(t, pc, page, 0x01, cp ? &cp[len] : NULL);
+		}
+		return len;
+	case 0x3f:
+		if (subpage == 0x00 || subpage == 0xff) {
+			for (i = 0x00; i < 0x3e; i++) len += scsi_mode_sense_page(t, pc, i, 0x00, cp ? &cp[len] : NULL);
+		}
+		if (subpage == 0xff) {
+			for (i = 0x00; i < 0x3e; i++) len += scsi_mode_sense_page(t, pc, i, 0xff, cp ? &cp[len] : NULL);
+		}
+		return len;
+	default:
+		return 0;
+	}
+	if (subpage != 0x00) return 0;
+	mode_page_init(cp, plen, page, subpage);
+	if (page == 0x08 && cp && pc != 0x01) cp[2] |= 0x4 | 0x1;	/* WCE (Malloc has a write cache) | RCD */
+	return plen;
+}
+
+/* spdk_bdev_scsi_mode_sense (scsi_bdev.c:1102-1174) */
+static int scsi_mode_sense(const struct orc_bdev *b, struct orc_task *t, int md, int dbd, int llbaa, int pc,
+			   int page, int subpage, uint8_t *data)
+{
+	int hlen = md == 6 ? 4 : 8, blen = md == 6 ? 8 : (llbaa ? 16 : 8), plen, total;
+
+	if (dbd) blen = 0;
+	plen = scsi_mode_sense_page(t, pc, page, subpage, data ? &data[hlen + blen] : NULL);
+	if (plen < 0) return -1;
+	total = hlen + blen + plen;
+	if (!data) return total;
+	if (hlen == 4) {
+		data[0] = total - 1; data[1] = 0; data[2] = 0; data[3] = blen;
+	} else {
+		to_be16(&data[0], total - 2);
+		data[2] = 0; data[3] = 0; data[4] = llbaa ? 1 : 0; data[5] = 0;
+		to_be16(&data[6], blen);
+	}
+	if (blen == 16) {
+		to_be64(&data[hlen], b->blockcnt);
+		memset(&data[hlen + 8], 0, 4);
+		to_be32(&data[hlen + 12], b->blocklen);
+	} else if (blen == 8) {
+		if (b->blockcnt > 0xffffffffULL) memset(&data[hlen], 0xff, 4);
+		else to_be32(&data[hlen], (uint32_t)b->blockcnt);
+		to_be32(&data[hlen + 4], b->blocklen);
+	}
+	return total;
+}
+
+/* spdk_bdev_scsi_check_len (scsi_bdev.c:1812-1825) */
+static int scsi_check_len(struct orc_task *t, int len, int min_len)
+{
+	if (len >= min_len) return 0;
+	task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD, ASCQ_NONE);
+	return -1;
+}
+
+/* spdk_bdev_scsi_process_primary (scsi_bdev.c:1827-2077) */
 static int scsi_process_primary(struct orc_bdev *b, struct orc_task *t)
 {
 	const uint8_t *cdb = t->cdb;
-	int rc = 0, data_len = -1, alloc_len = -1;
-	uint8_t data[32];
+	int rc = 0, data_len = -1, alloc_len = -1, md = 0, pllen, bdlen = 0;
+	uint8_t *data = NULL;
 
-	(void)b;
 	switch (cdb[0]) {
+	case 0x12:		/* INQUIRY */
+		alloc_len = be16(&cdb[3]);
+		data_len = alloc_len > 4096 ? alloc_len : 4096;
+		data = calloc(1, data_len);
+		rc = scsi_inquiry(b, t, cdb, data, (uint16_t)data_len);	/* the BUFFER size, not the CDB's allocation length (scsi_bdev.c:1850) */
+		data_len = rc < data_len ? rc : data_len;
+		break;
+	case 0xa0:		/* REPORT LUNS: one LUN (id 0), flat addressing (scsi_bdev.c:105-172) */
+		alloc_len = (int)be32(&cdb[6]);
+		rc = scsi_check_len(t, alloc_len, 16);
+		if (rc < 0) break;
+		data_len = alloc_len > 4096 ? alloc_len : 4096;
+		data = calloc(1, data_len);
+		if (cdb[2] > 0x02) {
+			rc = -1;
+			task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, ASC_NONE, ASCQ_NONE);
+			data_len = rc;
+			break;
+		}
+		to_be32(data, 8);
+		rc = data_len = 16;
+		break;
+	case 0x15: case 0x55:	/* MODE SELECT (6) / (10): lengths are validated, pages are accepted and ignored */
+		md = cdb[0] == 0x15 ? 4 : 8;
+		pllen = cdb[0] == 0x15 ? cdb[4] : be16(&cdb[7]);
+		if (pllen == 0) break;
+		rc = scsi_check_len(t, pllen, md);
+		if (rc < 0) break;
+		{
+			size_t total = 0;
+			int i;
+			for (i = 0; i < t->iovcnt; i++) total += t->iovs[i].len;
+			data_len = (int)total;
+			if (total) {
+				uint8_t *pos = data = malloc(total);
+				for (i = 0; i < t->iovcnt; i++) { if (t->iovs[i].len) memcpy(pos, t->iovs[i].base, t->iovs[i].len); pos += t->iovs[i].len; }
+			}
+		}
+		rc = scsi_check_len(t, data_len, md);
+		if (rc >= 0) bdlen = md == 4 ? data[3] : be16(&data[6]);
+		if (rc < 0) break;
+		(void)bdlen;	/* spdk_bdev_scsi_mode_select_page only walks the pages; nothing is applied */
+		rc = pllen;
+		data_len = 0;
+		break;
+	case 0x1a: case 0x5a: {	/* MODE SENSE (6) / (10) */
+		int llba = 0, dbd, pc, page, subpage;
+		if (cdb[0] == 0x1a) { alloc_len = cdb[4]; md = 6; }
+		else { alloc_len = be16(&cdb[7]); llba = !!(cdb[1] & 0x10); md = 10; }
+		dbd = !!(cdb[1] & 0x8);
+		pc = (cdb[2] & 0xc0) >> 6;
+		page = cdb[2] & 0x3f;
+		subpage = cdb[3];
+		rc = scsi_mode_sense(b, t, md, dbd, llba, pc, page, subpage, NULL);
+		if (rc < 0) break;
+		data_len = rc;
+		data = calloc(1, data_len);
+		rc = scsi_mode_sense(b, t, md, dbd, llba, pc, page, subpage, data);
+		break;
+	}
 	case 0x03:		/* REQUEST SENSE */
 		if (cdb[1] & 0x1) {
 			task_set_status(t, SC_CHECK_CONDITION, SK_ILLEGAL_REQUEST, ASC_INVALID_FIELD, ASCQ_NONE);
@@ -402,6 +763,7 @@ static int scsi_process_primary(struct orc_bdev *b, struct orc_task *t)
 		task_set_status(t, SC_CHECK_CONDITION, SK_NO_SENSE, 0, 0);	/* build_sense_data only... */
 		t->status = SC_GOOD;						/* ...status is set below */
 		data_len = (int)t->sense_data_len;
+		data = malloc(data_len);
 		memcpy(data, t->sense_data, data_len);
 		break;
 	case 0x4c: case 0x4d:	/* LOG SELECT / LOG SENSE */
@@ -422,6 +784,7 @@ static int scsi_process_primary(struct orc_bdev *b, struct orc_task *t)
 		t->data_transferred = rc;
 		t->status = SC_GOOD;
 	}
+	free(data);
 	return TASK_COMPLETE;
 }
 
@@ -567,6 +930,11 @@ void *oimorc_create(uint64_t num_blocks, uint32_t block_size, int target_num)
 	memset(o->bdev.buf, 0, num_blocks * block_size);
 	o->bdev.blockcnt = num_blocks;
 	o->bdev.blocklen = block_size;
+	snprintf(o->bdev.name, sizeof(o->bdev.name), "Malloc0");
+	snprintf(o->bdev.product_name, sizeof(o->bdev.product_name), "Malloc disk");
+	snprintf(o->bdev.dev_name, sizeof(o->bdev.dev_name), "Target %d", target_num);
+	snprintf(o->bdev.port_name, sizeof(o->bdev.port_name), "vhost");
+	o->bdev.protocol_id = 0x06;	/* SAS */
 	o->tgt[target_num].bdev = &o->bdev;
 	return o;
 }
@@ -578,6 +946,23 @@ void oimorc_destroy(void *h)
 	free(o->bdev.buf);
 	free(o);
 }
+
+/* the strings / ids INQUIRY reports: bdev name and the global SCSI device id */
+void oimorc_set_identity(void *h, const char *bdev_name, int scsi_dev_id)
+{
+	struct oimorc *o = h;
+	snprintf(o->bdev.name, sizeof(o->bdev.name), "%s", bdev_name);
+	o->bdev.dev_id = scsi_dev_id;
+}
+
+void *oimorc_create_named(const char *bdev_name, uint64_t num_blocks, uint32_t block_size, int target_num)
+{
+	void *h = oimorc_create(num_blocks, block_size, target_num);
+	if (h) oimorc_set_identity(h, bdev_name, 0);
+	return h;
+}
+
+int oimorc_scsi_dev_id(void *h, int target_num) { (void)target_num; return ((struct oimorc *)h)->bdev.dev_id; }
 
 uint8_t *oimorc_store(void *h) { return ((struct oimorc *)h)->bdev.buf; }
 uint64_t oimorc_num_blocks(void *h) { return ((struct oimorc *)h)->bdev.blockcnt; }

@@ -141,7 +141,27 @@ static void ref_hotremove_cb(struct spdk_scsi_lun *lun, void *arg) {}
 
 /* Create one Malloc bdev and expose it as "Target <target_num>" LUN 0 of a vhost-scsi session,
  * the state add_vhost_scsi_lun + a connected guest produce (vhost_scsi.c:951-1021, 1236-1292). */
+static void *ref_create(const char *bdev_name, uint64_t num_blocks, uint32_t block_size, int target_num);
+
 void *oimref_create(uint64_t num_blocks, uint32_t block_size, int target_num)
+{
+	return ref_create(NULL, num_blocks, block_size, target_num);
+}
+
+/* same with an explicit bdev name (INQUIRY reports it: serial number, NAA and T10 designators) */
+void *oimref_create_named(const char *bdev_name, uint64_t num_blocks, uint32_t block_size, int target_num)
+{
+	return ref_create(bdev_name, num_blocks, block_size, target_num);
+}
+
+/* spdk_scsi_dev.id of the target: slot in the process-wide SCSI device table (S/lib/scsi/dev.c:49-66) */
+int oimref_scsi_dev_id(void *h, int target_num)
+{
+	struct oimref *r = h;
+	return spdk_scsi_dev_get_id(r->svsession->scsi_dev_state[target_num].dev);
+}
+
+static void *ref_create(const char *bdev_name, uint64_t num_blocks, uint32_t block_size, int target_num)
 {
 	struct oimref *r;
 	const char *names[1];
@@ -154,7 +174,8 @@ void *oimref_create(uint64_t num_blocks, uint32_t block_size, int target_num)
 	if (ref_global_init() != 0) return NULL;
 
 	r = calloc(1, sizeof(*r));
-	snprintf(r->bdev_name, sizeof(r->bdev_name), "RefMalloc%d", __sync_fetch_and_add(&g_name_seq, 1));
+	if (bdev_name) snprintf(r->bdev_name, sizeof(r->bdev_name), "%s", bdev_name);
+	else snprintf(r->bdev_name, sizeof(r->bdev_name), "RefMalloc%d", __sync_fetch_and_add(&g_name_seq, 1));
 	r->bdev = create_malloc_disk(r->bdev_name, NULL, num_blocks, block_size);
 	if (!r->bdev) { free(r); return NULL; }
 

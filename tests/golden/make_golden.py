@@ -52,5 +52,19 @@ def main():
         print(name, len(t), "status hist", dict(zip(*np.unique(cpls["status"], return_counts=True))))
 
 
+def primary():
+    """SPC primary commands (INQUIRY / MODE SENSE / REPORT LUNS / MODE SELECT), bdev named Malloc0"""
+    n, seed = 400, 909
+    t = traces.primary_trace(n, seed=seed)
+    with bindings.RefOracle(16384, name="Malloc0") as probe:
+        dev_id = probe.scsi_dev_id
+    cpls, arena, _ = util.run_oracle(bindings.RefOracle, t, 16384, name="Malloc0")
+    np.savez_compressed(os.path.join(HERE, "primary.npz"), n=np.int64(n), seed=np.int64(seed), reqs=t.reqs,
+                        cpls=cpls, arena_sha=np.array(util.sha(arena)), scsi_dev_id=np.int64(dev_id),
+                        source=np.array(bindings.RefOracle.describe()))
+    print("primary", n, "scsi_dev_id", dev_id, dict(zip(*np.unique(cpls["status"], return_counts=True))))
+
+
 if __name__ == "__main__":
+    primary()
     main()

@@ -9,7 +9,7 @@ import pytest
 import util
 from oim_b200 import abi, traces
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "fuzz_*.npz")))
 
 
 def load_golden(path):

@@ -16,9 +16,11 @@ def sha(a: np.ndarray) -> str:
 
 
 def run_oracle(cls, trace: traces.Trace, num_blocks: int, *, block_size: int = 512, store_seed: int | None = 7,
-               arena_seed: int = 0x5EED, target: int = 0, removed: bool = False):
-    """-> (cpls, arena, store) after replaying `trace` on a CPU checker (RefOracle / PortOracle)."""
-    o = cls(num_blocks, block_size, target)
+               arena_seed: int = 0x5EED, target: int = 0, removed: bool = False, name: str | None = None,
+               scsi_dev_id: int | None = None):
+    """-> (cpls, arena, store) after replaying `trace` on a CPU checker (RefOracle / PortOracle).
+    name / scsi_dev_id: the identity INQUIRY reports (bdev name, global SCSI device id)."""
+    o = cls(num_blocks, block_size, target, name=name, scsi_dev_id=scsi_dev_id)
     try:
         if store_seed is not None:
             o.store[:] = traces.pattern_bytes(store_seed, 0, o.store.size)
@@ -34,12 +36,12 @@ def run_oracle(cls, trace: traces.Trace, num_blocks: int, *, block_size: int = 5
 
 def run_cuda(lib, trace: traces.Trace, num_blocks: int, *, block_size: int = 512, store_seed: int | None = 7,
              arena_seed: int = 0x5EED, target: int = 0, mem: str = "device", removed: bool = False,
-             queue_size: int = 1024):
+             queue_size: int = 1024, name: str | None = None):
     """Same replay through liboimgpu.so on cuda:0.  mem="device": client buffers in HBM (a torch
     tensor); mem="host": client buffers in pinned, registered host memory."""
     import torch
     tag = next(_seq)
-    bname, cname = f"par{tag}", f"parctl{tag}"
+    bname, cname = name or f"par{tag}", f"parctl{tag}"
     lib.construct_malloc_bdev(num_blocks, block_size, name=bname, device=0)
     lib.construct_vhost_scsi_controller(cname)
     lib.add_vhost_scsi_lun(cname, target, bname)
