@@ -916,9 +916,14 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		LaneState &s = sh.lane[lane];
 		uint32_t fills = 0;			/* stage fills so far */
 		uint32_t reaped = 0;			/* fills whose completions are published */
-		/* previous pass's store range per lane, for cross-pass hazards */
-		uint64_t prev_lo = 0, prev_hi = 0;
-		uint32_t prev_haz = 0;
+		/* store ranges of the previous kStages-1 passes, per lane, for cross-pass hazards: movers are not
+		 * in lock-step, one may already work on pass p+2 while another is still in pass p (the stage ring
+		 * only stops the parser from refilling pass p's stage) */
+		constexpr int kHist = kStages - 1;
+		uint64_t prev_lo[kHist], prev_hi[kHist];
+		uint32_t prev_haz[kHist];
+#pragma unroll
+		for (int h = 0; h < kHist; h++) { prev_lo[h] = prev_hi[h] = 0; prev_haz[h] = 0; }
 		uint32_t st_rd = 0, st_wr = 0, st_um = 0, st_er = 0;
 		unsigned long long st_rb = 0, st_wb = 0;
 		bool first = true;
@@ -1082,26 +1087,33 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					}
 					nwaves = __reduce_max_sync(0xffffffffu, (uint32_t)wave) + 1;
 				}
-				/* hazards against the previous pass, whose movers may still be running */
+				/* hazards against the passes whose movers may still be running.  Waiting for the previous
+				 * fill's `empty` barrier covers all of them: a mover arrives there only after it has
+				 * finished its share of every earlier fill. */
 				bool drain = false;
 				{
-					const uint32_t pw = __ballot_sync(0xffffffffu, prev_haz >= 2);
-					const uint32_t pt = __ballot_sync(0xffffffffu, prev_haz != 0);
-					uint32_t scan = writers ? pt : pw;	/* only pairs with a writer on one side matter */
 					bool hit = false;
-					if (touching) {
-						while (scan) {
-							const int j = __ffs(scan) - 1;
-							scan &= scan - 1;
-							const uint64_t jlo = __shfl_sync(0xffffffffu, prev_lo, j);
-							const uint64_t jhi = __shfl_sync(0xffffffffu, prev_hi, j);
-							const uint32_t jhaz = __shfl_sync(0xffffffffu, prev_haz, j);
-							if (haz != 0 && (jhaz >= 2 || haz >= 2) &&
-							    (jhaz == 3 || haz == 3 || (lo < jhi && jlo < hi))) hit = true;
+#pragma unroll
+					for (int h = 0; h < kHist; h++) {
+						const uint32_t pw = __ballot_sync(0xffffffffu, prev_haz[h] >= 2);
+						const uint32_t pt = __ballot_sync(0xffffffffu, prev_haz[h] != 0);
+						uint32_t scan = writers ? pt : pw;	/* only pairs with a writer on one side matter */
+						if (touching) {
+							while (scan) {
+								const int j = __ffs(scan) - 1;
+								scan &= scan - 1;
+								const uint64_t jlo = __shfl_sync(0xffffffffu, prev_lo[h], j);
+								const uint64_t jhi = __shfl_sync(0xffffffffu, prev_hi[h], j);
+								const uint32_t jhaz = __shfl_sync(0xffffffffu, prev_haz[h], j);
+								if (haz != 0 && (jhaz >= 2 || haz >= 2) &&
+								    (jhaz == 3 || haz == 3 || (lo < jhi && jlo < hi))) hit = true;
+							}
 						}
 					}
 					drain = __any_sync(0xffffffffu, hit);
-					prev_lo = lo; prev_hi = hi; prev_haz = haz;
+#pragma unroll
+					for (int h = kHist - 1; h > 0; h--) { prev_lo[h] = prev_lo[h - 1]; prev_hi[h] = prev_hi[h - 1]; prev_haz[h] = prev_haz[h - 1]; }
+					prev_lo[0] = lo; prev_hi[0] = hi; prev_haz[0] = haz;
 				}
 
 				/* counters for get_bdevs_iostat */

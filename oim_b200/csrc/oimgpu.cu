@@ -724,6 +724,7 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 
 	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
 		CU_OK(cudaHostAlloc((void **)&L->h_kick[k], sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 3, cudaHostAllocDefault));
+		memset(L->h_kick[k], 0, sizeof(KickHeader));
 		CU_OK(cudaEventCreateWithFlags(&L->kick_ev[k], cudaEventDisableTiming));
 	}
 	CU_OK(cudaMalloc((void **)&L->d_kick, sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 3));	/* ring + device-array + virtqueue per queue */
@@ -943,6 +944,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	if (nd == 0) return 0;
 	const uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap);
 	KickHeader *kh = (KickHeader *)L->h_kick[slot];
+	memset(kh, 0, sizeof(*kh));	/* run-to-completion: persistent = 0 (the staging buffer is recycled pinned memory) */
 	kh->next = grid;	/* queues 0..grid-1 are taken statically by CTA index */
 	kh->nqueues = nd;
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));

@@ -220,11 +220,10 @@ def fuzz_trace(n: int, num_blocks: int, *, block_size: int = 512, seed: int = 1,
     cursor = [0]
 
     def alloc(nbytes: int, align: int = 1) -> int:
-        """arena offset for a client buffer; offsets start at 64 so that offset+base != base"""
+        """arena offset for a client buffer.  Never reused: two requests never share client memory, as
+        no initiator hands one buffer to two commands in flight (the device tracks LBA hazards, not
+        aliasing of guest memory).  The arena grows to whatever the trace needs."""
         o = -(-(cursor[0] + 64) // align) * align
-        if o + nbytes > arena_bytes - 64:
-            cursor[0] = 0
-            o = -(-64 // align) * align
         cursor[0] = o + nbytes
         return o
 
@@ -363,7 +362,7 @@ def fuzz_trace(n: int, num_blocks: int, *, block_size: int = 512, seed: int = 1,
                   [(o + i * 512, 512) for i in range(k)])
 
     reqs, iovs = b.arrays()
-    t = Trace(reqs, iovs, arena_bytes, f"fuzz-{seed}", {"n": n})
+    t = Trace(reqs, iovs, max(arena_bytes, cursor[0] + 4096), f"fuzz-{seed}", {"n": n})
     t.meta["param_payloads"] = getattr(b, "_payloads", [])
     return t
 
@@ -408,8 +407,6 @@ def primary_trace(n: int, *, seed: int = 1, target: int = 0, arena_bytes: int = 
 
     def alloc(nbytes, align=1):
         o = -(-cur[0] // align) * align
-        if o + nbytes > arena_bytes - 64:
-            o = 64
         cur[0] = o + nbytes
         return o
 
@@ -487,6 +484,6 @@ def primary_trace(n: int, *, seed: int = 1, target: int = 0, arena_bytes: int = 
                 payloads.append((a, seg))
                 pos += l
     reqs, iovs = b.arrays()
-    t = Trace(reqs, iovs, arena_bytes, f"primary-{seed}", {"n": n})
+    t = Trace(reqs, iovs, max(arena_bytes, cur[0] + 4096), f"primary-{seed}", {"n": n})
     t.meta["param_payloads"] = payloads
     return t

@@ -63,6 +63,36 @@ def test_cuda_hazards_same_lba_chain(gpu, oracles):
     assert (got[1] == want[1]).all() and (got[2] == want[2]).all()
 
 
+def test_cuda_hazards_two_passes_apart(gpu, oracles):
+    """movers are not in lock-step: while one is still busy with a 4 MiB write of pass p, the others run
+    through pass p+1 (unrelated small reads) and reach pass p+2, which reads what pass p writes"""
+    nb = 1 << 16
+    b = abi.Batch(0)
+    off = 4096
+    big = 8192                                           # blocks = 4 MiB, the largest transfer
+    for rep in range(6):
+        base = (rep * 3 * 8192) % (nb - 3 * 8192)
+        b.write(base, big, [(off, big * 512)], opcode=abi.WRITE_16)          # pass p: one long write ...
+        off += big * 512
+        for i in range(31):                                                  # ... padded to a full pass
+            b.read(nb - 64 + (i % 8), 1, [(off, 512)])
+            off += 512
+        for i in range(32):                                                  # pass p+1: unrelated
+            b.read(nb - 128 + (i % 8), 1, [(off, 512)])
+            off += 512
+        for i in range(32):                                                  # pass p+2: reads across the big write
+            b.read(base + i * 250, 16, [(off, 8192)])
+            off += 8192
+    reqs, iovs = b.arrays()
+    t = traces.Trace(reqs, iovs, off + 4096, "two-apart")
+    want = util.run_oracle(oracles.PortOracle, t, nb)
+    for _ in range(3):
+        got = util.run_cuda(gpu, t, nb)
+        util.assert_cpls_equal(got[0], want[0], t.reqs)
+        assert (got[1] == want[1]).all(), "a read overtook the write two passes ahead of it"
+        assert (got[2] == want[2]).all()
+
+
 def test_cuda_non_pow2_block_size(gpu, oracles):
     nb, bs = 9000, 520
     t = traces.fuzz_trace(300, nb, block_size=bs, seed=77, max_io_blocks=16)
