@@ -383,7 +383,7 @@ def run_ours(args, rank, world, local):
     vq = None
     if not args.no_vq:
         from oim_b200 import vring
-        vnq, vper, vring_size = 1024, 256, 1024
+        vnq, vper, vring_size = 4096, 256, 1024
         g = vring.build_uniform_queues(vnq, vper, NUM_BLOCKS, ring_size=vring_size, seed=plan["trace_seed"] + 5)
         guest = torch.empty(g.total_bytes(), dtype=torch.uint8, device="cuda")
         guest[:g.data_off] = torch.from_numpy(g.arena).cuda()

@@ -703,15 +703,21 @@ __device__ __forceinline__ uint64_t gpa_to_dev_len(const LunCtx &L, uint64_t gpa
 struct VDesc { uint64_t addr; uint32_t len; uint16_t flags, next; };	/* struct vring_desc */
 enum : uint16_t { VD_NEXT = 1, VD_WRITE = 2, VD_INDIRECT = 4 };
 
+__device__ __forceinline__ VDesc decode_desc(const int4 v)
+{
+	VDesc d;
+	d.addr = (uint64_t)(uint32_t)v.x | (uint64_t)(uint32_t)v.y << 32;
+	d.len = (uint32_t)v.z;
+	d.flags = (uint16_t)((uint32_t)v.w & 0xffff);
+	d.next = (uint16_t)((uint32_t)v.w >> 16);
+	return d;
+}
+
 __device__ __forceinline__ VDesc load_desc(const uint8_t *p)
 {
 	VDesc d;
 	if (((uintptr_t)p & 15) == 0) {
-		const int4 v = ld_cg16(p);
-		d.addr = (uint64_t)(uint32_t)v.x | (uint64_t)(uint32_t)v.y << 32;
-		d.len = (uint32_t)v.z;
-		d.flags = (uint16_t)((uint32_t)v.w & 0xffff);
-		d.next = (uint16_t)((uint32_t)v.w >> 16);
+		d = decode_desc(ld_cg16(p));
 	} else {
 		uint64_t a = 0; uint32_t l = 0, w = 0;
 		for (int k = 7; k >= 0; k--) a = a << 8 | ld_cg8(p + k);
@@ -766,15 +772,14 @@ __device__ __forceinline__ int desc_to_iov(const LunCtx &L, oimgpu_iov *row, uin
 /* task_data_setup (vhost_scsi.c:490-624) for the chain starting at ring index `head`.  Fills the
  * request slot `r` (virtio header + direction + SG row reference) and *resp (device address of the
  * guest's response buffer).  Returns false for every `goto invalid_task`. */
-__device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc &q, uint32_t head, oimgpu_req &r,
+__device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc &q, uint32_t head, VDesc d, oimgpu_req &r,
 						oimgpu_iov *row, uint32_t row_index, uint64_t *resp)
 {
 	*resp = 0;
-	/* spdk_vhost_vq_get_desc (vhost.c:219-247) */
+	/* spdk_vhost_vq_get_desc (vhost.c:219-247); `d` = desc[head], loaded one pass ahead by the caller */
 	if (head >= q.vq_size) return false;
 	const uint8_t *table = q.vq_desc;
 	uint32_t table_size = q.vq_size;
-	VDesc d = load_desc(table + (size_t)head * 16);
 	if (d.flags & VD_INDIRECT) {
 		table_size = d.len / 16;
 		table = (const uint8_t *)(uintptr_t)gpa_to_dev_len(L, d.addr, 16ull * table_size);
@@ -1017,6 +1022,17 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					}
 				}
 			}
+			/* virtqueue mode walks guest memory: avail entry -> head descriptor -> chain -> request
+			 * header, each a dependent DRAM access under a saturated memory system.  The first two
+			 * are loaded one pass ahead into registers (an L2 prefetch of the rest does not survive:
+			 * at 6.5 TB/s the payload stream turns the 126 MB L2 over within one pass). */
+			uint32_t vq_head_cur = 0, vq_head_nxt = 0;
+			int4 vq_raw = make_int4(0, 0, 0, 0);	/* desc[head] of the coming pass, still in flight */
+			const bool vq_tbl_aligned = ((uintptr_t)q.vq_desc & 15) == 0;
+			if (q.count && q.mode == QMODE_VRING && (uint32_t)lane < min((uint32_t)kPass, q.count)) {
+				vq_head_cur = reinterpret_cast<const uint16_t *>(q.vq_avail + 4)[(q.head + lane) & (q.vq_size - 1)];
+				if (vq_tbl_aligned && vq_head_cur < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_cur * 16);
+			}
 			for (uint32_t done = 0; done < q.count; done += kPass) {
 				const uint32_t n = min((uint32_t)kPass, q.count - done);
 				const uint32_t slot0 = q.head + done;
@@ -1045,11 +1061,20 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				uint64_t my_resp = 0;
 				uint32_t my_head = 0;
 				bool chain_ok = true;
+				const bool vq_more = q.mode == QMODE_VRING && done + kPass < q.count &&
+						     (uint32_t)lane < min((uint32_t)kPass, q.count - done - kPass);
+				if (vq_more)	/* next pass's avail entries: in flight while this pass is walked */
+					vq_head_nxt = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(slot0 + kPass + lane) & (q.vq_size - 1)];
 				if (q.mode == QMODE_VRING && active) {
-					my_head = reinterpret_cast<const uint16_t *>(q.vq_avail + 4)[(slot0 + lane) & (q.vq_size - 1)];
-					chain_ok = vq_task_data_setup(L, q, my_head, sh.req[lane], const_cast<oimgpu_iov *>(q.iovs) + (size_t)lane * kIovRow,
+					my_head = vq_head_cur;
+					VDesc d0 = {0, 0, 0, 0};
+					if (my_head < q.vq_size) d0 = vq_tbl_aligned ? decode_desc(vq_raw) : load_desc(q.vq_desc + (size_t)my_head * 16);
+					chain_ok = vq_task_data_setup(L, q, my_head, d0, sh.req[lane], const_cast<oimgpu_iov *>(q.iovs) + (size_t)lane * kIovRow,
 								      lane * kIovRow, &my_resp);
 				}
+				/* next pass's head descriptors: issued now, consumed after the hazard analysis, the
+				 * reap and the segment emission of this pass */
+				if (vq_more && vq_tbl_aligned && vq_head_nxt < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_nxt * 16);
 				if (active && chain_ok) parse_request(L, q, sh.req[lane], s);
 				else if (active) {
 					/* invalid_request(): used element of length 0, response untouched (vhost_scsi.c:347-358) */
@@ -1090,11 +1115,11 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				/* hazards against the passes whose movers may still be running.  Waiting for the previous
 				 * fill's `empty` barrier covers all of them: a mover arrives there only after it has
 				 * finished its share of every earlier fill. */
-				bool drain = false;
+				uint32_t drain = 0;	/* 0 = none, d = wait until the movers have left fill c-d */
 				{
-					bool hit = false;
 #pragma unroll
-					for (int h = 0; h < kHist; h++) {
+					for (int h = kHist - 1; h >= 0; h--) {
+						bool hit = false;
 						const uint32_t pw = __ballot_sync(0xffffffffu, prev_haz[h] >= 2);
 						const uint32_t pt = __ballot_sync(0xffffffffu, prev_haz[h] != 0);
 						uint32_t scan = writers ? pt : pw;	/* only pairs with a writer on one side matter */
@@ -1109,8 +1134,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 								    (jhaz == 3 || haz == 3 || (lo < jhi && jlo < hi))) hit = true;
 							}
 						}
+						if (__any_sync(0xffffffffu, hit)) drain = (uint32_t)h + 1;	/* nearest pass wins */
 					}
-					drain = __any_sync(0xffffffffu, hit);
 #pragma unroll
 					for (int h = kHist - 1; h > 0; h--) { prev_lo[h] = prev_lo[h - 1]; prev_hi[h] = prev_hi[h - 1]; prev_haz[h] = prev_haz[h - 1]; }
 					prev_lo[0] = lo; prev_hi[0] = hi; prev_haz[0] = haz;
@@ -1165,7 +1190,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						st.nseg = tot_seg;
 						st.nunits = tot_unit;
 						st.nwaves = nwaves;
-						st.drain = (drain || r0 > 0) ? 1 : 0;
+						st.drain = (r0 > 0) ? 1 : drain;
 						st.stop = 0;
 						st.ncpl = r1 - r0;
 						st.cpl_ring = q.cpls;
@@ -1183,6 +1208,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					fills++;
 					r0 = r1;
 				}
+				vq_head_cur = vq_head_nxt;
 			}
 			if (q.mode == QMODE_VRING && lane == 0) q.vq_state->last_avail = (vq_last_avail + q.count) & 0xffff;
 			if (persistent && q.mode == QMODE_SLOTS && lane == 0) q.vq_state->last_avail = q.head + q.count;
@@ -1230,9 +1256,10 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			mbar_wait(&sh.full[sidx], (c / kStages) & 1);
 			if (st.stop) break;
 			const uint32_t nseg = st.nseg, nunits = st.nunits, nw = st.nwaves;
-			if (st.drain && c > 0) {
-				/* RAW/WAW/WAR against the previous fill: wait until every mover has left it */
-				const uint32_t p = c - 1;
+			if (st.drain && c >= st.drain) {
+				/* RAW/WAW/WAR against fill c-drain: wait until every mover has left it (a mover
+				 * arrives on `empty` only after finishing its share of all earlier fills too) */
+				const uint32_t p = c - st.drain;
 				mbar_wait(&sh.empty[p % kStages], (p / kStages) & 1);
 			}
 			for (uint32_t w = 0; w < nw; w++) {
