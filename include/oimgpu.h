@@ -207,11 +207,19 @@ int oimgpu_vhost_ctrlr_list(struct oimgpu_ctrlr_info *out, int max);
 
 /* ---- data path -------------------------------------------------------------------------- */
 
-typedef struct oimgpu_lun oimgpu_lun;	/* one attached SCSI target: backing store + queues + stream */
+typedef struct oimgpu_lun oimgpu_lun;	/* a data-path session on a vhost controller: queues + stream */
 
-/* Open the data path of target `scsi_target_num` of `ctrlr` with `num_queues` request queues of
- * `queue_size` slots (power of two, <= OIMGPU_MAX_VQ_SIZE) each.  The LUN gets its own CUDA
- * stream on the GPU that holds the bdev. */
+/* Open a data path on `ctrlr` with `num_queues` request queues of `queue_size` slots (power of two,
+ * <= OIMGPU_MAX_VQ_SIZE) each, on its own CUDA stream.
+ *
+ * As in the reference, the queues belong to the CONTROLLER: every request names its SCSI device in
+ * lun[1] and reaches whichever of the eight targets that is (spdk_vhost_scsi_task_init_target,
+ * S/lib/vhost/vhost_scsi.c:361-387); targets added to or removed from the controller while the
+ * session is open are hot-plugged into it (spdk_vhost_scsi_dev_add_tgt / _remove_tgt, :951-1100).
+ *
+ * scsi_target_num >= 0 names the session's home device: it must exist, pins its bdev, decides the
+ * GPU, and is what oimgpu_lun_iostat / _set_removed refer to.  scsi_target_num == -1 opens a
+ * session with no home device (what a vhost-user connection is): it may start with zero targets. */
 int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t num_queues,
 		    uint32_t queue_size, oimgpu_lun **out);
 int oimgpu_lun_close(oimgpu_lun *lun);
@@ -255,6 +263,8 @@ int oimgpu_submit_and_wait(oimgpu_lun *lun, uint32_t nq, uint32_t per_q,
 			   uint32_t niovs, struct oimgpu_cpl *cpls, int mem);
 
 int oimgpu_lun_iostat(oimgpu_lun *lun, struct oimgpu_iostat *out);
+/* the same counters for any target the session reaches (-ENODEV: none at that number) */
+int oimgpu_lun_target_iostat(oimgpu_lun *lun, int scsi_target_num, struct oimgpu_iostat *out);
 /* raw CUDA stream handle (cudaStream_t) of the LUN, for callers that time with CUDA events */
 void *oimgpu_lun_stream(oimgpu_lun *lun);
 

@@ -106,8 +106,8 @@ __device__ __forceinline__ void scsi_readwrite(const LunCtx &L, LaneState &s, ui
 	}
 	s.data_transferred = s.length;
 	s.off = lba * L.block_size;
-	s.store_lo = lba;
-	s.store_hi = lba + nblk;
+	s.store_lo = (uint64_t)(uintptr_t)L.store[0] + s.off;	/* absolute: two targets conflict only on a shared bdev */
+	s.store_hi = s.store_lo + nblk * L.block_size;
 	s.op = is_read ? OP_READ : OP_WRITE;
 	s.hazard = nblk ? (is_read ? 1 : 2) : 0;
 }
@@ -147,7 +147,7 @@ __device__ __noinline__ void scsi_unmap(const LunCtx &L, const QueueDesc &q, con
 			g.len = bytes;
 			g.first_unit = first_unit + units;
 			g.wave = wave;
-			g.mirror = 1;
+			g.mirror = L.nreplicas > 1 ? (uint8_t)(L.target + 1) : 0;
 		}
 		nseg++;
 		units += units_of(bytes);
@@ -209,6 +209,15 @@ __device__ __noinline__ void scsi_control(const LunCtx &L, const QueueDesc &q, c
 
 __device__ void scsi_primary(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, uint32_t cnt, uint32_t len, LaneState &s);
 
+/* spdk_vhost_scsi_task_init_target (vhost_scsi.c:361-387): all targets of a controller share its
+ * virtqueues; lun[1] selects the SCSI device.  nullptr = no such device (VIRTIO_SCSI_S_BAD_TARGET). */
+__device__ __forceinline__ const LunCtx *target_ctx(const LunCtx &L, const uint8_t *lun)
+{
+	if (lun[0] != 1 || lun[1] >= OIMGPU_CTRLR_MAX_DEVS) return nullptr;
+	if (lun[1] == L.target) return &L;
+	return L.peer[lun[1]];
+}
+
 __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, LaneState &s)
 {
 	const uint32_t cnt = r.iovcnt;
@@ -216,7 +225,7 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 	const uint32_t dxfer_dir = from_dev ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV;
 	uint32_t len = 0, nonzero = 0, units = 0;
 
-	s.op = OP_NONE; s.nseg = 0; s.valid = 1; s.length = 0; s.off = 0;
+	s.op = OP_NONE; s.nseg = 0; s.valid = 1; s.length = 0; s.off = 0; s.tgt = L.target;
 	s.store_lo = s.store_hi = 0;
 	s.status = SC_GOOD; s.sk = 0; s.asc = 0;
 	s.data_transferred = 0; s.units = 0; s.hazard = 0; s.response = OIMGPU_S_OK; s.resp_valid = 1;
@@ -243,22 +252,25 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 
 	/* ---- spdk_vhost_scsi_task_init_target (vhost_scsi.c:361-387) ---- */
 	const uint16_t lun_id = (uint16_t)((((uint16_t)r.lun[2] << 8) | r.lun[3]) & 0x3FFF);
-	if (r.lun[0] != 1 || r.lun[1] >= OIMGPU_CTRLR_MAX_DEVS || r.lun[1] != L.target) {
+	const LunCtx *tp = target_ctx(L, r.lun);
+	if (tp == nullptr) {
 		s.response = OIMGPU_S_BAD_TARGET;	/* resp->response only; nothing else is written */
 		return;
 	}
+	s.tgt = r.lun[1];
+	const LunCtx &T = *tp;	/* the SCSI device the request addresses: everything below is per target */
 	const uint8_t *cdb = r.cdb;
-	if (L.removed || lun_id != 0) {
+	if (T.removed || lun_id != 0) {
 		/* spdk_scsi_task_process_null_lun (task.c:258-293) */
 		if (cdb[0] == 0x12) {
-			scsi_control(L, q, r, cnt, len, s, 0);
+			scsi_control(T, q, r, cnt, len, s, 0);
 		} else {
 			set_check(s, SK_ILLEGAL_REQUEST, ASC_LUN_NOT_SUPPORTED);
 			s.data_transferred = 0;
 		}
 		return;
 	}
-	if (L.lun_removed) {
+	if (T.lun_removed) {
 		set_check(s, SK_ABORTED_COMMAND, ASC_NONE);	/* spdk_scsi_task_process_abort */
 		return;
 	}
@@ -268,41 +280,41 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 	case 0x08: case 0x0a: {
 		uint64_t lba = (uint64_t)cdb[1] << 16 | (uint64_t)cdb[2] << 8 | cdb[3];
 		uint32_t xl = cdb[4] ? cdb[4] : 256;
-		scsi_readwrite(L, s, dxfer_dir, len, lba, xl, cdb[0] == 0x08);
+		scsi_readwrite(T, s, dxfer_dir, len, lba, xl, cdb[0] == 0x08);
 		break;
 	}
 	case 0x28: case 0x2a:
-		scsi_readwrite(L, s, dxfer_dir, len, be32(&cdb[2]), be16(&cdb[7]), cdb[0] == 0x28);
+		scsi_readwrite(T, s, dxfer_dir, len, be32(&cdb[2]), be16(&cdb[7]), cdb[0] == 0x28);
 		break;
 	case 0xa8: case 0xaa:
-		scsi_readwrite(L, s, dxfer_dir, len, be32(&cdb[2]), be32(&cdb[6]), cdb[0] == 0xa8);
+		scsi_readwrite(T, s, dxfer_dir, len, be32(&cdb[2]), be32(&cdb[6]), cdb[0] == 0xa8);
 		break;
 	case 0x88: case 0x8a:
-		scsi_readwrite(L, s, dxfer_dir, len, be64(&cdb[2]), be32(&cdb[10]), cdb[0] == 0x88);
+		scsi_readwrite(T, s, dxfer_dir, len, be64(&cdb[2]), be32(&cdb[10]), cdb[0] == 0x88);
 		break;
 	case 0x25:
-		scsi_control(L, q, r, cnt, len, s, 1);
+		scsi_control(T, q, r, cnt, len, s, 1);
 		break;
 	case 0x9e:
-		if ((cdb[1] & 0x1f) == 0x10) scsi_control(L, q, r, cnt, len, s, 2);
+		if ((cdb[1] & 0x1f) == 0x10) scsi_control(T, q, r, cnt, len, s, 2);
 		else set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
 		break;
 	case 0x35: case 0x91: {	/* SYNCHRONIZE CACHE: bounds check only; FLUSH is a no-op on a RAM disk */
 		uint64_t lba; uint32_t n;
 		if (cdb[0] == 0x35) { lba = be32(&cdb[2]); n = be16(&cdb[7]); }
 		else { lba = be64(&cdb[2]); n = be32(&cdb[10]); }
-		if (n == 0) n = (uint32_t)(L.num_blocks - lba);
-		if (n != 0 && (lba >= L.num_blocks || n > L.num_blocks || lba > L.num_blocks - n)) {
+		if (n == 0) n = (uint32_t)(T.num_blocks - lba);
+		if (n != 0 && (lba >= T.num_blocks || n > T.num_blocks || lba > T.num_blocks - n)) {
 			set_check(s, SK_NO_SENSE, ASC_NONE);
 		}
 		break;
 	}
 	case 0x42:
-		scsi_unmap(L, q, r, cnt, s, nullptr, 0, 0);
+		scsi_unmap(T, q, r, cnt, s, nullptr, 0, 0);
 		break;
 	/* ---- spdk_bdev_scsi_process_primary (scsi_bdev.c:1827-2077), table-free commands ---- */
 	case 0x03:
-		scsi_control(L, q, r, cnt, len, s, 3);
+		scsi_control(T, q, r, cnt, len, s, 3);
 		break;
 	case 0x4c: case 0x4d:	/* LOG SELECT / LOG SENSE */
 		set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
@@ -310,7 +322,7 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 	case 0x00: case 0x1b:	/* TEST UNIT READY / START STOP UNIT */
 		break;
 	case 0x12: case 0xa0: case 0x15: case 0x55: case 0x1a: case 0x5a:
-		scsi_primary(L, q, r, cnt, len, s);
+		scsi_primary(T, q, r, cnt, len, s);
 		break;
 	default:
 		set_check(s, SK_ILLEGAL_REQUEST, ASC_INVALID_OPCODE);
@@ -326,11 +338,13 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 __device__ __forceinline__ void emit_segments(const LunCtx &L, const QueueDesc &q, const oimgpu_req &r, LaneState &s,
 					      Segment *out, uint32_t first_unit, uint16_t wave)
 {
+	const LunCtx &T = (s.tgt == L.target) ? L : *L.peer[s.tgt];
+	const uint8_t mirror_tag = T.nreplicas > 1 ? (uint8_t)(s.tgt + 1) : 0;	/* writes fan out to the replicas */
 	if (s.op == OP_UNMAP) {
-		scsi_unmap(L, q, r, r.iovcnt, s, out, first_unit, wave);
+		scsi_unmap(T, q, r, r.iovcnt, s, out, first_unit, wave);
 		return;
 	}
-	uint8_t *pos = L.store[0] + s.off;
+	uint8_t *pos = T.store[0] + s.off;
 	const bool rd = s.op == OP_READ;
 	uint32_t k = 0, u = first_unit;
 	for (uint32_t j = 0; j < r.iovcnt; j++) {
@@ -340,7 +354,7 @@ __device__ __forceinline__ void emit_segments(const LunCtx &L, const QueueDesc &
 		uint8_t *client = (uint8_t *)(uintptr_t)v.addr;
 		g.src = rd ? pos : client;
 		g.dst = rd ? client : pos;
-		g.mirror = rd ? 0 : 1;
+		g.mirror = rd ? 0 : mirror_tag;
 		g.len = v.len;
 		g.first_unit = u;
 		g.wave = wave;
@@ -1142,13 +1156,22 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				}
 
 				/* counters for get_bdevs_iostat */
-				const bool ok = active && s.resp_valid && s.response == OIMGPU_S_OK && s.status == SC_GOOD;
+				const bool good = active && s.resp_valid && s.response == OIMGPU_S_OK && s.status == SC_GOOD;
+				const bool own = !good || s.tgt == L.target;	/* failures are booked on the session's device */
+				const bool ok = good && own;
 				st_rd += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_READ));
 				st_wr += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_WRITE));
 				st_um += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_UNMAP));
-				st_er += __popc(__ballot_sync(0xffffffffu, active && !ok));
+				st_er += __popc(__ballot_sync(0xffffffffu, active && !good));
 				if (ok && s.op == OP_READ) st_rb += s.length;
 				if (ok && s.op == OP_WRITE) st_wb += s.length;
+				if (good && !own && (s.op == OP_READ || s.op == OP_WRITE || s.op == OP_UNMAP)) {
+					/* another device of the controller: book it there (rare path, plain atomics) */
+					LunCtx *P = L.peer[s.tgt];
+					const int k = s.op == OP_READ ? 0 : s.op == OP_WRITE ? 1 : 2;
+					atomicAdd(&P->stats[k], 1ull);
+					if (k < 2) atomicAdd(&P->stats[4 + k], (unsigned long long)s.length);
+				}
 
 				/* rounds: as many whole requests as fit in one stage's segment table */
 				uint32_t r0 = 0;
@@ -1249,7 +1272,6 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 	} else {
 		/* ======================= MOVERS ======================= */
 		const int mw = warp - 1;
-		const uint32_t nrep = lun->nreplicas;
 		for (uint32_t c = 0;; c++) {
 			const uint32_t sidx = c % kStages;
 			Stage &st = sh.stage[sidx];
@@ -1279,7 +1301,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						if (src) move_unit(dst + off, src + off, nbytes, lane);
 						else zero_unit(dst + off, nbytes, lane);
 					} else {
-						mirror_unit(*lun, dst, src, off, nbytes, lane, nrep);
+						const LunCtx &T = (g.mirror - 1 == lun->target) ? *lun : *lun->peer[g.mirror - 1];
+						mirror_unit(T, dst, src, off, nbytes, lane, T.nreplicas);
 					}
 				}
 				if (nw > 1) movers_barrier();

@@ -68,7 +68,8 @@ struct LunCtx {
 	uint64_t num_blocks;
 	uint32_t block_size;
 	uint32_t block_shift;		/* log2(block_size), or 0xffffffff when not a power of two */
-	uint8_t  target;		/* SCSI target number of this LUN inside its controller */
+	uint8_t  target;		/* SCSI target number of this LUN inside its controller (0xff: none -
+					 * a controller-wide session that reaches every device through peer[]) */
 	uint8_t  removed;		/* session saw a hot-remove of this target */
 	uint8_t  lun_removed;
 	/* guest memory table for virtqueue mode: struct rte_vhost_memory (rte_vhost.h:52-66) with
@@ -82,6 +83,9 @@ struct LunCtx {
 	uint16_t port_index;
 	uint8_t  protocol_id;
 	unsigned long long stats[8];	/* read ops, write ops, unmap ops, other, bytes r/w/unmapped, errors */
+	/* the other SCSI devices of the same vhost controller (svdev->scsi_dev[8], vhost_scsi.c:80-94):
+	 * one set of virtqueues serves them all */
+	LunCtx *peer[OIMGPU_CTRLR_MAX_DEVS];
 };
 
 /* per-launch work header: CTAs draw queue indices from `next` so that uneven queue counts and
@@ -133,14 +137,14 @@ struct Segment {
 	uint64_t len;
 	uint32_t first_unit;		/* exclusive prefix sum of units over the round's segments */
 	uint16_t wave;
-	uint16_t mirror;		/* 1: dst is in the backing store -> replicate to peers */
+	uint16_t mirror;		/* t+1: dst is in the store of target t, which has replicas to update; 0: plain */
 };
 
 /* What a parser lane knows about its request after decode; lives in shared memory so that the
  * parser's state never competes with the movers' data registers */
 struct LaneState {
 	uint64_t off;			/* byte offset in the backing store */
-	uint64_t store_lo, store_hi;	/* block range touched, for hazard detection */
+	uint64_t store_lo, store_hi;	/* device address range touched, for hazard detection */
 	uint32_t length;		/* task->length: sum of SG element lengths */
 	uint32_t nseg;			/* segments this request emits */
 	uint32_t units;
@@ -152,6 +156,7 @@ struct LaneState {
 	uint8_t  response;
 	uint8_t  resp_valid;
 	uint8_t  hazard;		/* 0 none, 1 reads store, 2 writes store, 3 barrier (multi-range writer) */
+	uint8_t  tgt;			/* SCSI target the request addressed (valid once the target check passed) */
 	uint8_t  scratch[256];		/* control payloads: READ CAPACITY, REQUEST SENSE, INQUIRY pages (<= 125 B),
 					 * MODE SENSE (<= 188 B), REPORT LUNS */
 };

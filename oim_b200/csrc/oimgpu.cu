@@ -50,12 +50,17 @@ static_assert(sizeof(Segment) == 32, "Segment layout");
 		}                                                                            \
 	} while (0)
 
+struct oimgpu_lun;
+
 namespace {
 
 struct Device {
 	int ordinal = -1;
 	int sm_count = 0;
 	uint64_t bytes_allocated = 0;
+	/* housekeeping (zero-fill, raw store access) runs here, never on the legacy stream and never behind
+	 * a cudaDeviceSynchronize: a resident poller kernel would make either wait for its watchdog */
+	cudaStream_t util = nullptr;
 };
 
 struct Bdev {
@@ -89,6 +94,7 @@ struct Registry {
 	int rbd_count = 0;
 	std::map<void *, size_t> registered;
 	int open_luns = 0;
+	std::vector<oimgpu_lun *> handles;	/* open data-path sessions: told about target hot-plug */
 };
 
 Registry g;
@@ -160,6 +166,11 @@ struct oimgpu_lun {
 	uint32_t *d_flags = nullptr;
 	bool poller_active = false;
 	uint32_t poller_grid = 0;
+	uint32_t poller_max_ctas = 0, poller_idle_ms = 0;	/* as given to start_poller: reused when a hot-unplug restarts it */
+	/* the other SCSI devices of the controller, reachable through the same queues (LunCtx::peer) */
+	LunCtx *d_peer[OIMGPU_CTRLR_MAX_DEVS] = {};
+	std::string peer_bdev[OIMGPU_CTRLR_MAX_DEVS];
+	bool any_mirror = false;
 	VqState *d_vq_state = nullptr;		/* [num_queues] ring cursors */
 	oimgpu_iov *d_iov_scratch = nullptr;	/* [grid_cap][32][kIovRow] SG rows built by the parser lanes */
 };
@@ -172,6 +183,132 @@ static int find_device_slot(int ordinal)
 		if (g.devices[i].ordinal == ordinal) return (int)i;
 	}
 	return -1;
+}
+
+/* what the kernel needs to know about one SCSI device: geometry, stores, and the identity strings
+ * INQUIRY reports: spdk_scsi_dev_construct("Target N", ...) + port 0 "vhost", SAS
+ * (vhost_scsi.c:1004-1013); the device id is the slot add_vhost_scsi_lun took in the global table */
+static void fill_lun_ctx(LunCtx &c, const Bdev &b, const Ctrlr &ctrlr, int target)
+{
+	for (size_t r = 0; r < b.stores.size(); r++) c.store[r] = b.stores[r];
+	c.nreplicas = (uint32_t)b.stores.size();
+	c.num_blocks = b.num_blocks;
+	c.block_size = b.block_size;
+	c.block_shift = (b.block_size & (b.block_size - 1)) ? 0xffffffffu : (uint32_t)__builtin_ctz(b.block_size);
+	c.target = (uint8_t)target;
+	snprintf(c.bdev_name, sizeof(c.bdev_name), "%s", b.name.c_str());
+	snprintf(c.product_name, sizeof(c.product_name), "%s", b.product.c_str());
+	snprintf(c.dev_name, sizeof(c.dev_name), "Target %d", target);
+	snprintf(c.port_name, sizeof(c.port_name), "vhost");
+	c.scsi_dev_id = ctrlr.scsi_id[target];
+	c.port_index = 0;
+	c.protocol_id = 0x06;
+}
+
+static bool device_reachable(int from, int to)
+{
+	if (from == to) return true;
+	int can = 0;
+	if (cudaDeviceCanAccessPeer(&can, from, to) != cudaSuccess || !can) return false;
+	cudaSetDevice(from);
+	cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+	if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+	return e == cudaSuccess;
+}
+
+/* Bring the session's view of its controller up to date: every target other than the session's
+ * own gets a device-resident LunCtx reachable through peer[] (the reference keeps all eight in
+ * svdev->scsi_dev[], vhost_scsi.c:80-94, and hot-plugs them while a session runs,
+ * spdk_vhost_scsi_dev_add_tgt / _remove_tgt).  Caller holds g.mu. */
+static int refresh_peers_locked(oimgpu_lun *L)
+{
+	auto it = g.ctrlrs.find(L->ctrlr);
+	CU_OK(cudaSetDevice(L->device));
+	bool changed = false, restart = false;
+	std::string wants[OIMGPU_CTRLR_MAX_DEVS];
+	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		std::string &want = wants[t];
+		if (it != g.ctrlrs.end() && t != L->target) want = it->second->targets[t];
+		if (!want.empty()) {
+			auto bi = g.bdevs.find(want);
+			if (bi == g.bdevs.end() || !device_reachable(L->device, bi->second->devices[0])) want.clear();
+		}
+		if (want != L->peer_bdev[t] && !L->peer_bdev[t].empty()) restart = true;	/* a device goes away */
+		if (!want.empty() && g.bdevs[want]->stores.size() > 1 && !L->any_mirror) restart = true;	/* other kernel variant */
+	}
+	/* a resident poller may be in the middle of a pass on a device that is being unplugged: park it,
+	 * like the reference waits for the session's outstanding tasks (process_removed_devs,
+	 * vhost_scsi.c:236-289), and bring it back afterwards */
+	const bool was_polling = L->poller_active;
+	if (restart && was_polling) {
+		int rc = oimgpu_lun_stop_poller(L);
+		if (rc) return rc;
+	}
+	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		const std::string &want = wants[t];
+		if (want == L->peer_bdev[t]) continue;
+		changed = true;
+		if (!L->peer_bdev[t].empty()) {
+			auto bi = g.bdevs.find(L->peer_bdev[t]);
+			if (bi != g.bdevs.end() && bi->second->open_luns > 0) bi->second->open_luns--;
+		}
+		L->peer_bdev[t] = want;
+		if (want.empty()) {
+			L->h_ctx.peer[t] = nullptr;	/* the context itself is freed at close: a resident kernel may still hold it */
+			continue;
+		}
+		Bdev &b = *g.bdevs[want];
+		b.open_luns++;
+		LunCtx c;
+		memset(&c, 0, sizeof(c));
+		fill_lun_ctx(c, b, *it->second, t);
+		if (!L->d_peer[t]) CU_OK(cudaMalloc((void **)&L->d_peer[t], sizeof(LunCtx)));
+		CU_OK(cudaMemcpyAsync(L->d_peer[t], &c, sizeof(c), cudaMemcpyHostToDevice, L->copy_stream));
+		CU_OK(cudaStreamSynchronize(L->copy_stream));	/* `c` is pageable stack memory */
+		L->h_ctx.peer[t] = L->d_peer[t];
+	}
+	if (!changed) {
+		if (restart && was_polling) return oimgpu_lun_start_poller(L, L->poller_max_ctas, L->poller_idle_ms) < 0 ? -EIO : 0;
+		return 0;
+	}
+	L->any_mirror = L->h_ctx.nreplicas > 1;
+	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		if (!L->peer_bdev[t].empty() && g.bdevs[L->peer_bdev[t]]->stores.size() > 1) L->any_mirror = true;
+	}
+	/* publish the pointers after the contexts they point at (same stream); a separate stream so that a
+	 * resident poller kernel on L->stream does not block the update */
+	CU_OK(cudaMemcpyAsync((uint8_t *)L->d_ctx + offsetof(LunCtx, peer), L->h_ctx.peer, sizeof(L->h_ctx.peer),
+			      cudaMemcpyHostToDevice, L->copy_stream));
+	CU_OK(cudaStreamSynchronize(L->copy_stream));
+	if (!L->poller_active) CU_OK(cudaStreamSynchronize(L->stream));
+	if (restart && was_polling) {
+		int rc = oimgpu_lun_start_poller(L, L->poller_max_ctas, L->poller_idle_ms);
+		if (rc < 0) return rc;
+	}
+	return 0;
+}
+
+/* cudaFree waits for the whole device, and a resident poller kernel never finishes on its own: park
+ * the pollers of that GPU around a free and bring them back afterwards */
+static std::vector<oimgpu_lun *> park_pollers_locked(int device)
+{
+	std::vector<oimgpu_lun *> parked;
+	for (oimgpu_lun *L : g.handles) {
+		if (L->device == device && L->poller_active && oimgpu_lun_stop_poller(L) == 0) parked.push_back(L);
+	}
+	return parked;
+}
+
+static void unpark_pollers_locked(const std::vector<oimgpu_lun *> &parked)
+{
+	for (oimgpu_lun *L : parked) oimgpu_lun_start_poller(L, L->poller_max_ctas, L->poller_idle_ms);
+}
+
+static void refresh_ctrlr_sessions_locked(const std::string &ctrlr)
+{
+	for (oimgpu_lun *L : g.handles) {
+		if (L->ctrlr == ctrlr) refresh_peers_locked(L);
+	}
 }
 
 static std::string random_uuid()
@@ -240,6 +377,8 @@ extern "C" int oimgpu_init(const int *devices, int ndevices)
 		Device d;
 		d.ordinal = o;
 		d.sm_count = prop.multiProcessorCount;
+		CU_OK(cudaSetDevice(o));
+		CU_OK(cudaStreamCreateWithFlags(&d.util, cudaStreamNonBlocking));
 		g.devices.push_back(d);
 	}
 	/* mirrored bdevs store to peer HBM directly: enable P2P between every pair we manage */
@@ -293,6 +432,9 @@ extern "C" void oimgpu_fini(void)
 	g.bdev_order.clear();
 	g.ctrlr_order.clear();
 	memset(g.scsi_slot_used, 0, sizeof(g.scsi_slot_used));
+	for (auto &d : g.devices) {
+		if (d.util) { cudaSetDevice(d.ordinal); cudaStreamDestroy(d.util); }
+	}
 	g.devices.clear();
 	g.malloc_disk_count = g.rbd_count = 0;
 	g.inited = false;
@@ -325,9 +467,10 @@ static int alloc_store(int ordinal, uint64_t bytes, uint8_t **out)
 		return -ENOMEM;
 	}
 	/* spdk_dma_zmalloc: the disk starts zero-filled (bdev_malloc.c:401) */
-	CU_OK(cudaMemset(*out, 0, bytes));
-	CU_OK(cudaDeviceSynchronize());
-	g.devices[find_device_slot(ordinal)].bytes_allocated += bytes;
+	Device &dev = g.devices[find_device_slot(ordinal)];
+	CU_OK(cudaMemsetAsync(*out, 0, bytes, dev.util));
+	CU_OK(cudaStreamSynchronize(dev.util));
+	dev.bytes_allocated += bytes;
 	return 0;
 }
 
@@ -429,20 +572,29 @@ extern "C" int oimgpu_bdev_delete(const char *name)
 	if (!g.inited) return -ENODEV;
 	auto it = g.bdevs.find(name ? name : "");
 	if (it == g.bdevs.end()) return -ENODEV;
-	if (it->second->open_luns) return -EBUSY;	/* a data path is open on it */
+	/* a session opened on exactly this device pins it; controller-wide sessions let go of it below */
+	for (oimgpu_lun *L : g.handles) {
+		if (L->bdev == it->first) return -EBUSY;
+	}
 	/* spdk_bdev_unregister hot-removes the SCSI LUNs built on the bdev (lun.c:213-260): the targets go */
 	for (auto &kv : g.ctrlrs) {
+		bool touched = false;
 		for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
 			if (kv.second->targets[t] == it->first) {
 				g.scsi_slot_used[kv.second->scsi_id[t]] = false;
 				kv.second->targets[t].clear();
+				touched = true;
 			}
 		}
+		if (touched && !g.control_only) refresh_ctrlr_sessions_locked(kv.first);
 	}
+	if (it->second->open_luns) return -EBUSY;
 	g.bdev_order.erase(std::remove(g.bdev_order.begin(), g.bdev_order.end(), it->first), g.bdev_order.end());
 	for (size_t r = 0; r < it->second->stores.size() && !g.control_only; r++) {
+		auto parked = park_pollers_locked(it->second->devices[r]);
 		cudaSetDevice(it->second->devices[r]);
 		cudaFree(it->second->stores[r]);
+		unpark_pollers_locked(parked);
 		g.devices[find_device_slot(it->second->devices[r])].bytes_allocated -=
 			it->second->num_blocks * (uint64_t)it->second->block_size;
 	}
@@ -496,9 +648,19 @@ static int raw_access(const char *name, int replica, uint64_t offset, void *host
 	uint64_t size = b.num_blocks * (uint64_t)b.block_size;
 	if (offset > size || len > size - offset) return -EINVAL;
 	CU_OK(cudaSetDevice(b.devices[replica]));
-	CU_OK(cudaDeviceSynchronize());
-	if (write) CU_OK(cudaMemcpy(b.stores[replica] + offset, host, len, cudaMemcpyHostToDevice));
-	else CU_OK(cudaMemcpy(host, b.stores[replica] + offset, len, cudaMemcpyDeviceToHost));
+	/* everything already launched on the sessions' streams comes first (a resident poller cannot be
+	 * waited for: with one running, quiescing the I/O is the caller's business) */
+	for (oimgpu_lun *L : g.handles) {
+		if (!L->poller_active) {
+			CU_OK(cudaSetDevice(L->device));
+			CU_OK(cudaStreamSynchronize(L->stream));
+		}
+	}
+	CU_OK(cudaSetDevice(b.devices[replica]));
+	cudaStream_t st = g.devices[find_device_slot(b.devices[replica])].util;
+	if (write) CU_OK(cudaMemcpyAsync(b.stores[replica] + offset, host, len, cudaMemcpyHostToDevice, st));
+	else CU_OK(cudaMemcpyAsync(host, b.stores[replica] + offset, len, cudaMemcpyDeviceToHost, st));
+	CU_OK(cudaStreamSynchronize(st));
 	return 0;
 }
 
@@ -599,6 +761,7 @@ extern "C" int oimgpu_vhost_scsi_add_lun(const char *ctrlr, int scsi_target_num,
 	c.scsi_id[scsi_target_num] = slot;
 	c.targets[scsi_target_num] = bdev_name;
 	b->second->claimed++;
+	if (!g.control_only) refresh_ctrlr_sessions_locked(it->first);	/* hot-plug into running sessions */
 	return scsi_target_num;
 }
 
@@ -613,8 +776,12 @@ extern "C" int oimgpu_vhost_scsi_remove_target(const char *ctrlr, int scsi_targe
 	if (c.targets[scsi_target_num].empty()) return -ENODEV;
 	auto b = g.bdevs.find(c.targets[scsi_target_num]);
 	if (b != g.bdevs.end() && b->second->claimed > 0) b->second->claimed--;
+	/* a session opened on exactly this target keeps serving it until it is closed (the reference
+	 * defers the removal until the session has no task in flight, vhost_scsi.c:236-289); for every
+	 * other session of the controller the target disappears now */
 	g.scsi_slot_used[c.scsi_id[scsi_target_num]] = false;
 	c.targets[scsi_target_num].clear();
+	if (!g.control_only) refresh_ctrlr_sessions_locked(it->first);
 	return 0;
 }
 
@@ -683,16 +850,26 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	    queue_size > OIMGPU_MAX_VQ_SIZE) return -EINVAL;
 	auto it = g.ctrlrs.find(ctrlr_key(ctrlr));
 	if (it == g.ctrlrs.end()) return -ENODEV;
-	if (scsi_target_num < 0 || scsi_target_num >= OIMGPU_CTRLR_MAX_DEVS) return -EINVAL;
-	const std::string &bn = it->second->targets[scsi_target_num];
-	if (bn.empty()) return -ENODEV;
-	Bdev &b = *g.bdevs[bn];
+	/* target -1: a controller-wide session (what a vhost-user connection is): no device of its own,
+	 * every target is reached through peer[]; it lives on the GPU of the first target present */
+	const bool session = scsi_target_num == -1;
+	if (!session && (scsi_target_num < 0 || scsi_target_num >= OIMGPU_CTRLR_MAX_DEVS)) return -EINVAL;
+	std::string bn;
+	if (!session) {
+		bn = it->second->targets[scsi_target_num];
+		if (bn.empty()) return -ENODEV;
+	}
+	Bdev *bp = session ? nullptr : g.bdevs[bn].get();
+	int session_device = g.devices[0].ordinal;
+	for (int t = 0; session && t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		if (!it->second->targets[t].empty()) { session_device = g.bdevs[it->second->targets[t]]->devices[0]; break; }
+	}
 
 	auto L = std::make_unique<oimgpu_lun>();
-	L->ctrlr = it->second->name;
+	L->ctrlr = it->first;
 	L->bdev = bn;
-	L->target = scsi_target_num;
-	L->device = b.devices[0];
+	L->target = session ? 0xff : scsi_target_num;
+	L->device = session ? session_device : bp->devices[0];
 	L->sm_count = g.devices[find_device_slot(L->device)].sm_count;
 	L->num_queues = num_queues;
 	L->queue_size = queue_size;
@@ -704,21 +881,9 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	CU_OK(cudaEventCreateWithFlags(&L->bs_uploaded, cudaEventDisableTiming));
 
 	memset(&L->h_ctx, 0, sizeof(L->h_ctx));
-	for (size_t r = 0; r < b.stores.size(); r++) L->h_ctx.store[r] = b.stores[r];
-	L->h_ctx.nreplicas = (uint32_t)b.stores.size();
-	L->h_ctx.num_blocks = b.num_blocks;
-	L->h_ctx.block_size = b.block_size;
-	L->h_ctx.block_shift = (b.block_size & (b.block_size - 1)) ? 0xffffffffu : (uint32_t)__builtin_ctz(b.block_size);
-	L->h_ctx.target = (uint8_t)scsi_target_num;
-	/* identity strings INQUIRY reports: spdk_scsi_dev_construct("Target N", ...) + port 0 "vhost", SAS
-	 * (vhost_scsi.c:1004-1013); the device id is the slot add_vhost_scsi_lun took in the global table */
-	snprintf(L->h_ctx.bdev_name, sizeof(L->h_ctx.bdev_name), "%s", b.name.c_str());
-	snprintf(L->h_ctx.product_name, sizeof(L->h_ctx.product_name), "%s", b.product.c_str());
-	snprintf(L->h_ctx.dev_name, sizeof(L->h_ctx.dev_name), "Target %d", scsi_target_num);
-	snprintf(L->h_ctx.port_name, sizeof(L->h_ctx.port_name), "vhost");
-	L->h_ctx.scsi_dev_id = it->second->scsi_id[scsi_target_num];
-	L->h_ctx.port_index = 0;
-	L->h_ctx.protocol_id = 0x06;
+	if (session) L->h_ctx.target = 0xff;
+	else fill_lun_ctx(L->h_ctx, *bp, *it->second, scsi_target_num);
+	L->any_mirror = L->h_ctx.nreplicas > 1;
 	CU_OK(cudaMalloc((void **)&L->d_ctx, sizeof(LunCtx)));
 	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, sizeof(LunCtx), cudaMemcpyHostToDevice));
 
@@ -760,8 +925,11 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes()));
 	if (per_sm < 1) per_sm = 1;
 	L->grid_cap = L->sm_count * per_sm;
+	int rc = refresh_peers_locked(L.get());
+	if (rc) return rc;
 	g.open_luns++;
-	b.open_luns++;
+	if (bp) bp->open_luns++;
+	g.handles.push_back(L.get());
 	*out = L.release();
 	return 0;
 }
@@ -776,6 +944,8 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 		L->poller_active = false;
 	}
 	cudaStreamSynchronize(L->stream);
+	auto parked = park_pollers_locked(L->device);	/* other sessions' resident kernels: see park_pollers_locked */
+	cudaSetDevice(L->device);
 	cudaFreeHost((void *)L->h_door);
 	cudaFreeHost((void *)L->h_flags);
 	if (!L->queues.empty()) cudaFreeHost(L->queues[0].h_reqs);
@@ -793,8 +963,17 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 	cudaEventDestroy(L->bs_uploaded);
 	cudaStreamDestroy(L->copy_stream);
 	cudaFree(L->d_ctx);
+	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		cudaFree(L->d_peer[t]);
+		if (!L->peer_bdev[t].empty()) {
+			auto bi = g.bdevs.find(L->peer_bdev[t]);
+			if (bi != g.bdevs.end() && bi->second->open_luns > 0) bi->second->open_luns--;
+		}
+	}
+	g.handles.erase(std::remove(g.handles.begin(), g.handles.end(), L), g.handles.end());
 	cudaEventDestroy(L->done);
 	cudaStreamDestroy(L->stream);
+	unpark_pollers_locked(parked);
 	g.open_luns--;
 	{
 		auto bi = g.bdevs.find(L->bdev);
@@ -950,7 +1129,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
 	L->kicks++;
-	if (L->h_ctx.nreplicas > 1) oim_lun_queue_mirror_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
 	else oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->done, L->stream));
@@ -1150,14 +1329,13 @@ extern "C" int oimgpu_submit_and_wait(oimgpu_lun *L, uint32_t nq, uint32_t per_q
 	return oimgpu_lun_sync(L);
 }
 
-extern "C" int oimgpu_lun_iostat(oimgpu_lun *L, oimgpu_iostat *out)
+static int read_iostat(oimgpu_lun *L, const LunCtx *d_ctx, oimgpu_iostat *out)
 {
-	if (!L || !out) return -EINVAL;
 	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
 	LunCtx c;
-	CU_OK(cudaMemcpy(&c, L->d_ctx, sizeof(c), cudaMemcpyDeviceToHost));
+	CU_OK(cudaMemcpy(&c, d_ctx, sizeof(c), cudaMemcpyDeviceToHost));
 	memset(out, 0, sizeof(*out));
 	out->num_read_ops = c.stats[0];
 	out->num_write_ops = c.stats[1];
@@ -1169,6 +1347,21 @@ extern "C" int oimgpu_lun_iostat(oimgpu_lun *L, oimgpu_iostat *out)
 	out->num_errors = c.stats[7];
 	out->kernel_launches = L->launches;
 	return 0;
+}
+
+extern "C" int oimgpu_lun_iostat(oimgpu_lun *L, oimgpu_iostat *out)
+{
+	if (!L || !out) return -EINVAL;
+	return read_iostat(L, L->d_ctx, out);
+}
+
+extern "C" int oimgpu_lun_target_iostat(oimgpu_lun *L, int scsi_target_num, oimgpu_iostat *out)
+{
+	if (!L || !out || scsi_target_num < 0 || scsi_target_num >= OIMGPU_CTRLR_MAX_DEVS) return -EINVAL;
+	if (scsi_target_num == L->target) return read_iostat(L, L->d_ctx, out);
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (L->peer_bdev[scsi_target_num].empty()) return -ENODEV;
+	return read_iostat(L, L->d_peer[scsi_target_num], out);
 }
 
 /* session-visible target state: hot-remove flags (vhost_scsi.c:1093-1100, lun.c:171-176) */
@@ -1329,13 +1522,15 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 	kh->stop = L->d_flags;
 	kh->exited = L->d_flags + 16;
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
-	if (L->h_ctx.nreplicas > 1) oim_lun_queue_mirror_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
 	else oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
 	L->kicks++;
 	L->launches++;
 	L->poller_grid = grid;
+	L->poller_max_ctas = max_ctas;
+	L->poller_idle_ms = idle_timeout_ms;
 	L->poller_active = true;
 	return (int)grid;
 }

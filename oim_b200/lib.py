@@ -86,6 +86,7 @@ SYMBOLS = [
     ("oimgpu_submit_batch", _I, [_VP, _U32, _U32, _VP, _VP, _U32, _VP, _I]),
     ("oimgpu_submit_and_wait", _I, [_VP, _U32, _U32, _VP, _VP, _U32, _VP, _I]),
     ("oimgpu_lun_iostat", _I, [_VP, C.POINTER(IoStat)]),
+    ("oimgpu_lun_target_iostat", _I, [_VP, _I, C.POINTER(IoStat)]),
     ("oimgpu_lun_stream", _VP, [_VP]),
     ("oimgpu_lun_set_removed", _I, [_VP, _I, _I]),
     ("oimgpu_lun_start_poller", _I, [_VP, _U32, _U32]),
@@ -273,7 +274,9 @@ class Timer:
 
 
 class Lun:
-    """Data path of one attached SCSI target (oimgpu_lun)."""
+    """Data-path session on a vhost controller (oimgpu_lun).  target >= 0: the session's home device;
+    target == -1: controller-wide session with no home device.  Either way requests reach every
+    target of the controller through lun[1], as in the reference."""
 
     def __init__(self, ctrlr: str, target: int, num_queues: int = 1, queue_size: int = 1024):
         self.h = C.c_void_p()
@@ -341,9 +344,13 @@ class Lun:
             lo = hi
         return np.concatenate(out) if out else np.zeros(0, dtype=abi.cpl_dtype)
 
-    def iostat(self) -> dict:
+    def iostat(self, target: int | None = None) -> dict:
+        """counters of the session's home device, or of any target it reaches"""
         s = IoStat()
-        _chk(load().oimgpu_lun_iostat(self.h, C.byref(s)), "iostat")
+        if target is None:
+            _chk(load().oimgpu_lun_iostat(self.h, C.byref(s)), "iostat")
+        else:
+            _chk(load().oimgpu_lun_target_iostat(self.h, target, C.byref(s)), "target_iostat")
         return {n: getattr(s, n) for n, _ in IoStat._fields_}
 
     def set_removed(self, removed: bool = True, lun_removed: bool = False) -> None:

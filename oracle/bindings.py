@@ -106,6 +106,35 @@ class _Oracle:
             raise RuntimeError(f"{self.prefix}_vq_process rc={n}")
         return n, la.value, lu.value
 
+    def add_target(self, target: int, num_blocks: int, block_size: int = 512, name: str | None = None,
+                   scsi_dev_id: int | None = None) -> np.ndarray:
+        """one more SCSI device (own Malloc bdev) behind the same queues; -> numpy view of its store.
+        The reference assigns the SCSI device id itself (lowest free global slot); the restatement is
+        told (scsi_dev_id)."""
+        fn = getattr(self.lib, self.prefix + "_add_target")
+        fn.restype = C.c_int
+        if self.prefix == "oimorc":
+            fn.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_uint64, C.c_uint32, C.c_int]
+            rc = fn(self.h, name.encode() if name else None, scsi_dev_id or 0, num_blocks, block_size, target)
+        else:
+            fn.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.c_int]
+            rc = fn(self.h, name.encode() if name else None, num_blocks, block_size, target)
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_add_target rc={rc}")
+        ts = getattr(self.lib, self.prefix + "_target_store")
+        ts.restype = C.c_void_p
+        ts.argtypes = [C.c_void_p, C.c_int]
+        buf = (C.c_uint8 * (num_blocks * block_size)).from_address(ts(self.h, target))
+        self.stores = getattr(self, "stores", {self.target: self.store})
+        self.stores[target] = np.frombuffer(buf, dtype=np.uint8)
+        return self.stores[target]
+
+    def target_scsi_dev_id(self, target: int) -> int:
+        gid = getattr(self.lib, self.prefix + "_scsi_dev_id")
+        gid.restype = C.c_int
+        gid.argtypes = [C.c_void_p, C.c_int]
+        return gid(self.h, target)
+
     def busy_ns(self, reset: bool = True) -> int:
         """ns spent inside the checker's own request processing (0 = not instrumented: time the call)"""
         return int(self._busy(self.h, int(reset)))
@@ -123,6 +152,7 @@ class _Oracle:
     def close(self) -> None:
         if self.h:
             self.store = None
+            self.stores = {}
             self._destroy(self.h)
             self.h = None
 

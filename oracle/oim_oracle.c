@@ -60,8 +60,9 @@ struct orc_tgt {
 };
 
 struct oimorc {
-	struct orc_bdev bdev;
+	struct orc_bdev bdev;		/* the device oimorc_create made */
 	struct orc_tgt  tgt[OIMGPU_CTRLR_MAX_DEVS];
+	struct orc_bdev *extra[OIMGPU_CTRLR_MAX_DEVS];	/* devices added later (oimorc_add_target), owned */
 };
 
 /* struct spdk_scsi_task, the fields the path touches (S/include/spdk/scsi.h:97-146) */
@@ -942,9 +943,44 @@ void *oimorc_create(uint64_t num_blocks, uint32_t block_size, int target_num)
 void oimorc_destroy(void *h)
 {
 	struct oimorc *o = h;
+	int t;
 	if (!o) return;
+	for (t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		if (o->extra[t]) { free(o->extra[t]->buf); free(o->extra[t]); }
+	}
 	free(o->bdev.buf);
 	free(o);
+}
+
+/* add_vhost_scsi_lun on the same controller (spdk_vhost_scsi_dev_add_tgt, vhost_scsi.c:951-1021):
+ * one more SCSI device, with its own Malloc bdev, behind the same request queues */
+int oimorc_add_target(void *h, const char *bdev_name, int scsi_dev_id, uint64_t num_blocks, uint32_t block_size, int target_num)
+{
+	struct oimorc *o = h;
+	struct orc_bdev *b;
+	if (num_blocks == 0 || block_size == 0 || target_num < 0 || target_num >= OIMGPU_CTRLR_MAX_DEVS) return -22;
+	if (o->tgt[target_num].bdev) return -17;
+	b = calloc(1, sizeof(*b));
+	if (!b || posix_memalign((void **)&b->buf, 2 * 1024 * 1024, num_blocks * block_size) != 0) { free(b); return -12; }
+	memset(b->buf, 0, num_blocks * block_size);
+	b->blockcnt = num_blocks;
+	b->blocklen = block_size;
+	snprintf(b->name, sizeof(b->name), "%s", bdev_name ? bdev_name : "Malloc1");
+	snprintf(b->product_name, sizeof(b->product_name), "Malloc disk");
+	snprintf(b->dev_name, sizeof(b->dev_name), "Target %d", target_num);
+	snprintf(b->port_name, sizeof(b->port_name), "vhost");
+	b->protocol_id = 0x06;
+	b->dev_id = scsi_dev_id;
+	o->extra[target_num] = b;
+	o->tgt[target_num].bdev = b;
+	return 0;
+}
+
+uint8_t *oimorc_target_store(void *h, int target_num)
+{
+	struct oimorc *o = h;
+	if (target_num < 0 || target_num >= OIMGPU_CTRLR_MAX_DEVS || !o->tgt[target_num].bdev) return NULL;
+	return o->tgt[target_num].bdev->buf;
 }
 
 /* the strings / ids INQUIRY reports: bdev name and the global SCSI device id */
@@ -962,7 +998,11 @@ void *oimorc_create_named(const char *bdev_name, uint64_t num_blocks, uint32_t b
 	return h;
 }
 
-int oimorc_scsi_dev_id(void *h, int target_num) { (void)target_num; return ((struct oimorc *)h)->bdev.dev_id; }
+int oimorc_scsi_dev_id(void *h, int target_num)
+{
+	struct oimorc *o = h;
+	return o->tgt[target_num].bdev ? o->tgt[target_num].bdev->dev_id : -1;
+}
 
 uint8_t *oimorc_store(void *h) { return ((struct oimorc *)h)->bdev.buf; }
 uint64_t oimorc_num_blocks(void *h) { return ((struct oimorc *)h)->bdev.blockcnt; }

@@ -87,6 +87,7 @@ int spdk_app_parse_core_mask(const char *mask, struct spdk_cpuset *cpumask)
 struct oimref {
 	struct spdk_bdev		*bdev;
 	char				bdev_name[32];
+	struct spdk_bdev		*extra[SPDK_VHOST_SCSI_CTRLR_MAX_DEVS];	/* oimref_add_target */
 	struct spdk_vhost_scsi_dev	*svdev;
 	struct spdk_vhost_scsi_session	*svsession;
 	struct spdk_vhost_virtqueue	*vq;		/* request queue (index VIRTIO_SCSI_REQUESTQ) */
@@ -233,6 +234,50 @@ static void *ref_create(const char *bdev_name, uint64_t num_blocks, uint32_t blo
 	return r;
 }
 
+/* add_vhost_scsi_lun on the same controller: one more Malloc bdev + SCSI device in another target
+ * slot of the same session (spdk_vhost_scsi_dev_add_tgt, vhost_scsi.c:951-1021, minus the RPC) */
+int oimref_add_target(void *h, const char *bdev_name, uint64_t num_blocks, uint32_t block_size, int target_num)
+{
+	struct oimref *r = h;
+	const char *names[1];
+	int lun_ids[1] = { 0 };
+	char tname[32], auto_name[32];
+	struct spdk_scsi_dev *sdev;
+	struct spdk_bdev *b;
+
+	if (target_num < 0 || target_num >= SPDK_VHOST_SCSI_CTRLR_MAX_DEVS) return -22;
+	if (r->svdev->scsi_dev_state[target_num].dev) return -17;
+	spdk_set_thread(g_thread);
+	if (!bdev_name) {
+		snprintf(auto_name, sizeof(auto_name), "RefMalloc%d", __sync_fetch_and_add(&g_name_seq, 1));
+		bdev_name = auto_name;
+	}
+	b = create_malloc_disk(bdev_name, NULL, num_blocks, block_size);
+	if (!b) return -12;
+	names[0] = spdk_bdev_get_name(b);
+	snprintf(tname, sizeof(tname), "Target %d", target_num);
+	sdev = spdk_scsi_dev_construct(tname, names, lun_ids, 1, SPDK_SPC_PROTOCOL_IDENTIFIER_SAS, ref_hotremove_cb, r);
+	if (!sdev) return -22;
+	spdk_scsi_dev_add_port(sdev, 0, "vhost");
+	if (spdk_scsi_dev_allocate_io_channels(sdev) != 0) return -12;
+	r->svdev->scsi_dev_state[target_num].dev = sdev;
+	r->svsession->scsi_dev_state[target_num].dev = sdev;
+	r->extra[target_num] = b;
+	return 0;
+}
+
+uint8_t *oimref_target_store(void *h, int target_num)
+{
+	struct oimref *r = h;
+	struct spdk_bdev *b = r->extra[target_num];
+	if (!b) {
+		struct spdk_scsi_dev *d = r->svdev->scsi_dev_state[target_num].dev;
+		if (!d) return NULL;
+		b = r->bdev;
+	}
+	return *(uint8_t **)((char *)b->ctxt + sizeof(struct spdk_bdev));
+}
+
 uint8_t *oimref_store(void *h)
 {
 	struct oimref *r = h;
@@ -268,6 +313,9 @@ void oimref_destroy(void *h)
 	}
 	for (t = 0; t < 8; t++) spdk_thread_poll(g_thread, 0, 0);
 	delete_malloc_disk(r->bdev, dummy_unregister_cb, NULL);
+	for (t = 0; t < SPDK_VHOST_SCSI_CTRLR_MAX_DEVS; t++) {
+		if (r->extra[t]) delete_malloc_disk(r->extra[t], dummy_unregister_cb, NULL);
+	}
 	for (t = 0; t < 8; t++) spdk_thread_poll(g_thread, 0, 0);
 	close(r->eventfd);
 	free(r->vq->tasks); free(r->indirect); free(r->resp_bufs); free(r->req_bufs);
