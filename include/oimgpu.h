@@ -229,6 +229,8 @@ int oimgpu_lun_device(const oimgpu_lun *lun);
  * spdk_mem_register() on the guest's memory table (S/lib/vhost/vhost.c:1044-1100). */
 int oimgpu_mem_register(void *addr, size_t len);
 int oimgpu_mem_unregister(void *addr);
+/* device-side address of a byte inside a registered range (for oimgpu_lun_set_mem_table / oimgpu_vq_attach) */
+int oimgpu_mem_device_addr(const void *addr, uint64_t *dev);
 
 /* Submit `nreqs` requests to queue `q` of the LUN.  reqs[i].iov_start indexes into `iovs`
  * (niovs entries).  `mem` says where SG addresses AND the reqs/iovs/cpls arrays of this call live:

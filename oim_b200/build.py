@@ -48,14 +48,16 @@ def build(force: bool = False, verbose: bool = False, defs: str | None = None, o
 
 DAEMON = os.path.join(HERE, "oim-gpu-vhost")
 DAEMON_SRC = os.path.join(HERE, "daemon", "oim_gpu_vhost.cpp")
+DAEMON_SRCS = [DAEMON_SRC, os.path.join(HERE, "daemon", "vhost_user.cpp")]
+DAEMON_DEPS = DAEMON_SRCS + [os.path.join(HERE, "daemon", "vhost_user.h")]
 
 
 def build_daemon(force: bool = False) -> str:
     """the JSON-RPC daemon (drop-in for SPDK's `vhost` binary): plain C++ on top of the C ABI"""
     if not force and os.path.exists(DAEMON) and os.path.getmtime(DAEMON) >= max(
-            os.path.getmtime(DAEMON_SRC), os.path.getmtime(LIB), os.path.getmtime(os.path.join(ROOT, "include", "oimgpu.h"))):
+            *[os.path.getmtime(d) for d in DAEMON_DEPS], os.path.getmtime(LIB), os.path.getmtime(os.path.join(ROOT, "include", "oimgpu.h"))):
         return DAEMON
-    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", DAEMON, DAEMON_SRC,
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", DAEMON, *DAEMON_SRCS,
            "-L", HERE, "-loimgpu", "-Wl,-rpath,$ORIGIN"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:

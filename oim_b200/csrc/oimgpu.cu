@@ -127,6 +127,9 @@ struct Queue {
 }  // namespace
 
 struct oimgpu_lun {
+	/* a session is driven by one thread (its owner); the exception is target hot-plug, which reaches
+	 * into it from whichever thread runs the control call: the entry points both sides use lock this */
+	std::recursive_mutex mu;
 	std::string ctrlr, bdev;
 	int target = 0;
 	int device = 0;
@@ -222,6 +225,7 @@ static bool device_reachable(int from, int to)
  * spdk_vhost_scsi_dev_add_tgt / _remove_tgt).  Caller holds g.mu. */
 static int refresh_peers_locked(oimgpu_lun *L)
 {
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	auto it = g.ctrlrs.find(L->ctrlr);
 	CU_OK(cudaSetDevice(L->device));
 	bool changed = false, restart = false;
@@ -1000,6 +1004,22 @@ extern "C" int oimgpu_mem_register(void *addr, size_t len)
 	return 0;
 }
 
+/* the address the GPU uses for a byte of registered host memory (identical to the host address on
+ * systems with a unified address space for registered memory, but that is the driver's call) */
+extern "C" int oimgpu_mem_device_addr(const void *addr, uint64_t *dev)
+{
+	if (!addr || !dev) return -EINVAL;
+	if (!g.inited || g.control_only) return -ENODEV;
+	void *d = nullptr;
+	cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<void *>(addr), 0);
+	if (e != cudaSuccess) {
+		(void)cudaGetLastError();
+		return -EFAULT;
+	}
+	*dev = (uint64_t)(uintptr_t)d;
+	return 0;
+}
+
 extern "C" int oimgpu_mem_unregister(void *addr)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
@@ -1060,6 +1080,7 @@ extern "C" int oimgpu_submit_device(oimgpu_lun *L, uint32_t q, const oimgpu_req 
 extern "C" int oimgpu_kick(oimgpu_lun *L)
 {
 	if (!L) return -EINVAL;
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	if (L->poller_active) {
 		/* the resident kernel is polling: a kick is a doorbell write (after the slot contents) */
 		int n = 0;
@@ -1142,6 +1163,7 @@ static int batch_finish(oimgpu_lun *L);
 extern "C" int oimgpu_lun_sync(oimgpu_lun *L)
 {
 	if (!L) return -EINVAL;
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	return batch_finish(L);		/* stream sync + hand over the completions of a host-array batch */
 }
 
@@ -1384,6 +1406,7 @@ extern "C" int oimgpu_lun_set_removed(oimgpu_lun *L, int removed, int lun_remove
 extern "C" int oimgpu_lun_set_mem_table(oimgpu_lun *L, const oimgpu_mem_region *regions, uint32_t nregions)
 {
 	if (!L || (!regions && nregions) || nregions > (uint32_t)kMaxRegions) return -EINVAL;
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
@@ -1403,6 +1426,7 @@ extern "C" int oimgpu_vq_attach(oimgpu_lun *L, uint32_t q, const void *desc, con
 				uint32_t size, uint16_t last_avail_idx, uint16_t last_used_idx)
 {
 	if (!L || q >= L->num_queues || !desc || !avail || !used) return -EINVAL;
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	if (size == 0 || size > OIMGPU_MAX_VQ_SIZE || (size & (size - 1))) return -EINVAL;
 	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
@@ -1424,6 +1448,7 @@ extern "C" int oimgpu_vq_attach(oimgpu_lun *L, uint32_t q, const void *desc, con
 extern "C" int oimgpu_vq_detach(oimgpu_lun *L, uint32_t q, uint16_t *last_avail_idx, uint16_t *last_used_idx)
 {
 	if (!L || q >= L->num_queues || !L->queues[q].vq_size) return -EINVAL;
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	if (L->poller_active) return -EBUSY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
@@ -1443,6 +1468,7 @@ extern "C" int oimgpu_vq_detach(oimgpu_lun *L, uint32_t q, uint16_t *last_avail_
 extern "C" int oimgpu_vq_kick(oimgpu_lun *L)
 {
 	if (!L) return -EINVAL;
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	if (L->poller_active) return 0;	/* the resident kernel sees avail->idx by itself */
 	int n = 0;
 	for (auto &Q : L->queues) {
@@ -1463,6 +1489,7 @@ extern "C" int oimgpu_vq_kick(oimgpu_lun *L)
 extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_t idle_timeout_ms)
 {
 	if (!L) return -EINVAL;
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	if (L->poller_active) return -EALREADY;
 	CU_OK(cudaSetDevice(L->device));
 	CU_OK(cudaStreamSynchronize(L->stream));
@@ -1538,6 +1565,7 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 extern "C" int oimgpu_lun_stop_poller(oimgpu_lun *L)
 {
 	if (!L) return -EINVAL;
+	std::lock_guard<std::recursive_mutex> hl(L->mu);
 	if (!L->poller_active) return 0;
 	CU_OK(cudaSetDevice(L->device));
 	std::atomic_thread_fence(std::memory_order_seq_cst);

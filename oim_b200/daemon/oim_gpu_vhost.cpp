@@ -33,6 +33,7 @@
 #include <unistd.h>
 
 #include "oimgpu.h"
+#include "vhost_user.h"
 
 /* ---- a small JSON value (parse + the subset of writing the replies need) ------------------------ */
 
@@ -302,6 +303,7 @@ static std::string ctrlr_json(const oimgpu_ctrlr_info &c)
 struct NbdDisk { std::string dev, bdev; };
 static std::vector<NbdDisk> g_nbd;
 static uint64_t g_rbd_default_size = 8ull << 30;
+static bool g_serve_vhost_user = true;
 
 static Reply dispatch(const std::string &method, const Json *params, const Json *id)
 {
@@ -356,6 +358,15 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 			return error(id, E_INVALID_PARAMS, strerr(EINVAL));
 		int rc = oimgpu_vhost_scsi_ctrlr_create(a->raw.c_str(), b ? b->raw.c_str() : nullptr);
 		if (rc < 0) return error(id, E_INVALID_PARAMS, strerr(rc));
+		/* spdk_vhost_dev_register: the controller's vhost-user socket appears at <socket dir><name> (vhost.c:715-760) */
+		oimgpu_ctrlr_info info;
+		if (g_serve_vhost_user && oimgpu_vhost_ctrlr_get(a->raw.c_str(), &info) == 0) {
+			rc = vhost_user::listen_ctrlr(info.ctrlr, info.socket);
+			if (rc < 0) {
+				oimgpu_vhost_ctrlr_remove(a->raw.c_str());
+				return error(id, E_INVALID_PARAMS, strerr(rc));
+			}
+		}
 		return result(id, "true");
 	}
 	if (method == "add_vhost_scsi_lun") {
@@ -364,6 +375,8 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 		    !to_i32(b, &num)) return error(id, E_INVALID_PARAMS, strerr(EINVAL));
 		int rc = oimgpu_vhost_scsi_add_lun(a->raw.c_str(), num, c->raw.c_str());
 		if (rc < 0) return error(id, E_INVALID_PARAMS, strerr(rc));
+		oimgpu_ctrlr_info info;
+		if (g_serve_vhost_user && oimgpu_vhost_ctrlr_get(a->raw.c_str(), &info) == 0) vhost_user::notify_target(info.ctrlr, rc, true);
 		return result(id, std::to_string(rc));
 	}
 	if (method == "remove_vhost_scsi_target") {
@@ -372,12 +385,17 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 		    !to_u64(b, &num) || num > UINT32_MAX) return error(id, E_INVALID_PARAMS, strerr(EINVAL));
 		int rc = oimgpu_vhost_scsi_remove_target(a->raw.c_str(), num > INT32_MAX ? INT32_MAX : (int)num);
 		if (rc < 0) return error(id, E_INVALID_PARAMS, strerr(rc));
+		oimgpu_ctrlr_info info;
+		if (g_serve_vhost_user && oimgpu_vhost_ctrlr_get(a->raw.c_str(), &info) == 0) vhost_user::notify_target(info.ctrlr, (int)num, false);
 		return result(id, "true");
 	}
 	if (method == "remove_vhost_controller") {
 		if (!decode(params, {{"ctrlr", Json::Str, false, &a}})) return error(id, E_INVALID_PARAMS, strerr(EINVAL));
+		oimgpu_ctrlr_info info;
+		const bool known = oimgpu_vhost_ctrlr_get(a->raw.c_str(), &info) == 0;
 		int rc = oimgpu_vhost_ctrlr_remove(a->raw.c_str());
 		if (rc < 0) return error(id, E_INVALID_PARAMS, strerr(rc));
+		if (g_serve_vhost_user && known) vhost_user::close_ctrlr(info.ctrlr);
 		return result(id, "true");
 	}
 	if (method == "get_vhost_controllers") {
@@ -461,6 +479,7 @@ int main(int argc, char **argv)
 	std::string rpc_sock = "/var/tmp/spdk.sock", sock_dir, pidfile, coremask;
 	std::vector<int> gpus;
 	bool control_only = false;
+	vhost_user::Config vu_cfg;
 	for (int i = 1; i < argc; i++) {
 		std::string a = argv[i];
 		auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -471,6 +490,8 @@ int main(int argc, char **argv)
 		else if (a == "-s") next();
 		else if (a == "-R") {}
 		else if (a == "--control-only") control_only = true;	/* protocol tests without a GPU: no data path */
+		else if (a == "--poller") vu_cfg.poller = true;		/* a resident GPU poller per vhost-user session */
+		else if (a == "--no-vhost-user") g_serve_vhost_user = false;
 		else if (a == "--rbd-size") g_rbd_default_size = strtoull(next(), nullptr, 0);
 		else if (a == "--gpus") {
 			std::string l = next();
@@ -482,6 +503,8 @@ int main(int argc, char **argv)
 			}
 		} else { usage(argv[0]); return 2; }
 	}
+	vu_cfg.control_only = control_only;
+	vhost_user::configure(vu_cfg);
 	int rc = control_only ? oimgpu_init_control_only() : oimgpu_init(gpus.empty() ? nullptr : gpus.data(), (int)gpus.size());
 	if (rc != 0) {
 		fprintf(stderr, "oim-gpu-vhost: oimgpu_init failed: %s\n", strerror(-rc));
@@ -559,6 +582,7 @@ int main(int argc, char **argv)
 		}
 	}
 	for (auto &c : conns) close(c.fd);
+	vhost_user::shutdown();
 	close(lfd);
 	unlink(rpc_sock.c_str());
 	if (!pidfile.empty()) unlink(pidfile.c_str());

@@ -78,6 +78,7 @@ SYMBOLS = [
     ("oimgpu_lun_device", _I, [_VP]),
     ("oimgpu_mem_register", _I, [_VP, C.c_size_t]),
     ("oimgpu_mem_unregister", _I, [_VP]),
+    ("oimgpu_mem_device_addr", _I, [_VP, C.POINTER(C.c_uint64)]),
     ("oimgpu_submit", _I, [_VP, _U32, _VP, _U32, _VP, _U32, _I]),
     ("oimgpu_submit_device", _I, [_VP, _U32, _VP, _U32, _VP, _VP]),
     ("oimgpu_kick", _I, [_VP]),

@@ -27,6 +27,7 @@
  * Stubs for the vhost-user transport and the event framework, which the data path never calls
  * once a session is running (same set SPDK's vhost_ut.c stubs out).
  * ---------------------------------------------------------------------------------------- */
+#ifndef OIMREF_REAL_VHOST
 int rte_vhost_driver_callback_register(const char *p, struct vhost_device_ops const *const o) { return 0; }
 int rte_vhost_driver_disable_features(const char *p, uint64_t f) { return 0; }
 int rte_vhost_driver_set_features(const char *p, uint64_t f) { return 0; }
@@ -41,6 +42,35 @@ int rte_vhost_get_vhost_vring(int vid, uint16_t idx, struct rte_vhost_vring *v) 
 void rte_vhost_log_used_vring(int vid, uint16_t idx, uint64_t off, uint64_t len) {}
 void rte_vhost_log_write(int vid, uint64_t addr, uint64_t len) {}
 int rte_vhost_set_vhost_vring_last_idx(int vid, uint16_t i, uint16_t a, uint16_t u) { return 0; }
+#else
+/* liboim_ref_vhost.so: the reference's own vhost-user transport (S/lib/vhost/rte_vhost/{socket,vhost_user,
+ * vhost,fd_man}.c) is linked instead of the stubs above; what it needs from DPDK is a logger, an
+ * allocator and an address translation, provided here. */
+#include <stdarg.h>
+int rte_log(uint32_t level, uint32_t logtype, const char *fmt, ...)
+{
+	va_list ap;
+	if (!getenv("OIMREF_VERBOSE")) return 0;
+	va_start(ap, fmt);
+	vfprintf(stderr, fmt, ap);
+	va_end(ap);
+	return 0;
+}
+static void *ref_alloc(size_t size, unsigned align, int zero)
+{
+	void *p = NULL;
+	if (posix_memalign(&p, align < 64 ? 64 : align, size ? size : 1) != 0) return NULL;
+	if (zero) memset(p, 0, size);
+	return p;
+}
+void *rte_malloc(const char *type, size_t size, unsigned align) { return ref_alloc(size, align, 0); }
+void *rte_zmalloc(const char *type, size_t size, unsigned align) { return ref_alloc(size, align, 1); }
+void *rte_malloc_socket(const char *type, size_t size, unsigned align, int socket) { return ref_alloc(size, align, 0); }
+void *rte_zmalloc_socket(const char *type, size_t size, unsigned align, int socket) { return ref_alloc(size, align, 1); }
+void rte_free(void *p) { free(p); }
+uint64_t rte_mem_virt2phy(const void *virt) { return (uint64_t)(uintptr_t)virt; }
+void rte_pktmbuf_free(void *m) {}
+#endif
 int spdk_vhost_nvme_admin_passthrough(int vid, void *cmd, void *cqe, void *buf) { return 0; }
 int spdk_vhost_nvme_set_cq_call(int vid, uint16_t qid, int fd) { return 0; }
 int spdk_vhost_nvme_set_bar_mr(int vid, void *bar, uint64_t sz) { return 0; }
@@ -51,8 +81,46 @@ int spdk_vhost_blk_controller_construct(void) { return 0; }
 int spdk_vhost_blk_construct(const char *n, const char *m, const char *d, bool ro) { return -ENOTSUP; }
 int spdk_vhost_nvme_dev_construct(const char *n, const char *m, uint32_t q) { return -ENOTSUP; }
 int spdk_vhost_nvme_dev_add_ns(struct spdk_vhost_dev *v, const char *b) { return -ENOTSUP; }
+#ifndef OIMREF_REAL_VHOST
 struct spdk_event *spdk_event_allocate(uint32_t lcore, spdk_event_fn fn, void *a1, void *a2) { return NULL; }
 void spdk_event_call(struct spdk_event *e) {}
+static void ref_run_events(void) {}
+#else
+/* the reactor's event ring, reduced to what the transport needs: the vhost-user thread posts
+ * start/stop-session events (spdk_vhost_event_send, vhost.c:927-968), the one polling thread runs them */
+struct spdk_event { spdk_event_fn fn; void *a1, *a2; struct spdk_event *next; };
+static pthread_mutex_t g_ev_mu = PTHREAD_MUTEX_INITIALIZER;
+static struct spdk_event *g_ev_head, **g_ev_tail = &g_ev_head;
+struct spdk_event *spdk_event_allocate(uint32_t lcore, spdk_event_fn fn, void *a1, void *a2)
+{
+	struct spdk_event *e = calloc(1, sizeof(*e));
+	e->fn = fn; e->a1 = a1; e->a2 = a2;
+	return e;
+}
+void spdk_event_call(struct spdk_event *e)
+{
+	pthread_mutex_lock(&g_ev_mu);
+	*g_ev_tail = e;
+	g_ev_tail = &e->next;
+	pthread_mutex_unlock(&g_ev_mu);
+}
+static void ref_run_events(void)
+{
+	for (;;) {
+		struct spdk_event *e;
+		pthread_mutex_lock(&g_ev_mu);
+		e = g_ev_head;
+		if (e) {
+			g_ev_head = e->next;
+			if (!g_ev_head) g_ev_tail = &g_ev_head;
+		}
+		pthread_mutex_unlock(&g_ev_mu);
+		if (!e) return;
+		e->fn(e->a1, e->a2);
+		free(e);
+	}
+}
+#endif
 int spdk_mem_register(void *vaddr, size_t len) { return 0; }
 int spdk_mem_unregister(void *vaddr, size_t len) { return 0; }
 void *spdk_call_unaffinitized(void *cb(void *arg), void *arg) { return cb(arg); }
@@ -547,10 +615,24 @@ int oimref_vq_process(void *h, uint64_t desc, uint64_t avail, uint64_t used, uin
 /* ---- the reference's own JSON-RPC server (S/lib/rpc, S/lib/jsonrpc) with its registered handlers:
  * get_bdevs / construct_malloc_bdev / delete_bdev (bdev_rpc.c, bdev_malloc_rpc.c) and the vhost-scsi
  * methods (vhost_rpc.c).  Used to pin the wire behaviour of our daemon (tests/test_rpc_daemon.py). */
+#include <execinfo.h>
+#include <signal.h>
+static void ref_segv(int sig)
+{
+	void *bt[48];
+	int n = backtrace(bt, 48);
+	backtrace_symbols_fd(bt, n, 2);
+	_exit(139);
+}
+
+extern uint64_t ut_spdk_get_ticks;
+
 int oimref_rpc_start(const char *sock_path, const char *vhost_socket_dir)
 {
+	if (getenv("OIMREF_VERBOSE")) signal(SIGSEGV, ref_segv);
 	if (ref_global_init() != 0) return -1;
 	if (vhost_socket_dir && spdk_vhost_set_socket_path(vhost_socket_dir) != 0) return -2;
+	if (spdk_vhost_init() != 0) return -4;	/* per-core controller counters used when a session starts */
 	if (spdk_rpc_listen(sock_path) != 0) return -3;
 	spdk_rpc_set_state(SPDK_RPC_RUNTIME);
 	return 0;
@@ -561,7 +643,13 @@ void oimref_rpc_poll(int iterations)
 	int i;
 	spdk_set_thread(g_thread);
 	for (i = 0; i < iterations; i++) {
+		struct timespec ts;
+		/* the unit-test env's clock (1 tick = 1 us, test_env.c:412-435) follows real time here, so that
+		 * timed pollers - the 5 ms management poller, the session-stop poller - run as in the daemon */
+		clock_gettime(CLOCK_MONOTONIC, &ts);
+		ut_spdk_get_ticks = (uint64_t)ts.tv_sec * 1000000 + ts.tv_nsec / 1000;
 		spdk_rpc_accept();
+		ref_run_events();
 		spdk_thread_poll(g_thread, 0, 0);
 	}
 }

@@ -1,0 +1,309 @@
+"""The vhost-user transport: a master - what QEMU's vhost-user-scsi-pci is - connects to
+<socket dir>/<controller>, shares its memory, hands over the virtqueues and does I/O.
+
+The same master script (tests/vhost_user_master.py) runs against oim-gpu-vhost and against the REFERENCE'S OWN
+transport + vhost-scsi + bdev stack (oracle/_ref/liboim_ref_vhost.so: S/lib/vhost/rte_vhost/* compiled where it
+lies), and the protocol transcripts and the guest memory are compared.
+
+CPU: handshake, control queue, event queue / hot-plug (our daemon with --control-only: no data path exists then).
+GPU: request queues served by the kernel, launch-per-kick and resident-poller mode."""
+import os
+import struct
+import subprocess
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from oim_b200 import abi, traces, vring
+from test_rpc_daemon import DAEMON, ROOT, Client
+import vhost_user_master as vu
+
+META_END = 2 * vring.R01_SIZE + (4 << 20)          # end of the image's metadata area (rings, headers)
+NB = 32768
+
+
+class Slave:
+    """one server process (ours or the reference) + its RPC client"""
+
+    def __init__(self, kind: str, tmp, extra=()):
+        self.dir = tmp / kind
+        (self.dir / "vhost").mkdir(parents=True)
+        self.rpc = str(self.dir / "rpc.sock")
+        self.log = open(self.dir / "log.txt", "wb")
+        if kind == "ref":
+            cmd = [sys.executable, os.path.join(ROOT, "tests", "ref_rpc_server.py"), self.rpc, str(self.dir / "vhost"), "vhost"]
+        else:
+            cmd = [DAEMON, "-r", self.rpc, "-S", str(self.dir / "vhost"), *extra]
+        self.p = subprocess.Popen(cmd, stdout=self.log, stderr=self.log)
+        t0 = time.time()
+        while not os.path.exists(self.rpc):
+            assert self.p.poll() is None, f"{kind} server died: {open(self.dir / 'log.txt').read()[-2000:]}"
+            assert time.time() - t0 < 60
+            time.sleep(0.01)
+        self.c = Client(self.rpc)
+
+    def call(self, method, params=None):
+        return self.c.call(method, params)
+
+    def sock(self, ctrlr):
+        return str(self.dir / "vhost" / ctrlr)
+
+    def close(self):
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.log.close()
+
+
+def provision(s: Slave):
+    assert b'"result"' in s.call("construct_malloc_bdev", {"num_blocks": NB, "block_size": 512, "name": "M0"})
+    assert b'"result"' in s.call("construct_malloc_bdev", {"num_blocks": 4096, "block_size": 512, "name": "M1"})
+    assert b'"result":true' in s.call("construct_vhost_scsi_controller", {"ctrlr": "scsi0"})
+    assert b'"result":0' in s.call("add_vhost_scsi_lun", {"ctrlr": "scsi0", "scsi_target_num": 0, "bdev_name": "M0"})
+
+
+def small_ring(k: int):
+    """(desc, avail, used, buffers) offsets of a 16-entry ring in the tail of the metadata area"""
+    base = META_END - (k + 1) * 8192
+    return base, base + 256, base + 320, base + 1024
+
+
+def gpa_of(img, off):
+    for g, s, o in img.regions:
+        if o <= off < o + s:
+            return off - o + g
+    raise KeyError(off)
+
+
+def put_chain(ram, img, ring, slot0, bufs):
+    """descriptor chain in ring slots slot0.. : bufs = [(arena offset, len, writable)]; -> head"""
+    d_off = ring[0]
+    d = ram.mem[d_off:d_off + 16 * 16].view(vring.desc_dtype)
+    for k, (off, ln, wr) in enumerate(bufs):
+        last = k + 1 == len(bufs)
+        d[slot0 + k] = (gpa_of(img, off), ln, (vring.F_WRITE if wr else 0) | (0 if last else vring.F_NEXT), 0 if last else slot0 + k + 1)
+    return slot0
+
+
+def publish(ram, ring, heads):
+    a_off = ring[1]
+    idx = int(ram.mem[a_off + 2:a_off + 4].view("<u2")[0])
+    for h in heads:
+        ram.mem[a_off + 4 + 2 * (idx % 16):a_off + 6 + 2 * (idx % 16)] = np.frombuffer(struct.pack("<H", h), np.uint8)
+        idx += 1
+    ram.mem[a_off + 2:a_off + 4] = np.frombuffer(struct.pack("<H", idx & 0xFFFF), np.uint8)
+
+
+def handshake(m: vu.Master, ram, img, queues):
+    f = m.get_u64(vu.GET_FEATURES)
+    pf = m.get_u64(vu.GET_PROTOCOL_FEATURES)
+    m.set_u64(vu.SET_PROTOCOL_FEATURES, pf & ((1 << vu.PF_MQ) | (1 << vu.PF_REPLY_ACK)))
+    m.get_u64(vu.GET_QUEUE_NUM)
+    m.get_config()
+    m.send(vu.SET_OWNER)
+    m.set_u64(vu.SET_FEATURES, f & ~(1 << vu.F_LOG_ALL), need_reply=True)
+    regs = [(g, s, vu.UVA_BASE + o, o, ram.fd) for g, s, o in img.regions]
+    assert m.set_mem_table(regs, need_reply=True) == 0
+    for q in queues:                                    # in index order, as QEMU does
+        q.setup(m)
+        m.vring_state(vu.SET_VRING_ENABLE, q.index, 1)
+    return f, pf
+
+
+def control_requests(ram, img, ring):
+    """task-management / async-notification requests on the control queue -> heads"""
+    buf = ring[3]
+
+    def req(slot, typ, sub, lun):
+        o = buf + 64 * slot
+        ram.mem[o:o + 24] = np.frombuffer(struct.pack("<II8sQ", typ, sub, bytes(lun), 0x1000 + slot), np.uint8)
+        ram.mem[o + 32:o + 48] = 0xEE
+        return o
+
+    lun0, lun5, bad = [1, 0, 0, 0, 0, 0, 0, 0], [1, 5, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0, 0, 0]
+    heads = []
+    o = req(0, 0, 5, lun0); heads.append(put_chain(ram, img, ring, 0, [(o, 24, 0), (o + 32, 1, 1)]))     # LUN RESET, present
+    o = req(1, 0, 0, lun0); heads.append(put_chain(ram, img, ring, 2, [(o, 24, 0), (o + 32, 1, 1)]))     # ABORT TASK: unsupported
+    o = req(2, 0, 5, lun5); heads.append(put_chain(ram, img, ring, 4, [(o, 24, 0), (o + 32, 1, 1)]))     # absent target
+    o = req(3, 0, 5, bad); heads.append(put_chain(ram, img, ring, 6, [(o, 24, 0), (o + 32, 1, 1)]))      # malformed address
+    o = req(4, 1, 0, lun0); heads.append(put_chain(ram, img, ring, 8, [(o, 24, 0), (o + 32, 5, 1)]))     # AN_QUERY
+    o = req(5, 2, 0, lun0); heads.append(put_chain(ram, img, ring, 10, [(o, 24, 0), (o + 32, 4, 1)]))    # AN_SUBSCRIBE, short buffer
+    o = req(6, 9, 0, lun0); heads.append(put_chain(ram, img, ring, 12, [(o, 24, 0), (o + 32, 1, 1)]))    # unknown type
+    o = req(7, 0, 5, lun0); heads.append(put_chain(ram, img, ring, 14, [(o, 24, 0)]))                     # no response descriptor
+    return heads
+
+
+def event_buffers(ram, img, ring, n=4):
+    heads = []
+    for k in range(n):
+        o = ring[3] + 32 * k
+        ram.mem[o:o + 16] = 0xEE
+        heads.append(put_chain(ram, img, ring, k, [(o, 16, 1)]))
+    return heads
+
+
+def wait_used(ram, ring, want, timeout=10.0):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        if int(ram.mem[ring[2] + 2:ring[2] + 4].view("<u2")[0]) == want:
+            return
+        time.sleep(0.002)
+    raise TimeoutError(f"used idx {int(ram.mem[ring[2] + 2:ring[2] + 4].view('<u2')[0])}, wanted {want}")
+
+
+def run_script(s: Slave, rq, *, data: bool, seed=5):
+    """the whole life of one VM against one slave; -> (transcript, {label: guest memory snapshot})"""
+    img = vring.build_image(rq if data else [], ring_size=256, seed=seed, mutate=False)
+    ram = vu.GuestRam(img.arena.size)
+    ram.mem[:] = img.arena
+    cq, eq, q3 = small_ring(0), small_ring(1), small_ring(2)
+    for r in (cq, eq, q3):
+        ram.mem[r[0]:r[0] + 8192] = 0
+    queues = [vu.Queue(0, 16, *cq[:3]), vu.Queue(1, 16, *eq[:3]), vu.Queue(2, img.ring_size, img.desc_off, img.avail_off, img.used_off),
+              vu.Queue(3, 16, *q3[:3])]
+    snaps = {}
+    m = vu.Master(s.sock("scsi0"))
+    try:
+        handshake(m, ram, img, queues)
+        time.sleep(0.3)                                  # the reference starts the session asynchronously
+        for q in queues:
+            assert q.drain_calls() >= 1, "every queue gets a spurious interrupt at start (vhost.c:1101-1115)"
+        # ---- control queue
+        publish(ram, cq, control_requests(ram, img, cq))
+        queues[0].notify()
+        wait_used(ram, cq, 8)
+        # ---- event queue: hot-plug a second target, then remove it
+        publish(ram, eq, event_buffers(ram, img, eq))
+        queues[1].notify()
+        assert b'"result":1' in s.call("add_vhost_scsi_lun", {"ctrlr": "scsi0", "scsi_target_num": 1, "bdev_name": "M1"})
+        wait_used(ram, eq, 1)
+        if data:
+            # ---- request queues: the image's requests on queue 2, one READ of the hot-plugged target on queue 3
+            o = q3[3]
+            hdr = np.zeros(51, np.uint8)
+            hdr[0:2] = [1, 1]
+            hdr[19:51] = abi.cdb_rw(abi.READ_10, 8, 8)
+            ram.mem[o:o + 51] = hdr
+            ram.mem[o + 64:o + 64 + 108] = 0xEE
+            data_off = META_END - 4 * 8192                # a spare page in the metadata area
+            ram.mem[data_off:data_off + 4096] = 0x11
+            publish(ram, q3, [put_chain(ram, img, q3, 0, [(o, 51, 0), (o + 64, 108, 1), (data_off, 4096, 1)])])
+            queues[2].notify()
+            queues[3].notify()
+            queues[2].wait_used(ram, img.meta["placed"])
+            queues[3].wait_used(ram, 1)
+        assert b'"result":true' in s.call("remove_vhost_scsi_target", {"ctrlr": "scsi0", "scsi_target_num": 1})
+        wait_used(ram, eq, 2)
+        snaps["end"] = ram.mem.copy()
+        for q in queues:
+            m.get_vring_base(q.index)
+        return m.log, snaps, img, (cq, eq, q3)
+    finally:
+        m.close()
+        for q in queues:
+            q.close()
+        ram.close()
+
+
+def mask(mem, img, rings):
+    """what may differ between two correct slaves: the order of used-ring elements on the request queue
+    (completion order is timing in the reference) and used->flags (the reference polls and sets NO_NOTIFY;
+    a launch per kick needs the kick)"""
+    c = img.masked(mem)
+    for used_off in [img.used_off] + [r[2] for r in rings]:
+        c[used_off:used_off + 2] = 0
+    cq = rings[0]
+    c[cq[2] + 4:cq[2] + 4 + 8 * 16] = 0       # control queue: the reference completes a LUN RESET asynchronously, i.e. last
+    return c
+
+
+def used_set(mem, ring, n):
+    u = mem[ring[2] + 4:ring[2] + 4 + 8 * n].view(vring.used_elem_dtype)
+    return sorted((int(i), int(l)) for i, l in u)
+
+
+@pytest.fixture()
+def slaves(oracles, tmp_path):
+    if not oracles.ref_available() or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "liboim_ref_vhost.so")):
+        pytest.skip("oracle/_ref/liboim_ref_vhost.so not built here")
+    from oim_b200 import build
+    build.build()
+    made = []
+
+    def make(kind, extra=()):
+        s = Slave(kind, tmp_path, extra)
+        made.append(s)
+        provision(s)
+        return s
+    yield make
+    for s in made:
+        s.close()
+
+
+def test_vhost_user_handshake_control_and_event_queues(slaves):
+    ours, ref = slaves("ours", ["--control-only"]), slaves("ref")
+    lo, so, img, rings = run_script(ours, [], data=False)
+    lr, sr, _, _ = run_script(ref, [], data=False)
+    assert lo == lr, f"protocol transcripts differ:\nours {lo}\nref  {lr}"
+    a, b = mask(so["end"], img, rings), mask(sr["end"], img, rings)
+    assert (a == b).all(), f"guest memory differs at {np.nonzero(a != b)[0][:16]}"
+    # and the values themselves, so that two equally wrong slaves cannot pass
+    d = dict((k, v) for k, v in lo if v is not None)
+    assert d[vu.GET_FEATURES] == 0x154000007 and d[vu.GET_PROTOCOL_FEATURES] == 0x21F and d[vu.GET_QUEUE_NUM] == 128
+    cq, eq, _ = rings
+    resp = [int(so["end"][cq[3] + 64 * k + 32]) for k in range(8)]
+    assert resp[:4] == [0, 2, 3, 3] and int(so["end"][cq[3] + 64 * 4 + 36]) == 2 and resp[6] == 0xEE
+    assert used_set(so["end"], cq, 8) == used_set(sr["end"], cq, 8) == [(0, 0), (2, 1), (4, 1), (6, 1), (8, 1), (10, 0), (12, 1), (14, 0)]
+    ev = so["end"][eq[3]:eq[3] + 16].tobytes()
+    assert struct.unpack("<I8sI", ev) == (1, bytes([1, 1, 0, 0, 0, 0, 0, 0]), 1)      # TRANSPORT_RESET, target 1, RESCAN
+    ev2 = so["end"][eq[3] + 32:eq[3] + 48].tobytes()
+    assert struct.unpack("<I8sI", ev2) == (1, bytes([1, 1, 0, 0, 0, 0, 0, 0]), 2)     # ... REMOVED
+
+
+def test_vhost_user_reconnect_and_odd_masters(slaves):
+    """a master that disappears mid-handshake, one that sends an unknown request, and a clean reconnect"""
+    ours = slaves("ours", ["--control-only"])
+    m = vu.Master(ours.sock("scsi0"))
+    m.get_u64(vu.GET_FEATURES)
+    m.close()                                           # gone without a word
+    m = vu.Master(ours.sock("scsi0"))
+    m.send(200, b"")                                    # >= VHOST_USER_MAX: the slave drops the connection
+    with pytest.raises((ConnectionError, OSError)):
+        m.s.settimeout(5)
+        m.recv()
+    m.close()
+    m = vu.Master(ours.sock("scsi0"))
+    assert m.set_u64(vu.SET_FEATURES, 1 << 40, need_reply=True) == 1      # unsupported feature bit: refused
+    assert m.get_u64(vu.GET_FEATURES) == 0x154000007
+    m.close()
+    # the RPC side is unaffected, and removing the controller removes its socket
+    assert b'"result":true' in ours.call("remove_vhost_scsi_target", {"ctrlr": "scsi0", "scsi_target_num": 0})
+    assert b'"result":true' in ours.call("remove_vhost_controller", {"ctrlr": "scsi0"})
+    assert not os.path.exists(ours.sock("scsi0"))
+
+
+def make_requests(seed, n=96):
+    t = traces.fuzz_trace(n, NB, seed=seed, max_io_blocks=64, arena_bytes=16 << 20)
+    a0 = np.zeros(t.arena_bytes, dtype=np.uint8)
+    traces.fill_arena(a0, t)
+    return vring.requests_from_trace(t, a0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["kick", "poller"])
+def test_cuda_vhost_user_io_matches_reference(slaves, mode):
+    ours, ref = slaves("ours", ["--poller"] if mode == "poller" else []), slaves("ref")
+    rq = make_requests(11)
+    lo, so, img, rings = run_script(ours, rq, data=True)
+    lr, sr, _, _ = run_script(ref, rq, data=True)
+    assert lo == lr, f"protocol transcripts differ:\nours {lo}\nref  {lr}"
+    a, b = mask(so["end"], img, rings), mask(sr["end"], img, rings)
+    assert (a == b).all(), f"guest memory differs at {np.nonzero(a != b)[0][:16]}"
+    assert dict((k, v) for k, v in lo if v is not None)[vu.GET_VRING_BASE] is not None
+    # the READ on queue 3 went to the hot-plugged target (a fresh Malloc bdev: zeros)
+    data_off = META_END - 4 * 8192
+    assert (so["end"][data_off:data_off + 4096] == 0).all()
