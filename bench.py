@@ -53,6 +53,7 @@ def parse_args():
     p.add_argument("--no-vq", action="store_true", help="skip the virtqueue-mode leg")
     p.add_argument("--no-mixed", action="store_true", help="skip the 70/30 mixed leg (config 4 shape)")
     p.add_argument("--no-lat", action="store_true", help="skip the single-queue qd=32 closed-loop leg")
+    p.add_argument("--no-vu", action="store_true", help="skip the leg through the daemon's vhost-user socket")
     return p.parse_args()
 
 
@@ -513,6 +514,15 @@ def run_ours(args, rank, world, local):
 
     lun.close()
     lun_e2e.close()
+    # ---- the path a VM takes: a separate daemon process, a vhost-user master, guest RAM in a shared memfd ----
+    vuser = None
+    if rank == 0 and world == 1 and not args.no_vu:
+        try:
+            vuser = {"launch_per_kick": vhost_user_leg(args, local, "kick"), "resident_poller": vhost_user_leg(args, local, "poller"),
+                     "workload": "oim-gpu-vhost + vhost-user master over its socket: 64 request queues x 256 READ(10) of 4 KiB "
+                                 "per round, 3-descriptor chains in guest RAM (host memory, pinned by the daemon), 1 GiB Malloc bdev"}
+        except Exception as e:                          # a leg that cannot run must not cost the headline line
+            vuser = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         line = {
             "metric": "4KiB rand-read IOPS", "value": iops, "unit": "IOPS", "n_gpus": world, "steps": args.steps,
@@ -529,11 +539,119 @@ def run_ours(args, rank, world, local):
                          "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
             "seq128k": seq, "virtqueue": vq, "mixed_70_30": mixed, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
+            "vhost_user": vuser,
         }
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def vhost_user_leg(args, device: int, mode: str) -> dict:
+    """The path a VM takes: oim-gpu-vhost as a separate process, a vhost-user master (what QEMU is) connected
+    to <socket dir>/scsi0, guest RAM in a shared memfd that the daemon pins for the GPU, 4 KiB random READs
+    published on virtio rings and kicked through eventfds; completion = used index + call eventfd.
+    Wall-clock around kick -> all completions seen (two processes: there is no common CUDA stream to time on)."""
+    import json as _json
+    import socket
+    import subprocess
+    import tempfile
+    import time
+    from oim_b200 import build, vhost_user_master as vu, vring
+
+    nq, per_q, ring = 64, 256, 1024
+    nb = 1 << 21                                         # 1 GiB bdev: far larger than L2
+    tmp = tempfile.mkdtemp(prefix="oimvu")
+    os.mkdir(os.path.join(tmp, "vhost"))
+    rpc = os.path.join(tmp, "rpc.sock")
+    log = open(os.path.join(tmp, "daemon.log"), "wb")
+    cmd = [build.DAEMON, "-r", rpc, "-S", os.path.join(tmp, "vhost"), "--gpus", str(device)] + (["--poller"] if mode == "poller" else [])
+    proc = subprocess.Popen(cmd, stdout=log, stderr=log)
+    try:
+        t0 = time.time()
+        while not os.path.exists(rpc):
+            if proc.poll() is not None or time.time() - t0 > 120:
+                raise RuntimeError("oim-gpu-vhost did not start: " + open(os.path.join(tmp, "daemon.log")).read()[-500:])
+            time.sleep(0.02)
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.connect(rpc)
+
+        def call(i, method, params):
+            c.sendall((_json.dumps({"jsonrpc": "2.0", "method": method, "params": params, "id": i}) + "\n").encode())
+            buf = b""
+            while not buf.endswith(b"\n"):
+                buf += c.recv(65536)
+            return _json.loads(buf)
+        assert call(1, "construct_malloc_bdev", {"num_blocks": nb, "block_size": BLOCK, "name": "M0"})["result"] == "M0"
+        assert call(2, "construct_vhost_scsi_controller", {"ctrlr": "scsi0"})["result"] is True
+        assert call(3, "add_vhost_scsi_lun", {"ctrlr": "scsi0", "scsi_target_num": 0, "bdev_name": "M0"})["result"] == 0
+
+        g = vring.build_uniform_queues(nq, per_q, nb, ring_size=ring, seed=77)
+        tail = 2 << 20                                   # control / event rings live behind the payload area
+        total = -(-(g.total_bytes() + tail) // (2 << 20)) * (2 << 20)
+        ram = vu.GuestRam(total)
+        ram.mem[:g.data_off] = g.arena
+        ram.mem[g.data_off:g.data_off + g.data_bytes] = 0xAA
+        m = vu.Master(os.path.join(tmp, "vhost", "scsi0"), timeout=60)
+        f = m.get_u64(vu.GET_FEATURES)
+        m.set_u64(vu.SET_PROTOCOL_FEATURES, m.get_u64(vu.GET_PROTOCOL_FEATURES) & 0x9)
+        m.send(vu.SET_OWNER)
+        m.set_u64(vu.SET_FEATURES, f & ~(1 << vu.F_LOG_ALL))
+        # one region: guest-physical gpa_base.. <-> memfd offset 0..; master VA = UVA_BASE + offset
+        assert m.set_mem_table([(g.gpa_base, total, vu.UVA_BASE, 0, ram.fd)], need_reply=True) == 0
+        t_off = g.total_bytes()
+        queues = [vu.Queue(0, 16, t_off, t_off + 256, t_off + 320), vu.Queue(1, 16, t_off + 8192, t_off + 8192 + 256, t_off + 8192 + 320)]
+        for q in range(nq):
+            b = q * g.q_stride
+            queues.append(vu.Queue(2 + q, ring, b + g.desc_off, b + g.avail_off, b + g.used_off))
+        for q in queues:
+            q.setup(m)
+        time.sleep(0.5)
+        a_off = [q * g.q_stride + g.avail_off + 2 for q in range(nq)]
+        u_off = [q * g.q_stride + g.used_off + 2 for q in range(nq)]
+        avail = [ram.mem[o:o + 2].view("<u2") for o in a_off]
+        used = [ram.mem[o:o + 2].view("<u2") for o in u_off]
+
+        def round_trip(k):
+            want = (per_q * (k + 1)) & 0xFFFF
+            for a in avail:
+                a[0] = want
+            for q in queues[2:]:
+                q.notify()
+            spin = time.perf_counter()
+            while True:
+                if all(int(u[0]) == want for u in used):
+                    return
+                if time.perf_counter() - spin > 60:
+                    raise TimeoutError("vhost-user leg: completions missing")
+        for k in range(args.warmup):
+            round_trip(k)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            round_trip(args.warmup + k)
+        dt = time.perf_counter() - t0
+        payload = ram.mem[g.data_off:g.data_off + g.data_bytes]
+        assert not payload.any(), "a fresh Malloc bdev reads as zeros; the buffers were 0xAA"
+        el = ram.mem[g.used_off + 4:g.used_off + 4 + 8 * ring].view(vring.used_elem_dtype)
+        assert int(el["len"][0]) == 108 + 4096
+        for q in queues:
+            m.get_vring_base(q.index)
+        m.close()
+        iops = nq * per_q * args.steps / dt
+        for q in queues:
+            q.close()
+        del avail, used, payload, el
+        ram.close()
+        return {"value": iops, "unit": "IOPS", "mode": mode, "queues": nq, "requests_per_kick_round": nq * per_q,
+                "payload_gbs": iops * 4096 / 1e9, "ms_per_round": dt / args.steps * 1e3,
+                "timing": "host wall clock in the master process, kick -> every used index seen"}
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(10)
+        except Exception:
+            proc.kill()
+        log.close()
 
 
 def main():

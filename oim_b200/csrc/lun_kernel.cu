@@ -686,6 +686,11 @@ __device__ __forceinline__ uint64_t globaltimer_ns()
 	return t;
 }
 
+__device__ __forceinline__ void st_vol32(volatile void *p, uint32_t v)
+{
+	asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ uint16_t ld_vol16(const void *p)
 {
 	uint16_t r;
@@ -844,6 +849,10 @@ __device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc
 	return true;
 }
 
+#ifndef OIM_IDLE_NS
+#define OIM_IDLE_NS 500
+#endif
+
 /* ---- the kernel ----------------------------------------------------------------------------- */
 
 /* parser side: publish the completions of the fill that occupied `st` (all movers are done with it) */
@@ -920,6 +929,42 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 	CtaShared &sh = *reinterpret_cast<CtaShared *>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+	if (hdr->persistent && hdr->dispatcher && blockIdx.x == gridDim.x - 1) {
+		/* ======================= DISPATCHER (see KickHeader) ======================= */
+		if (warp != 0) return;
+		const uint32_t nq = hdr->nqueues;
+		uint64_t last_change = globaltimer_ns();
+		for (;;) {
+			bool changed = false;
+			for (uint32_t base = 0; base < nq; base += 32) {
+				const uint32_t qi = base + lane;
+				if (qi < nq) {
+					const QueueDesc &q = queues[qi];
+					const uint32_t v = q.mode == QMODE_VRING ? (uint32_t)ld_vol16(q.vq_avail + 2) : ld_vol32(q.doorbell);
+					if (v != ld_vol32(&q.vq_state->hint)) {
+						st_vol32(&q.vq_state->hint, v);
+						changed = true;
+					}
+				}
+			}
+			changed = __any_sync(0xffffffffu, changed);
+			uint32_t quit = 0;
+			if (lane == 0) {
+				const uint64_t now = globaltimer_ns();
+				if (changed) last_change = now;
+				quit = ld_vol32(hdr->stop) != 0;
+				if (!quit && hdr->idle_timeout_ms && now - last_change > (uint64_t)hdr->idle_timeout_ms * 1000000ull) quit = 1;
+				if (quit) st_vol32(&hdr->stop_mirror, 1u);
+			}
+			if (__shfl_sync(0xffffffffu, quit, 0)) break;
+		}
+		if (lane == 0) {
+			__threadfence_system();
+			atomicAdd_system(const_cast<uint32_t *>(hdr->exited), 1u);
+		}
+		return;
+	}
+
 	if (tid == 0) {
 		for (int s = 0; s < kStages; s++) {
 			mbar_init(&sh.full[s], 1);
@@ -949,6 +994,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 
 		const uint32_t nqueues = hdr->nqueues;
 		const bool persistent = hdr->persistent != 0;
+		const bool hinted = persistent && hdr->dispatcher != 0;
+		const uint32_t nworkers = hinted ? gridDim.x - 1 : gridDim.x;
 		uint32_t sweep_qi = blockIdx.x;
 		bool progress = false;
 		uint64_t last_progress = persistent ? globaltimer_ns() : 0;
@@ -979,16 +1026,16 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					}
 					uint32_t quit = 0;
 					if (lane == 0) {
-						quit = ld_vol32(hdr->stop) != 0;
+						quit = (hinted ? ld_vol32(&hdr->stop_mirror) : ld_vol32(hdr->stop)) != 0;
 						if (!quit && hdr->idle_timeout_ms &&
 						    globaltimer_ns() - last_progress > (uint64_t)hdr->idle_timeout_ms * 1000000ull) quit = 1;
 					}
 					if (__shfl_sync(0xffffffffu, quit, 0)) break;
-					__nanosleep(500);
+					__nanosleep(OIM_IDLE_NS);
 					continue;
 				}
 				qi = sweep_qi;
-				sweep_qi += gridDim.x;
+				sweep_qi += nworkers;
 			}
 			QueueDesc q = queues[qi];
 			if (persistent && q.mode == QMODE_SLOTS) {
@@ -996,7 +1043,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				uint32_t cnt = 0, consumed = 0;
 				if (lane == 0) {
 					consumed = q.vq_state->last_avail;
-					cnt = ld_vol32(q.doorbell) - consumed;
+					cnt = (hinted ? ld_vol32(&q.vq_state->hint) : ld_vol32(q.doorbell)) - consumed;
 				}
 				q.count = __shfl_sync(0xffffffffu, cnt, 0);
 				q.head = __shfl_sync(0xffffffffu, consumed, 0);
@@ -1008,7 +1055,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				if (lane == 0) {
 					vq_last_avail = q.vq_state->last_avail;
 					vq_last_used = q.vq_state->last_used;
-					cnt = (uint16_t)(ld_vol16(q.vq_avail + 2) - (uint16_t)vq_last_avail);
+					cnt = (uint16_t)((hinted ? (uint16_t)ld_vol32(&q.vq_state->hint) : ld_vol16(q.vq_avail + 2)) - (uint16_t)vq_last_avail);
 					if (cnt > q.vq_size) cnt = 0;	/* "the queue is unrecoverably broken" */
 				}
 				q.count = __shfl_sync(0xffffffffu, cnt, 0);

@@ -1434,7 +1434,7 @@ extern "C" int oimgpu_vq_attach(oimgpu_lun *L, uint32_t q, const void *desc, con
 	if (!L->d_iov_scratch) {
 		CU_OK(cudaMalloc((void **)&L->d_iov_scratch, sizeof(oimgpu_iov) * (size_t)L->grid_cap * kPass * kIovRow));
 	}
-	VqState st = { last_avail_idx, last_used_idx };
+	VqState st = { last_avail_idx, last_used_idx, last_avail_idx, 0 };
 	CU_OK(cudaMemcpy(L->d_vq_state + q, &st, sizeof(st), cudaMemcpyHostToDevice));
 	Queue &Q = L->queues[q];
 	Q.vq_desc = (const uint8_t *)desc;
@@ -1532,12 +1532,14 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 			cursors[q].last_avail = Q.kicked;
 		}
 	}
-	/* slot-ring cursors live in the same VqState array (virtqueues keep theirs) */
-	for (uint32_t q = 0; q < L->num_queues; q++) {
-		if (!L->queues[q].vq_size) CU_OK(cudaMemcpy(L->d_vq_state + q, &cursors[q], sizeof(VqState), cudaMemcpyHostToDevice));
-	}
-	uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap);
+	/* slot-ring cursors live in the same VqState array (virtqueues keep theirs); the dispatcher's view of
+	 * every doorbell starts at "nothing new" */
+	for (uint32_t q = 0; q < L->num_queues; q++) cursors[q].hint = cursors[q].last_avail;
+	CU_OK(cudaMemcpy(L->d_vq_state, cursors.data(), sizeof(VqState) * L->num_queues, cudaMemcpyHostToDevice));
+	/* worker CTAs + one dispatcher CTA (KickHeader::dispatcher) */
+	uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap - 1);
 	if (max_ctas) grid = std::min(grid, max_ctas);
+	if (grid == 0) grid = 1;
 	L->h_flags[0] = 0;
 	L->h_flags[16] = 0;
 	KickHeader *kh = (KickHeader *)L->h_kick[slot];
@@ -1548,14 +1550,15 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 	kh->idle_timeout_ms = idle_timeout_ms;
 	kh->stop = L->d_flags;
 	kh->exited = L->d_flags + 16;
+	kh->dispatcher = 1;
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
-	if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
-	else oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid + 1, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	else oim_lun_queue_kernel<<<grid + 1, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
 	L->kicks++;
 	L->launches++;
-	L->poller_grid = grid;
+	L->poller_grid = grid + 1;	/* CTAs that report in `exited` when the poller winds down */
 	L->poller_max_ctas = max_ctas;
 	L->poller_idle_ms = idle_timeout_ms;
 	L->poller_active = true;

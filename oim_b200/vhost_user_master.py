@@ -4,8 +4,8 @@ Speaks the protocol S/lib/vhost/rte_vhost/vhost_user.{h,c} implements: 12-byte h
 {u32 request, u32 flags, u32 size} + payload, file descriptors as SCM_RIGHTS.  Guest memory is a memfd
 shared with the slave; rings and buffers are laid out in it by oim_b200.vring.
 
-TEST INFRASTRUCTURE - used against oim-gpu-vhost and against the reference's own transport
-(oracle/_ref/liboim_ref_vhost.so) with the same script."""
+Used by the tests (against oim-gpu-vhost and against the reference's own transport
+oracle/_ref/liboim_ref_vhost.so, with the same script) and by bench.py's vhost-user leg."""
 from __future__ import annotations
 
 import mmap

@@ -138,3 +138,76 @@ def test_poller_watchdog_and_busy_errors(gpu):
             assert lun.iostat()["kernel_launches"] == 1
     finally:
         _teardown(gpu, "pw0")
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(180)
+def test_poller_guest_reuses_ring_and_buffers(gpu, oracles):
+    """What a real guest does all day under a resident kernel: the SAME descriptor slots, request headers,
+    indirect tables and data buffers are rewritten by the CPU with different contents round after round,
+    with nothing but the avail index as a signal.  Every round must see the new contents, never what
+    the GPU read from those addresses in an earlier round."""
+    import torch
+    nb, rounds = 32768, 6
+    imgs, refs = [], []
+    with oracles.PortOracle(nb) as o:
+        o.store[:] = traces.pattern_bytes(7, 0, o.store.size)
+        la = lu = 0
+        for r in range(rounds):
+            t = traces.fuzz_trace(40, nb, seed=900 + r, max_io_blocks=32, arena_bytes=8 << 20, include_malformed=False)
+            a0 = np.zeros(t.arena_bytes, dtype=np.uint8)
+            traces.fill_arena(a0, t)
+            rq = vring.requests_from_trace(t, a0)
+            # same seed -> same ring slots, header / table / buffer addresses in every round; different requests
+            img = vring.build_image(rq, ring_size=256, seed=3, mutate=False, pattern_seed=0x5EED + r)
+            ref = vring.build_image(rq, ring_size=256, seed=3, mutate=False, pattern_seed=0x5EED + r)
+            assert img.meta["placed"] == 40
+            o.vq_process(ref)                                      # each image is a fresh ring for the oracle
+            imgs.append(img)
+            refs.append(ref)
+        want_store = o.store.copy()
+    _setup(gpu, "pv1", nb)
+    try:
+        guest = torch.from_numpy(imgs[0].arena.copy()).pin_memory()
+        g = guest.numpy()
+        img0 = imgs[0]
+        avail_idx = g[img0.avail_off + 2:img0.avail_off + 4].view("<u2")
+        used_idx = g[img0.used_off + 2:img0.used_off + 4].view("<u2")
+        avail_idx[0] = 0
+        base = guest.data_ptr()
+        with gpu.Lun("pv1.ctl", 0, num_queues=1, queue_size=32) as lun:
+            lun.set_mem_table(img0.region_table(base))
+            lun.vq_attach(0, base + img0.desc_off, base + img0.avail_off, base + img0.used_off, img0.ring_size, 0, 0)
+            lun.start_poller(idle_timeout_ms=WATCHDOG_MS)
+            try:
+                done = 0
+                for r in range(rounds):
+                    img = imgs[r]
+                    if r:
+                        # the guest rewrites its memory in place: everything except the ring indices, then
+                        # the avail ring entries at the positions the next 40 heads go to
+                        keep_a, keep_u = int(avail_idx[0]), int(used_idx[0])
+                        lo, hi = img.avail_off, img.used_off + 4 + 8 * img.ring_size
+                        g[:lo] = img.arena[:lo]
+                        g[hi:] = img.arena[hi:]
+                        ring = g[img.avail_off + 4:img.avail_off + 4 + 2 * img.ring_size].view("<u2")
+                        src = img.arena[img.avail_off + 4:img.avail_off + 4 + 2 * img.ring_size].view("<u2")
+                        for k in range(40):
+                            ring[(keep_a + k) % img.ring_size] = src[k]
+                        assert (int(avail_idx[0]), int(used_idx[0])) == (keep_a, keep_u)
+                    done += 40
+                    avail_idx[0] = done
+                    deadline = time.time() + 20
+                    while int(used_idx[0]) != done and time.time() < deadline:
+                        time.sleep(0.0005)
+                    assert int(used_idx[0]) == done, f"round {r}: used->idx stuck at {int(used_idx[0])}"
+                    # everything outside the two rings equals what the oracle left for this round's image
+                    want = refs[r].arena
+                    lo, hi = img.avail_off, img.used_off + 4 + 8 * img.ring_size
+                    assert (g[:lo] == want[:lo]).all(), f"round {r}: guest memory differs at {np.nonzero(g[:lo] != want[:lo])[0][:8]}"
+                    assert (g[hi:] == want[hi:]).all(), f"round {r}: guest memory differs at {hi + np.nonzero(g[hi:] != want[hi:])[0][:8]}"
+            finally:
+                lun.stop_poller()
+        assert (gpu.bdev_read_raw("pv1", 0, nb * 512) == want_store).all()
+    finally:
+        _teardown(gpu, "pv1")

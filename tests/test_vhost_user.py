@@ -1,7 +1,7 @@
 """The vhost-user transport: a master - what QEMU's vhost-user-scsi-pci is - connects to
 <socket dir>/<controller>, shares its memory, hands over the virtqueues and does I/O.
 
-The same master script (tests/vhost_user_master.py) runs against oim-gpu-vhost and against the REFERENCE'S OWN
+The same master script (oim_b200/vhost_user_master.py) runs against oim-gpu-vhost and against the REFERENCE'S OWN
 transport + vhost-scsi + bdev stack (oracle/_ref/liboim_ref_vhost.so: S/lib/vhost/rte_vhost/* compiled where it
 lies), and the protocol transcripts and the guest memory are compared.
 
@@ -18,7 +18,7 @@ import pytest
 
 from oim_b200 import abi, traces, vring
 from test_rpc_daemon import DAEMON, ROOT, Client
-import vhost_user_master as vu
+from oim_b200 import vhost_user_master as vu
 
 META_END = 2 * vring.R01_SIZE + (4 << 20)          # end of the image's metadata area (rings, headers)
 NB = 32768
