@@ -269,9 +269,10 @@ def run_ours(args, rank, world, local):
     timer = lib.Timer()
     out = {}
 
-    def resident_leg(io_blocks, pattern, sg, nq, per_q, steps, warmup, check):
+    def resident_leg(io_blocks, pattern, sg, nq, per_q, steps, warmup, check, target=0):
         n = nq * per_q
-        t = traces.uniform_trace(n, NUM_BLOCKS, io_blocks=io_blocks, pattern=pattern, sg=sg, seed=plan["trace_seed"])
+        t = traces.uniform_trace(n, NUM_BLOCKS, io_blocks=io_blocks, pattern=pattern, sg=sg, seed=plan["trace_seed"],
+                                 target=target)
         arena = torch.empty(t.arena_bytes, dtype=torch.uint8, device="cuda")
         if "write" in pattern:
             arena.view(torch.int64)[:] = 0x0123456789ABCDEF
@@ -493,15 +494,22 @@ def run_ours(args, rank, world, local):
             lat[mode] = {"iops": 32 * rounds / dt, "us_per_round_trip": dt / rounds * 1e6}
         lat["workload"] = "1 queue, qd=32, 4 KiB random read, closed loop of oimgpu_submit_and_wait calls, pinned client buffers"
 
-    # ---- second metric: 128 KiB sequential write (runs last: it overwrites the patterned store) ----
+    # ---- second metric: 128 KiB sequential write ----
     seq = None
     if not args.no_seq:
+        # BASELINE config 3: the volume is what oim-csi-driver's ceph path maps - construct_rbd_bdev (HBM-backed
+        # here) - attached as a SECOND target of the same controller, the way MapVolume adds volumes; the same
+        # session reaches it through lun[1] = 1
+        rbd = lib.construct_rbd_bdev("rbd", f"bench-image-{rank}", BLOCK, NUM_BLOCKS * BLOCK, name=f"Ceph{rank}", device=local)
+        lib.add_vhost_scsi_lun(plan["ctrlr"], 1, rbd)
         sq, sp = args.seq_queues, args.seq_per_queue       # 256 x 256 x 128 KiB = one pass over the 8 GiB device
-        n2, ms2, l2, _ = resident_leg(256, "seqwrite", "pages", sq, sp, args.steps, args.warmup, None)
+        n2, ms2, l2, _ = resident_leg(256, "seqwrite", "pages", sq, sp, args.steps, args.warmup, None, target=1)
+        assert lun.iostat(1)["bytes_written"] >= n2 * 131072, "the writes were not booked on the RBD volume"
         seq_gbs = n2 * args.steps * world * 131072 / (ms2 / 1e3) / 1e9
         seq = {"metric": "128KiB seq-write GB/s (32 x 4 KiB SG pages)", "value": seq_gbs, "unit": "GB/s",
                "ms_per_step": ms2 / args.steps, "hbm_frac": 2 * seq_gbs / world / peak,
-               "requests_per_step": n2, "queues": sq}
+               "requests_per_step": n2, "queues": sq,
+               "volume": "construct_rbd_bdev (Ceph RBD emulated in HBM), target 1 of the benchmark controller"}
 
     clocks = sampler.stop() if rank == 0 else {}
 

@@ -180,6 +180,18 @@ struct oimgpu_lun {
 
 /* ---------------------------------------------------------------------------------------------- */
 
+/* Small host->device updates of a session's state.  A plain cudaMemcpy from pageable memory may return
+ * before the DMA has landed, and it runs on the legacy stream, which the sessions' non-blocking streams do
+ * not wait for: a kernel launched right afterwards could still read the old bytes.  Going through the
+ * session's own stream and waiting for it closes both gaps.  (Never called with a resident poller on
+ * that stream: those paths stop it first.) */
+static cudaError_t h2d_sync(oimgpu_lun *L, void *dst, const void *src, size_t n)
+{
+	cudaError_t e = cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, L->stream);
+	if (e != cudaSuccess) return e;
+	return cudaStreamSynchronize(L->stream);
+}
+
 static int find_device_slot(int ordinal)
 {
 	for (size_t i = 0; i < g.devices.size(); i++) {
@@ -293,19 +305,31 @@ static int refresh_peers_locked(oimgpu_lun *L)
 }
 
 /* cudaFree waits for the whole device, and a resident poller kernel never finishes on its own: park
- * the pollers of that GPU around a free and bring them back afterwards */
-static std::vector<oimgpu_lun *> park_pollers_locked(int device)
+ * the pollers of that GPU around a free and bring them back afterwards.  Every session of the GPU is
+ * held (its mutex taken) for the duration, so that none can start a resident kernel in the window -
+ * their owners' calls simply wait.  Caller holds g.mu; sessions never take g.mu while holding their own
+ * mutex, so the order g.mu -> session mutex is safe. */
+struct ParkedSession { oimgpu_lun *L; bool restart; };
+
+static std::vector<ParkedSession> park_pollers_locked(int device, oimgpu_lun *except = nullptr)
 {
-	std::vector<oimgpu_lun *> parked;
+	std::vector<ParkedSession> parked;
 	for (oimgpu_lun *L : g.handles) {
-		if (L->device == device && L->poller_active && oimgpu_lun_stop_poller(L) == 0) parked.push_back(L);
+		if (L == except || L->device != device) continue;
+		L->mu.lock();
+		const bool was = L->poller_active;
+		if (was) oimgpu_lun_stop_poller(L);
+		parked.push_back({L, was});
 	}
 	return parked;
 }
 
-static void unpark_pollers_locked(const std::vector<oimgpu_lun *> &parked)
+static void unpark_pollers_locked(const std::vector<ParkedSession> &parked)
 {
-	for (oimgpu_lun *L : parked) oimgpu_lun_start_poller(L, L->poller_max_ctas, L->poller_idle_ms);
+	for (const ParkedSession &p : parked) {
+		if (p.restart) oimgpu_lun_start_poller(p.L, p.L->poller_max_ctas, p.L->poller_idle_ms);
+		p.L->mu.unlock();
+	}
 }
 
 static void refresh_ctrlr_sessions_locked(const std::string &ctrlr)
@@ -889,7 +913,7 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	else fill_lun_ctx(L->h_ctx, *bp, *it->second, scsi_target_num);
 	L->any_mirror = L->h_ctx.nreplicas > 1;
 	CU_OK(cudaMalloc((void **)&L->d_ctx, sizeof(LunCtx)));
-	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, sizeof(LunCtx), cudaMemcpyHostToDevice));
+	CU_OK(h2d_sync(L.get(), L->d_ctx, &L->h_ctx, sizeof(LunCtx)));
 
 	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
 		CU_OK(cudaHostAlloc((void **)&L->h_kick[k], sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 3, cudaHostAllocDefault));
@@ -924,7 +948,8 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	CU_OK(cudaHostGetDevicePointer((void **)&L->d_flags, (void *)L->h_flags, 0));
 	memset((void *)L->h_flags, 0, 256);
 	CU_OK(cudaMalloc((void **)&L->d_vq_state, sizeof(VqState) * num_queues));
-	CU_OK(cudaMemset(L->d_vq_state, 0, sizeof(VqState) * num_queues));
+	CU_OK(cudaMemsetAsync(L->d_vq_state, 0, sizeof(VqState) * num_queues, L->stream));
+	CU_OK(cudaStreamSynchronize(L->stream));
 	int per_sm = 0;
 	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes()));
 	if (per_sm < 1) per_sm = 1;
@@ -948,7 +973,7 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 		L->poller_active = false;
 	}
 	cudaStreamSynchronize(L->stream);
-	auto parked = park_pollers_locked(L->device);	/* other sessions' resident kernels: see park_pollers_locked */
+	auto parked = park_pollers_locked(L->device, L);	/* other sessions' resident kernels: see park_pollers_locked */
 	cudaSetDevice(L->device);
 	cudaFreeHost((void *)L->h_door);
 	cudaFreeHost((void *)L->h_flags);
@@ -1395,7 +1420,7 @@ extern "C" int oimgpu_lun_set_removed(oimgpu_lun *L, int removed, int lun_remove
 	CU_OK(cudaStreamSynchronize(L->stream));
 	L->h_ctx.removed = removed != 0;
 	L->h_ctx.lun_removed = lun_removed != 0;
-	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, offsetof(LunCtx, stats), cudaMemcpyHostToDevice));
+	CU_OK(h2d_sync(L, L->d_ctx, &L->h_ctx, offsetof(LunCtx, stats)));
 	return 0;
 }
 
@@ -1416,7 +1441,7 @@ extern "C" int oimgpu_lun_set_mem_table(oimgpu_lun *L, const oimgpu_mem_region *
 		L->h_ctx.region[i].size = regions[i].size;
 		L->h_ctx.region[i].addr = regions[i].addr;
 	}
-	CU_OK(cudaMemcpy(L->d_ctx, &L->h_ctx, offsetof(LunCtx, stats), cudaMemcpyHostToDevice));
+	CU_OK(h2d_sync(L, L->d_ctx, &L->h_ctx, offsetof(LunCtx, stats)));
 	return 0;
 }
 
@@ -1435,7 +1460,7 @@ extern "C" int oimgpu_vq_attach(oimgpu_lun *L, uint32_t q, const void *desc, con
 		CU_OK(cudaMalloc((void **)&L->d_iov_scratch, sizeof(oimgpu_iov) * (size_t)L->grid_cap * kPass * kIovRow));
 	}
 	VqState st = { last_avail_idx, last_used_idx, last_avail_idx, 0 };
-	CU_OK(cudaMemcpy(L->d_vq_state + q, &st, sizeof(st), cudaMemcpyHostToDevice));
+	CU_OK(h2d_sync(L, L->d_vq_state + q, &st, sizeof(st)));
 	Queue &Q = L->queues[q];
 	Q.vq_desc = (const uint8_t *)desc;
 	Q.vq_avail = (const uint8_t *)avail;
@@ -1535,7 +1560,7 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 	/* slot-ring cursors live in the same VqState array (virtqueues keep theirs); the dispatcher's view of
 	 * every doorbell starts at "nothing new" */
 	for (uint32_t q = 0; q < L->num_queues; q++) cursors[q].hint = cursors[q].last_avail;
-	CU_OK(cudaMemcpy(L->d_vq_state, cursors.data(), sizeof(VqState) * L->num_queues, cudaMemcpyHostToDevice));
+	CU_OK(h2d_sync(L, L->d_vq_state, cursors.data(), sizeof(VqState) * L->num_queues));
 	/* worker CTAs + one dispatcher CTA (KickHeader::dispatcher) */
 	uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap - 1);
 	if (max_ctas) grid = std::min(grid, max_ctas);

@@ -13,6 +13,7 @@
 #include <cerrno>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -85,6 +86,8 @@ struct MemTableMsg {
 
 Config g_cfg;
 std::mutex g_mu;
+const bool g_debug = getenv("OIM_VU_DEBUG") != nullptr;
+#define VU_DEBUG(...) do { if (g_debug) { fprintf(stderr, "vhost-user: " __VA_ARGS__); fputc('\n', stderr); } } while (0)
 
 struct Server;
 
@@ -483,7 +486,10 @@ bool Session::start()
 			}
 			r.registered = rc == 0;
 			uint64_t dev = 0;
-			if (oimgpu_mem_device_addr(r.host, &dev) != 0) return false;
+			if (oimgpu_mem_device_addr(r.host, &dev) != 0) {
+				fprintf(stderr, "oim-gpu-vhost: %s: guest memory has no device address\n", srv->name.c_str());
+				return false;
+			}
 			r.dev = dev;
 		}
 		const uint32_t want = max_queues > 2 ? max_queues - 2 : 1;
@@ -499,7 +505,11 @@ bool Session::start()
 		}
 		std::vector<oimgpu_mem_region> tbl;
 		for (const Region &r : mem) tbl.push_back({r.gpa, r.size, r.dev});
-		if (oimgpu_lun_set_mem_table(lun, tbl.data(), (uint32_t)tbl.size()) != 0) return false;
+		int mrc = oimgpu_lun_set_mem_table(lun, tbl.data(), (uint32_t)tbl.size());
+		if (mrc != 0) {
+			fprintf(stderr, "oim-gpu-vhost: %s: memory table refused: %s\n", srv->name.c_str(), strerror(-mrc));
+			return false;
+		}
 		for (uint32_t i = 2; i < max_queues; i++) {
 			Vq &q = vq[i];
 			q.attached = false;
@@ -519,6 +529,8 @@ bool Session::start()
 		}
 	}
 	running = true;
+	VU_DEBUG("%s: session %d started: %u queues, %zu regions, %s", srv->name.c_str(), fd, max_queues, mem.size(),
+		 polling ? "resident poller" : lun ? "launch per kick" : "no data path");
 	return true;
 }
 
@@ -537,6 +549,7 @@ void Session::stop()
 		}
 	}
 	running = false;
+	VU_DEBUG("%s: session %d stopped", srv->name.c_str(), fd);
 }
 
 /* vdev_worker + vdev_mgmt_worker (vhost_scsi.c:742-772), event driven */

@@ -307,3 +307,64 @@ def test_cuda_vhost_user_io_matches_reference(slaves, mode):
     # the READ on queue 3 went to the hot-plugged target (a fresh Malloc bdev: zeros)
     data_off = META_END - 4 * 8192
     assert (so["end"][data_off:data_off + 4096] == 0).all()
+
+
+class Vm:
+    """a connected master with one request queue's worth of work laid out in its RAM"""
+
+    def __init__(self, s: Slave, rq, seed):
+        self.img = vring.build_image(rq, ring_size=256, seed=seed, mutate=False)
+        self.ram = vu.GuestRam(self.img.arena.size)
+        self.ram.mem[:] = self.img.arena
+        self.rings = (small_ring(0), small_ring(1))
+        for r in self.rings:
+            self.ram.mem[r[0]:r[0] + 8192] = 0
+        img = self.img
+        self.queues = [vu.Queue(0, 16, *self.rings[0][:3]), vu.Queue(1, 16, *self.rings[1][:3]),
+                       vu.Queue(2, img.ring_size, img.desc_off, img.avail_off, img.used_off)]
+        self.m = vu.Master(s.sock("scsi0"))
+        handshake(self.m, self.ram, img, self.queues)
+        time.sleep(0.3)
+
+    def io(self):
+        self.queues[2].notify()
+        self.queues[2].wait_used(self.ram, self.img.meta["placed"])
+        c = self.img.masked(self.ram.mem)
+        for used_off in [self.img.used_off] + [r[2] for r in self.rings]:
+            c[used_off:used_off + 2] = 0
+        return c
+
+    def close(self, graceful=True):
+        base = [self.m.get_vring_base(q.index) for q in self.queues] if graceful else None
+        self.m.close()
+        for q in self.queues:
+            q.close()
+        self.ram.close()
+        return base
+
+
+def two_vm_script(s: Slave):
+    """VM A connects and idles; VM B connects, does I/O and disappears without a word; A then does its I/O and
+    shuts down cleanly; a third VM re-uses the controller afterwards"""
+    out = {}
+    a = Vm(s, make_requests(21, 64), 3)
+    b = Vm(s, make_requests(22, 64), 4)
+    out["b"] = b.io()
+    b.close(graceful=False)
+    out["a"] = a.io()
+    out["a_base"] = a.close()
+    c = Vm(s, make_requests(23, 64), 5)
+    out["c"] = c.io()
+    out["c_base"] = c.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["kick", "poller"])
+def test_cuda_vhost_user_sessions_come_and_go(slaves, mode):
+    ours, ref = slaves("ours", ["--poller"] if mode == "poller" else []), slaves("ref")
+    got, want = two_vm_script(ours), two_vm_script(ref)
+    for k in ("a", "b", "c"):
+        assert (got[k] == want[k]).all(), f"VM {k}: guest memory differs at {np.nonzero(got[k] != want[k])[0][:16]}"
+    assert got["a_base"] == want["a_base"] and got["c_base"] == want["c_base"]
+    assert got["a_base"][2] == 64 - 0 or got["a_base"][2] > 0
