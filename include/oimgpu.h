@@ -190,6 +190,10 @@ int oimgpu_bdev_delete(const char *name);			/* -ENODEV if unknown; attached targ
 								 * data path (oimgpu_lun) is open on it */
 int oimgpu_bdev_get(const char *name, struct oimgpu_bdev_info *out);	/* -ENODEV if unknown */
 int oimgpu_bdev_list(struct oimgpu_bdev_info *out, int max);	/* returns count */
+/* get_bdevs_iostat (S/lib/bdev/rpc/bdev_rpc.c:50-205): what the bdev has served over its lifetime, through
+ * whichever sessions and targets; -ENODEV if there is no such bdev.  kernel_launches is 0 here. */
+int oimgpu_bdev_iostat(const char *name, struct oimgpu_iostat *out);
+
 /* test/digest helpers: raw access to the backing store of replica r (synchronous) */
 int oimgpu_bdev_read_raw(const char *name, int replica, uint64_t offset, void *dst, uint64_t len);
 int oimgpu_bdev_write_raw(const char *name, int replica, uint64_t offset, const void *src, uint64_t len);

@@ -128,6 +128,7 @@ __device__ __noinline__ void scsi_unmap(const LunCtx &L, const QueueDesc &q, con
 		return;
 	}
 	uint32_t nseg = 0, units = 0;
+	uint64_t total = 0;
 	for (int i = 0; i < desc_count; i++) {
 		uint64_t ob = 0;
 		uint32_t nb = 0;
@@ -151,10 +152,12 @@ __device__ __noinline__ void scsi_unmap(const LunCtx &L, const QueueDesc &q, con
 		}
 		nseg++;
 		units += units_of(bytes);
+		total += bytes;
 	}
 	if (!emit) {
 		s.nseg = nseg;
 		s.units = units;
+		s.unmap_bytes = total;
 		s.op = OP_UNMAP;
 		s.hazard = nseg ? 3 : 0;
 	}
@@ -989,7 +992,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 #pragma unroll
 		for (int h = 0; h < kHist; h++) { prev_lo[h] = prev_hi[h] = 0; prev_haz[h] = 0; }
 		uint32_t st_rd = 0, st_wr = 0, st_um = 0, st_er = 0;
-		unsigned long long st_rb = 0, st_wb = 0;
+		unsigned long long st_rb = 0, st_wb = 0, st_ub = 0;
 		bool first = true;
 
 		const uint32_t nqueues = hdr->nqueues;
@@ -1208,16 +1211,24 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				const bool ok = good && own;
 				st_rd += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_READ));
 				st_wr += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_WRITE));
-				st_um += __popc(__ballot_sync(0xffffffffu, ok && s.op == OP_UNMAP));
+				/* UNMAP reaches the bdev once per applied descriptor, whatever the command's final status */
+				const bool um = active && s.resp_valid && s.response == OIMGPU_S_OK && s.op == OP_UNMAP && s.tgt == L.target;
+				st_um += __reduce_add_sync(0xffffffffu, um ? s.nseg : 0u);
+				if (um) st_ub += s.unmap_bytes;
 				st_er += __popc(__ballot_sync(0xffffffffu, active && !good));
 				if (ok && s.op == OP_READ) st_rb += s.length;
 				if (ok && s.op == OP_WRITE) st_wb += s.length;
-				if (good && !own && (s.op == OP_READ || s.op == OP_WRITE || s.op == OP_UNMAP)) {
+				if (active && s.resp_valid && s.response == OIMGPU_S_OK && s.tgt != L.target &&
+				    ((good && (s.op == OP_READ || s.op == OP_WRITE)) || s.op == OP_UNMAP)) {
 					/* another device of the controller: book it there (rare path, plain atomics) */
 					LunCtx *P = L.peer[s.tgt];
-					const int k = s.op == OP_READ ? 0 : s.op == OP_WRITE ? 1 : 2;
-					atomicAdd(&P->stats[k], 1ull);
-					if (k < 2) atomicAdd(&P->stats[4 + k], (unsigned long long)s.length);
+					if (s.op == OP_UNMAP) {
+						if (s.nseg) { atomicAdd(&P->stats[2], (unsigned long long)s.nseg); atomicAdd(&P->stats[6], (unsigned long long)s.unmap_bytes); }
+					} else {
+						const int k = s.op == OP_READ ? 0 : 1;
+						atomicAdd(&P->stats[k], 1ull);
+						atomicAdd(&P->stats[4 + k], (unsigned long long)s.length);
+					}
 				}
 
 				/* rounds: as many whole requests as fit in one stage's segment table */
@@ -1308,11 +1319,15 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			atomicAdd_system(const_cast<uint32_t *>(hdr->exited), 1u);
 		}
 		/* flush counters: one atomic per counter per CTA */
-		st_rb = __reduce_add_sync(0xffffffffu, (uint32_t)(st_rb >> 9));
-		st_wb = __reduce_add_sync(0xffffffffu, (uint32_t)(st_wb >> 9));
+		for (int o = 16; o; o >>= 1) {
+			st_rb += __shfl_xor_sync(0xffffffffu, st_rb, o);
+			st_wb += __shfl_xor_sync(0xffffffffu, st_wb, o);
+			st_ub += __shfl_xor_sync(0xffffffffu, st_ub, o);
+		}
+		if (lane == 0 && st_ub) atomicAdd(&lun->stats[6], st_ub);
 		if (lane == 0) {
-			if (st_rd) { atomicAdd(&lun->stats[0], (unsigned long long)st_rd); atomicAdd(&lun->stats[4], st_rb << 9); }
-			if (st_wr) { atomicAdd(&lun->stats[1], (unsigned long long)st_wr); atomicAdd(&lun->stats[5], st_wb << 9); }
+			if (st_rd) { atomicAdd(&lun->stats[0], (unsigned long long)st_rd); atomicAdd(&lun->stats[4], st_rb); }
+			if (st_wr) { atomicAdd(&lun->stats[1], (unsigned long long)st_wr); atomicAdd(&lun->stats[5], st_wb); }
 			if (st_um) atomicAdd(&lun->stats[2], (unsigned long long)st_um);
 			if (st_er) atomicAdd(&lun->stats[7], (unsigned long long)st_er);
 		}

@@ -166,6 +166,7 @@ struct LaneState {
 	uint8_t  resp_valid;
 	uint8_t  hazard;		/* 0 none, 1 reads store, 2 writes store, 3 barrier (multi-range writer) */
 	uint8_t  tgt;			/* SCSI target the request addressed (valid once the target check passed) */
+	uint64_t unmap_bytes;		/* UNMAP: bytes of the descriptors that were applied */
 	uint8_t  scratch[256];		/* control payloads: READ CAPACITY, REQUEST SENSE, INQUIRY pages (<= 125 B),
 					 * MODE SENSE (<= 188 B), REPORT LUNS */
 };

@@ -71,6 +71,7 @@ struct Bdev {
 	int open_luns = 0;	/* oimgpu_lun handles */
 	std::vector<int> devices;	/* replica r lives on devices[r] */
 	std::vector<uint8_t *> stores;
+	unsigned long long retired[8] = {};	/* counters of sessions that are gone (same layout as LunCtx::stats) */
 };
 
 struct Ctrlr {
@@ -220,6 +221,27 @@ static void fill_lun_ctx(LunCtx &c, const Bdev &b, const Ctrlr &ctrlr, int targe
 	c.protocol_id = 0x06;
 }
 
+/* counters of one device-resident context, read on the housekeeping stream (works next to a resident poller) */
+static bool read_ctx_stats(int device, const LunCtx *d_ctx, unsigned long long out[8])
+{
+	const int slot = find_device_slot(device);
+	if (slot < 0 || !d_ctx) return false;
+	cudaSetDevice(device);
+	cudaStream_t st = g.devices[slot].util;
+	if (cudaMemcpyAsync(out, (const uint8_t *)d_ctx + offsetof(LunCtx, stats), sizeof(unsigned long long) * 8,
+			    cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+	return cudaStreamSynchronize(st) == cudaSuccess;
+}
+
+/* a session lets go of a bdev: keep what it counted (get_bdevs_iostat is per bdev, for its lifetime) */
+static void retire_stats_locked(const std::string &bdev, int device, const LunCtx *d_ctx)
+{
+	auto bi = g.bdevs.find(bdev);
+	unsigned long long v[8];
+	if (bi == g.bdevs.end() || !read_ctx_stats(device, d_ctx, v)) return;
+	for (int k = 0; k < 8; k++) bi->second->retired[k] += v[k];
+}
+
 static bool device_reachable(int from, int to)
 {
 	if (from == to) return true;
@@ -267,6 +289,8 @@ static int refresh_peers_locked(oimgpu_lun *L)
 		if (!L->peer_bdev[t].empty()) {
 			auto bi = g.bdevs.find(L->peer_bdev[t]);
 			if (bi != g.bdevs.end() && bi->second->open_luns > 0) bi->second->open_luns--;
+			if (!L->poller_active) cudaStreamSynchronize(L->stream);
+			retire_stats_locked(L->peer_bdev[t], L->device, L->d_peer[t]);
 		}
 		L->peer_bdev[t] = want;
 		if (want.empty()) {
@@ -973,6 +997,10 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 		L->poller_active = false;
 	}
 	cudaStreamSynchronize(L->stream);
+	if (!L->bdev.empty()) retire_stats_locked(L->bdev, L->device, L->d_ctx);
+	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		if (!L->peer_bdev[t].empty()) retire_stats_locked(L->peer_bdev[t], L->device, L->d_peer[t]);
+	}
 	auto parked = park_pollers_locked(L->device, L);	/* other sessions' resident kernels: see park_pollers_locked */
 	cudaSetDevice(L->device);
 	cudaFreeHost((void *)L->h_door);
@@ -1409,6 +1437,39 @@ extern "C" int oimgpu_lun_target_iostat(oimgpu_lun *L, int scsi_target_num, oimg
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (L->peer_bdev[scsi_target_num].empty()) return -ENODEV;
 	return read_iostat(L, L->d_peer[scsi_target_num], out);
+}
+
+/* spdk_bdev_get_device_stat as get_bdevs_iostat reports it (S/lib/bdev/rpc/bdev_rpc.c:50-110): the counters of
+ * a bdev over its lifetime, whichever sessions and targets the I/O came through */
+extern "C" int oimgpu_bdev_iostat(const char *name, oimgpu_iostat *out)
+{
+	if (!out) return -EINVAL;
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.bdevs.find(name ? name : "");
+	if (it == g.bdevs.end()) return -ENODEV;
+	unsigned long long sum[8], v[8];
+	memcpy(sum, it->second->retired, sizeof(sum));
+	for (oimgpu_lun *L : g.handles) {
+		if (L->bdev == it->first && read_ctx_stats(L->device, L->d_ctx, v)) {
+			for (int k = 0; k < 8; k++) sum[k] += v[k];
+		}
+		for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+			if (L->peer_bdev[t] == it->first && read_ctx_stats(L->device, L->d_peer[t], v)) {
+				for (int k = 0; k < 8; k++) sum[k] += v[k];
+			}
+		}
+	}
+	memset(out, 0, sizeof(*out));
+	out->num_read_ops = sum[0];
+	out->num_write_ops = sum[1];
+	out->num_unmap_ops = sum[2];
+	out->num_other_ops = sum[3];
+	out->bytes_read = sum[4];
+	out->bytes_written = sum[5];
+	out->bytes_unmapped = sum[6];
+	out->num_errors = sum[7];
+	return 0;
 }
 
 /* session-visible target state: hot-remove flags (vhost_scsi.c:1093-1100, lun.c:171-176) */

@@ -325,6 +325,33 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 		}
 		return result(id, out + "]");
 	}
+	if (method == "get_bdevs_iostat") {
+		/* S/lib/bdev/rpc/bdev_rpc.c:50-205.  Latencies are not tracked per request on the GPU path: the three
+		 * *_latency_ticks members are reported as 0; tick_rate is the GPU's global timer (1 GHz). */
+		if (params && !decode(params, {{"name", Json::Str, true, &a}})) return bad;
+		std::vector<std::string> names;
+		if (a) {
+			oimgpu_bdev_info info;
+			if (oimgpu_bdev_get(a->raw.c_str(), &info) != 0) return bad;
+			names.push_back(info.name);
+		} else {
+			int n = oimgpu_bdev_list(nullptr, 0);
+			std::vector<oimgpu_bdev_info> v(n > 0 ? n : 1);
+			n = oimgpu_bdev_list(v.data(), n);
+			for (int i = 0; i < n; i++) names.push_back(v[i].name);
+		}
+		std::string out = "[{\"tick_rate\":1000000000}";
+		for (auto &nm : names) {
+			oimgpu_iostat st;
+			if (oimgpu_bdev_iostat(nm.c_str(), &st) != 0) continue;
+			out += ",{\"name\":" + jstr(nm) + ",\"bytes_read\":" + std::to_string(st.bytes_read) +
+			       ",\"num_read_ops\":" + std::to_string(st.num_read_ops) + ",\"bytes_written\":" + std::to_string(st.bytes_written) +
+			       ",\"num_write_ops\":" + std::to_string(st.num_write_ops) + ",\"bytes_unmapped\":" + std::to_string(st.bytes_unmapped) +
+			       ",\"num_unmap_ops\":" + std::to_string(st.num_unmap_ops) +
+			       ",\"read_latency_ticks\":0,\"write_latency_ticks\":0,\"unmap_latency_ticks\":0}";
+		}
+		return result(id, out + "]");
+	}
 	if (method == "construct_malloc_bdev") {
 		uint64_t nb = 0, bs = 0;
 		if (!decode(params, {{"name", Json::Str, true, &a}, {"uuid", Json::Str, true, &b},

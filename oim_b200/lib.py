@@ -86,6 +86,7 @@ SYMBOLS = [
     ("oimgpu_lun_sync", _I, [_VP]),
     ("oimgpu_submit_batch", _I, [_VP, _U32, _U32, _VP, _VP, _U32, _VP, _I]),
     ("oimgpu_submit_and_wait", _I, [_VP, _U32, _U32, _VP, _VP, _U32, _VP, _I]),
+    ("oimgpu_bdev_iostat", _I, [C.c_char_p, C.POINTER(IoStat)]),
     ("oimgpu_lun_iostat", _I, [_VP, C.POINTER(IoStat)]),
     ("oimgpu_lun_target_iostat", _I, [_VP, _I, C.POINTER(IoStat)]),
     ("oimgpu_lun_stream", _VP, [_VP]),
@@ -182,6 +183,13 @@ def _bdev_dict(i: BdevInfo) -> dict:
     return {"name": i.name.decode(), "product_name": i.product_name.decode(), "uuid": i.uuid.decode(),
             "num_blocks": i.num_blocks, "block_size": i.block_size, "claimed": bool(i.claimed),
             "device": i.device, "replicas": i.replicas, "device_ptr": i.device_ptr}
+
+
+def get_bdevs_iostat(name: str) -> dict:
+    """S/lib/bdev/rpc/bdev_rpc.c:50-205 get_bdevs_iostat for one bdev"""
+    s = IoStat()
+    _chk(load().oimgpu_bdev_iostat(_b(name), C.byref(s)), "get_bdevs_iostat")
+    return {n: getattr(s, n) for n, _ in IoStat._fields_}
 
 
 def get_bdevs(name: str | None = None) -> list[dict]:

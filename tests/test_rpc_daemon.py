@@ -57,6 +57,7 @@ class Client:
 
 def norm(reply: bytes) -> str:
     s = reply.decode()
+    s = re.sub(r'"tick_rate":\d+', '"tick_rate":"<hz>"', s)                          # the clock is the implementation's own
     return re.sub(r'"uuid":"(?!11111111-)[0-9a-f-]{36}"', '"uuid":"<uuid>"', s)     # random unless the test chose it
 
 
@@ -141,6 +142,14 @@ def test_rpc_transcript_matches_reference_server(servers):
                                                       "luns": [{"id": 0, "bdev_name": "MyVol"}]}
     both(servers, "get_vhost_controllers", {"name": "vhost.1"})
     assert both(servers, "get_vhost_controllers", {"name": "nope"})["error"]["code"] == -32603
+    # ---- get_bdevs_iostat (bdev_rpc.c:50-205): member names and order, one object per bdev in registration order
+    st = both(servers, "get_bdevs_iostat")["result"]
+    assert [x.get("name") for x in st[1:]] == ["Malloc0", "MyVol", "Malloc1", "WithUuid"] and "tick_rate" in st[0]
+    assert list(st[1].keys()) == ["name", "bytes_read", "num_read_ops", "bytes_written", "num_write_ops", "bytes_unmapped",
+                                  "num_unmap_ops", "read_latency_ticks", "write_latency_ticks", "unmap_latency_ticks"]
+    assert len(both(servers, "get_bdevs_iostat", {"name": "MyVol"})["result"]) == 2
+    assert both(servers, "get_bdevs_iostat", {"name": "nope"})["error"]["code"] == -32602
+    both(servers, "get_bdevs_iostat", {"nam": "MyVol"})
     # ---- teardown order of UnmapVolume (controller.go:159-212)
     assert both(servers, "remove_vhost_controller", {"ctrlr": "vhost.0"})["error"]["message"] == "Device or resource busy"
     assert both(servers, "remove_vhost_scsi_target", {"ctrlr": "vhost.0", "scsi_target_num": 0})["result"] is True

@@ -307,6 +307,16 @@ def test_cuda_vhost_user_io_matches_reference(slaves, mode):
     # the READ on queue 3 went to the hot-plugged target (a fresh Malloc bdev: zeros)
     data_off = META_END - 4 * 8192
     assert (so["end"][data_off:data_off + 4096] == 0).all()
+    # get_bdevs_iostat: what each bdev served, counted the way the bdev layer counts (the sessions are gone by
+    # now: the counters outlive them)
+    import json
+    import re
+    time.sleep(0.5)
+    a = json.loads(re.sub(rb'"(tick_rate|\w+_latency_ticks)":\d+', rb'"\1":0', ours.call("get_bdevs_iostat")))["result"]
+    b = json.loads(re.sub(rb'"(tick_rate|\w+_latency_ticks)":\d+', rb'"\1":0', ref.call("get_bdevs_iostat")))["result"]
+    assert a == b, f"iostat differs:\nours {a}\nref  {b}"
+    m0 = [x for x in a if x.get("name") == "M0"][0]
+    assert m0["num_read_ops"] > 0 and m0["num_write_ops"] > 0 and [x for x in a if x.get("name") == "M1"][0]["num_read_ops"] == 1
 
 
 class Vm:
