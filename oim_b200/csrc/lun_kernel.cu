@@ -856,6 +856,13 @@ __device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc
 #define OIM_IDLE_NS 500
 #endif
 
+/* hazard signature: which bit a 4 KiB granule of device address space maps to */
+__device__ __forceinline__ uint32_t sig_index(uint64_t granule)
+{
+	return (uint32_t)(((uint32_t)granule ^ (uint32_t)(granule >> 20)) * 0x9E3779B1u) >> (32 - 12);
+}
+static_assert(kSigBits == 1 << 12, "sig_index produces 12 bits");
+
 /* ---- the kernel ----------------------------------------------------------------------------- */
 
 /* parser side: publish the completions of the fill that occupied `st` (all movers are done with it) */
@@ -987,10 +994,9 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		 * in lock-step, one may already work on pass p+2 while another is still in pass p (the stage ring
 		 * only stops the parser from refilling pass p's stage) */
 		constexpr int kHist = kStages - 1;
-		uint64_t prev_lo[kHist], prev_hi[kHist];
-		uint32_t prev_haz[kHist];
-#pragma unroll
-		for (int h = 0; h < kHist; h++) { prev_lo[h] = prev_hi[h] = 0; prev_haz[h] = 0; }
+		uint32_t pass_no = 0;			/* passes parsed by this CTA: index into the hazard history ring */
+		if (lane < kStages) { sh.hist[lane].writers = 0; sh.hist[lane].touching = 0; }
+		__syncwarp();
 		uint32_t st_rd = 0, st_wr = 0, st_um = 0, st_er = 0;
 		unsigned long long st_rb = 0, st_wb = 0, st_ub = 0;
 		bool first = true;
@@ -1151,14 +1157,102 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				const uint32_t haz = active ? s.hazard : 0;
 				const uint64_t lo = s.store_lo, hi = s.store_hi;
 
-				/* hazards inside the pass -> waves.  Writers are visited in ring order; a writer is
-				 * pushed behind every earlier request it overlaps, every later overlapping request
-				 * behind the writer. */
-				uint16_t wave = 0;
-				uint32_t nwaves = 1;
+				/* hazards against the passes whose movers may still be running (the stage ring only stops
+				 * the parser from refilling a stage; a mover may be two fills behind).  The segments of a
+				 * request that conflicts with one of them are flagged; a mover that reaches a flagged unit
+				 * first waits until the conflicting fill is finished, everything else in the pass proceeds
+				 * at once.  (Waiting for fill c-d's `empty` barrier covers all older ones too: a mover
+				 * arrives there only after finishing its share of every earlier fill.) */
+				uint32_t drain = 0;	/* 0 = none, d = fill c-d must be finished before flagged units move */
+				bool cross = false;	/* this lane's request is one of the conflicting ones */
 				const uint32_t writers = __ballot_sync(0xffffffffu, haz >= 2);
 				const uint32_t touching = __ballot_sync(0xffffffffu, haz != 0);
-				if (writers && (touching & (touching - 1))) {
+				/* This pass's ranges and signatures go into a small ring in shared memory */
+				HazPass &cur = sh.hist[pass_no % kStages];
+				/* a read-only stream never needs signatures: while neither this pass nor the ones it could
+				 * be compared with contain a writer, the pass is left unsigned (= "dense": whoever meets
+				 * it later falls back to the exact ranges) */
+				bool sign = writers != 0;
+#pragma unroll
+				for (int h = 1; h <= kHist; h++) {
+					if ((uint32_t)h <= pass_no) sign |= sh.hist[(pass_no - h) % kStages].writers != 0;
+				}
+				if (sign) {
+					for (int k = lane; k < kSigWords; k += 32) { cur.sig_r[k] = 0; cur.sig_w[k] = 0; }
+				}
+				cur.lo[lane] = lo;
+				cur.hi[lane] = hi;
+				cur.haz[lane] = (uint8_t)haz;
+				if (lane == 0) { cur.writers = writers; cur.touching = touching; cur.dense = sign ? 0 : 1; }
+				__syncwarp();
+				const uint64_t g0 = lo >> 12, g1 = haz ? (hi - 1) >> 12 : g0;
+				const bool mydense = haz == 3 || (haz && g1 - g0 >= (uint64_t)kSigMaxGranules);
+				bool wcollide = false;	/* a writer found one of its granules already written in this pass */
+				if (!sign) { /* nothing to publish */ }
+				else if (mydense) cur.dense = 1;
+				else if (haz) {
+					for (uint64_t g = g0; g <= g1; g++) {
+						const uint32_t idx = sig_index(g);
+						if (haz >= 2) wcollide |= (atomicOr(&cur.sig_w[idx >> 5], 1u << (idx & 31)) >> (idx & 31)) & 1u;
+						else atomicOr(&cur.sig_r[idx >> 5], 1u << (idx & 31));
+					}
+				}
+				__syncwarp();
+				/* against the kStages-1 passes before this one: signature first, exact ranges only for the
+				 * requests the signature cannot clear */
+#pragma unroll
+				for (int h = kHist; h >= 1; h--) {
+					if ((uint32_t)h > pass_no) continue;
+					const HazPass &pp = sh.hist[(pass_no - h) % kStages];
+					const uint32_t candidates = haz >= 2 ? pp.touching : haz ? pp.writers : 0u;
+					bool maybe = false;
+					if (candidates) {
+						if (mydense || pp.dense) maybe = true;
+						else {
+							for (uint64_t g = g0; g <= g1; g++) {
+								const uint32_t idx = sig_index(g);
+								uint32_t word = pp.sig_w[idx >> 5];
+								if (haz >= 2) word |= pp.sig_r[idx >> 5];
+								maybe |= (word >> (idx & 31)) & 1u;
+							}
+						}
+					}
+					bool hit = false;
+					if (maybe) {
+						uint32_t scan = candidates;
+						while (scan) {
+							const int j = __ffs(scan) - 1;
+							scan &= scan - 1;
+							if (haz == 3 || pp.haz[j] == 3 || (lo < pp.hi[j] && pp.lo[j] < hi)) hit = true;
+						}
+					}
+					cross |= hit;
+					if (__any_sync(0xffffffffu, hit)) drain = (uint32_t)h;	/* nearest pass wins */
+				}
+				pass_no++;
+
+				/* hazards inside the pass -> waves.  Writers are visited in ring order; a writer is
+				 * pushed behind every earlier request it overlaps, every later overlapping request
+				 * behind the writer.  Most passes have no overlap at all: the signatures say so. */
+				uint16_t wave = 0;
+				uint32_t nwaves = 1;
+				bool inpass = false;
+				if (writers && (touching & (touching - 1)) && haz) {
+					if (mydense || cur.dense) inpass = true;
+					else if (haz >= 2) {
+						inpass = wcollide;
+						for (uint64_t g = g0; g <= g1; g++) {
+							const uint32_t idx = sig_index(g);
+							inpass |= (cur.sig_r[idx >> 5] >> (idx & 31)) & 1u;
+						}
+					} else {
+						for (uint64_t g = g0; g <= g1; g++) {
+							const uint32_t idx = sig_index(g);
+							inpass |= (cur.sig_w[idx >> 5] >> (idx & 31)) & 1u;
+						}
+					}
+				}
+				if (__any_sync(0xffffffffu, inpass)) {
 					uint32_t w = writers;
 					while (w) {
 						const int j = __ffs(w) - 1;
@@ -1175,34 +1269,6 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						if (overlap && lane > j && jw + 1 > wave) wave = (uint16_t)(jw + 1);
 					}
 					nwaves = __reduce_max_sync(0xffffffffu, (uint32_t)wave) + 1;
-				}
-				/* hazards against the passes whose movers may still be running.  Waiting for the previous
-				 * fill's `empty` barrier covers all of them: a mover arrives there only after it has
-				 * finished its share of every earlier fill. */
-				uint32_t drain = 0;	/* 0 = none, d = wait until the movers have left fill c-d */
-				{
-#pragma unroll
-					for (int h = kHist - 1; h >= 0; h--) {
-						bool hit = false;
-						const uint32_t pw = __ballot_sync(0xffffffffu, prev_haz[h] >= 2);
-						const uint32_t pt = __ballot_sync(0xffffffffu, prev_haz[h] != 0);
-						uint32_t scan = writers ? pt : pw;	/* only pairs with a writer on one side matter */
-						if (touching) {
-							while (scan) {
-								const int j = __ffs(scan) - 1;
-								scan &= scan - 1;
-								const uint64_t jlo = __shfl_sync(0xffffffffu, prev_lo[h], j);
-								const uint64_t jhi = __shfl_sync(0xffffffffu, prev_hi[h], j);
-								const uint32_t jhaz = __shfl_sync(0xffffffffu, prev_haz[h], j);
-								if (haz != 0 && (jhaz >= 2 || haz >= 2) &&
-								    (jhaz == 3 || haz == 3 || (lo < jhi && jlo < hi))) hit = true;
-							}
-						}
-						if (__any_sync(0xffffffffu, hit)) drain = (uint32_t)h + 1;	/* nearest pass wins */
-					}
-#pragma unroll
-					for (int h = kHist - 1; h > 0; h--) { prev_lo[h] = prev_lo[h - 1]; prev_hi[h] = prev_hi[h - 1]; prev_haz[h] = prev_haz[h - 1]; }
-					prev_lo[0] = lo; prev_hi[0] = hi; prev_haz[0] = haz;
 				}
 
 				/* counters for get_bdevs_iostat */
@@ -1258,7 +1324,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						__syncwarp();
 					}
 					if (mine) {
-						if (segs) emit_segments(L, q, sh.req[lane], s, &st.seg[seg_incl - segs], unit_incl - units, wave);
+						if (segs) emit_segments(L, q, sh.req[lane], s, &st.seg[seg_incl - segs], unit_incl - units,
+									(uint16_t)(wave | (cross ? kSegWaitsForDrain : 0)));
 						build_cpl(sh.req[lane], s, &st.cpl[lane - r0]);
 						if (q.mode == QMODE_VRING) {
 							st.resp[lane - r0] = my_resp;
@@ -1271,7 +1338,13 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						st.nseg = tot_seg;
 						st.nunits = tot_unit;
 						st.nwaves = nwaves;
+						/* later fills of a split pass simply wait for the fill before them, up front */
 						st.drain = (r0 > 0) ? 1 : drain;
+#ifdef OIM_DRAIN_UPFRONT	/* tuning builds: stall the whole fill, as before the per-unit flag existed */
+						st.drain_upfront = 1;
+#else
+						st.drain_upfront = r0 > 0;
+#endif
 						st.stop = 0;
 						st.ncpl = r1 - r0;
 						st.cpl_ring = q.cpls;
@@ -1340,11 +1413,15 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			mbar_wait(&sh.full[sidx], (c / kStages) & 1);
 			if (st.stop) break;
 			const uint32_t nseg = st.nseg, nunits = st.nunits, nw = st.nwaves;
-			if (st.drain && c >= st.drain) {
-				/* RAW/WAW/WAR against fill c-drain: wait until every mover has left it (a mover
-				 * arrives on `empty` only after finishing its share of all earlier fills too) */
-				const uint32_t p = c - st.drain;
+			/* RAW/WAW/WAR against fill c-drain: before touching a flagged unit, wait until every mover has
+			 * left that fill (a mover arrives on `empty` only after finishing its share of all earlier
+			 * fills too) */
+			const uint32_t drain = st.drain;
+			bool drained = !(drain && c >= drain);
+			if (!drained && st.drain_upfront) {
+				const uint32_t p = c - drain;
 				mbar_wait(&sh.empty[p % kStages], (p / kStages) & 1);
+				drained = true;
 			}
 			for (uint32_t w = 0; w < nw; w++) {
 				for (uint32_t u = mw; u < nunits; u += kMovers) {
@@ -1354,7 +1431,12 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						if (st.seg[mid].first_unit <= u) lo = mid; else hi = mid;
 					}
 					const Segment &g = st.seg[lo];
-					if (nw > 1 && g.wave != w) continue;
+					if (nw > 1 && (g.wave & kSegWaveMask) != w) continue;
+					if ((g.wave & kSegWaitsForDrain) && !drained) {
+						const uint32_t p = c - drain;
+						mbar_wait(&sh.empty[p % kStages], (p / kStages) & 1);
+						drained = true;
+					}
 					const uint64_t off = (uint64_t)(u - g.first_unit) * kUnitBytes;
 					const uint32_t nbytes = (uint32_t)min((uint64_t)kUnitBytes, g.len - off);
 					const uint8_t *src = g.src;

@@ -140,6 +140,8 @@ struct QueueDesc {
 };
 
 /* one contiguous piece of payload to move (or to zero when src == nullptr) */
+enum : uint16_t { kSegWaveMask = 0x7fff, kSegWaitsForDrain = 0x8000 };	/* Segment::wave */
+
 struct Segment {
 	const uint8_t *src;
 	uint8_t *dst;
@@ -185,12 +187,29 @@ struct __align__(16) Stage {
 	volatile uint32_t *done;	/* persistent slot ring: completion counter in host memory */
 	uint32_t vq_size, used_base, mode;
 	uint32_t nseg, nunits, nwaves;
-	uint32_t drain;			/* conflicts with the previous fill: wait for it to finish */
+	uint32_t drain;			/* d != 0: fill c-d must be finished before flagged units of this one move */
+	uint32_t drain_upfront;		/* ... before anything of this one moves (later fills of a split pass) */
 	uint32_t stop;
+};
+
+/* Store ranges of one pass, for hazard detection against the passes after it (parser-private).
+ * Exact ranges per request plus two signatures - hashed bitmaps over 4 KiB granules of device address
+ * space, one for the granules read, one for the granules written.  A request can only conflict with
+ * the pass if one of its granules is set in the signature that matters for it, so the common case (no
+ * conflict) costs a handful of shared-memory loads per request instead of a 32-entry range scan. */
+constexpr int kSigBits = 4096, kSigWords = kSigBits / 32, kSigMaxGranules = 32;
+
+struct __align__(16) HazPass {
+	uint64_t lo[kPass], hi[kPass];
+	uint8_t  haz[kPass];		/* LaneState::hazard of each request */
+	uint32_t writers, touching;	/* lane masks: haz >= 2, haz != 0 */
+	uint32_t dense;			/* a request too large (or a barrier) for the signatures: always scan */
+	uint32_t sig_r[kSigWords], sig_w[kSigWords];
 };
 
 struct __align__(16) CtaShared {
 	Stage stage[kStages];
+	HazPass hist[kStages];		/* ring: the pass being parsed + the kStages-1 before it */
 	oimgpu_req req[kPass];		/* parser-private: the pass being parsed */
 	LaneState lane[kPass];
 	uint64_t full[kStages];		/* mbarriers */

@@ -169,9 +169,13 @@ def run_script(s: Slave, rq, *, data: bool, seed=5):
     m = vu.Master(s.sock("scsi0"))
     try:
         handshake(m, ram, img, queues)
-        time.sleep(0.3)                                  # the reference starts the session asynchronously
-        for q in queues:
-            assert q.drain_calls() >= 1, "every queue gets a spurious interrupt at start (vhost.c:1101-1115)"
+        # both slaves start the session asynchronously (ours pins the guest memory first)
+        deadline, pending = time.time() + 10, list(queues)
+        while pending and time.time() < deadline:
+            pending = [q for q in pending if q.drain_calls() < 1]
+            time.sleep(0.02)
+        assert not pending, "every queue gets a spurious interrupt at start (vhost.c:1101-1115)"
+        time.sleep(0.2)
         # ---- control queue
         publish(ram, cq, control_requests(ram, img, cq))
         queues[0].notify()
