@@ -63,6 +63,38 @@ def test_cuda_hazards_same_lba_chain(gpu, oracles):
     assert (got[1] == want[1]).all() and (got[2] == want[2]).all()
 
 
+@pytest.mark.parametrize("shape", ["hot4k", "sub_granule", "mixed_sizes"])
+def test_cuda_hazard_signatures(gpu, oracles, shape):
+    """the signature filter in front of the exact range check (lun_kernel.cu): conflicts in nearly every pass
+    (hot4k), requests that share a 4 KiB granule without overlapping and with overlapping (sub_granule),
+    and requests from one block to more than the signature's granule limit (mixed_sizes)"""
+    nb = 1 << 15
+    rng = np.random.default_rng({"hot4k": 1, "sub_granule": 2, "mixed_sizes": 3}[shape])
+    b = abi.Batch(0)
+    off = 4096
+    for i in range(1500):
+        if shape == "hot4k":
+            lba, n = int(rng.integers(0, 48)) * 8, 8                      # 48 hot slots
+        elif shape == "sub_granule":
+            lba, n = int(rng.integers(0, 256)), int(rng.integers(1, 5))  # 512 B .. 2 KiB inside a few granules
+        else:
+            n = int(rng.choice([1, 8, 64, 256, 300, 1024]))
+            lba = int(rng.integers(0, 2048 - n))
+        if rng.random() < 0.45:
+            b.write(lba, n, [(off, n * 512)])
+        else:
+            b.read(lba, n, [(off, n * 512)])
+        off += n * 512
+    reqs, iovs = b.arrays()
+    t = traces.Trace(reqs, iovs, off + 4096, shape)
+    want = util.run_oracle(oracles.PortOracle, t, nb)
+    for _ in range(2):
+        got = util.run_cuda(gpu, t, nb)
+        util.assert_cpls_equal(got[0], want[0], t.reqs)
+        assert (got[1] == want[1]).all(), f"client memory differs at {np.nonzero(got[1] != want[1])[0][:8]}"
+        assert (got[2] == want[2]).all(), f"store differs at {np.nonzero(got[2] != want[2])[0][:8]}"
+
+
 def test_cuda_hazards_two_passes_apart(gpu, oracles):
     """movers are not in lock-step: while one is still busy with a 4 MiB write of pass p, the others run
     through pass p+1 (unrelated small reads) and reach pass p+2, which reads what pass p writes"""
