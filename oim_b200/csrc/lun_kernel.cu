@@ -905,7 +905,11 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 		ue[0] = st.vq_head[lane];
 		ue[1] = c.used_len;
 	}
-	__threadfence_system();		/* "Ensure the used ring is updated before we ... increment used->idx" */
+	/* "Ensure the used ring is updated before we ... increment used->idx" (vhost.c:416-417).  Guest memory in
+	 * host RAM needs that at system scope (the guest's CPUs are watching); when the guest image lives in HBM
+	 * the observers are on this GPU and the cheaper scope does */
+	if (st.vq_in_hbm) __threadfence();
+	else __threadfence_system();
 	__syncwarp();
 	if (lane == 0 && n) {
 		const uint32_t idx = st.used_base + n;
@@ -1354,6 +1358,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						st.vq_used = q.vq_used;
 						st.vq_state = q.vq_state;
 						st.vq_size = q.vq_size;
+						st.vq_in_hbm = q.vq_in_hbm;
 						st.used_base = vq_last_used + done + r0;
 						st.done = persistent ? q.done : nullptr;
 					}

@@ -137,6 +137,9 @@ struct QueueDesc {
 	const uint8_t *vq_avail;	/* struct vring_avail */
 	uint8_t       *vq_used;		/* struct vring_used */
 	VqState       *vq_state;
+	uint32_t vq_in_hbm;		/* the ring and the response buffers are device memory: ordering the used
+					 * index behind them needs a GPU-scope fence only (host memory: system scope) */
+	uint32_t pad;
 };
 
 /* one contiguous piece of payload to move (or to zero when src == nullptr) */
@@ -185,7 +188,7 @@ struct __align__(16) Stage {
 	uint8_t  *vq_used;
 	VqState  *vq_state;
 	volatile uint32_t *done;	/* persistent slot ring: completion counter in host memory */
-	uint32_t vq_size, used_base, mode;
+	uint32_t vq_size, used_base, mode, vq_in_hbm;
 	uint32_t nseg, nunits, nwaves;
 	uint32_t drain;			/* d != 0: fill c-d must be finished before flagged units of this one move */
 	uint32_t drain_upfront;		/* ... before anything of this one moves (later fills of a split pass) */

@@ -123,6 +123,7 @@ struct Queue {
 	uint8_t *vq_used = nullptr;
 	uint32_t vq_size = 0;
 	bool vq_pending = false;
+	bool vq_in_hbm = false;		/* the used ring is device memory (a guest image in HBM), not pinned host memory */
 };
 
 }  // namespace
@@ -1178,6 +1179,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 			D.vq_desc = Q.vq_desc;
 			D.vq_avail = Q.vq_avail;
 			D.vq_used = Q.vq_used;
+			D.vq_in_hbm = Q.vq_in_hbm ? 1 : 0;
 			D.vq_state = L->d_vq_state + q;
 			Q.vq_pending = false;
 		}
@@ -1528,6 +1530,9 @@ extern "C" int oimgpu_vq_attach(oimgpu_lun *L, uint32_t q, const void *desc, con
 	Q.vq_used = (uint8_t *)used;
 	Q.vq_size = size;
 	Q.vq_pending = false;
+	cudaPointerAttributes attr{};
+	Q.vq_in_hbm = cudaPointerGetAttributes(&attr, used) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+	(void)cudaGetLastError();
 	return 0;
 }
 
@@ -1600,6 +1605,7 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 			D.vq_desc = Q.vq_desc;
 			D.vq_avail = Q.vq_avail;
 			D.vq_used = Q.vq_used;
+			D.vq_in_hbm = Q.vq_in_hbm ? 1 : 0;
 			D.vq_state = L->d_vq_state + q;
 		} else {
 			QueueDesc &D = h_desc[nd++];
