@@ -57,7 +57,7 @@ def build_daemon(force: bool = False) -> str:
     if not force and os.path.exists(DAEMON) and os.path.getmtime(DAEMON) >= max(
             *[os.path.getmtime(d) for d in DAEMON_DEPS], os.path.getmtime(LIB), os.path.getmtime(os.path.join(ROOT, "include", "oimgpu.h"))):
         return DAEMON
-    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", DAEMON, *DAEMON_SRCS,
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-rdynamic", "-g", "-I", os.path.join(ROOT, "include"), "-o", DAEMON, *DAEMON_SRCS,
            "-L", HERE, "-loimgpu", "-Wl,-rpath,$ORIGIN"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:

@@ -338,9 +338,10 @@ struct ParkedSession { oimgpu_lun *L; bool restart; };
 
 static std::vector<ParkedSession> park_pollers_locked(int device, oimgpu_lun *except = nullptr)
 {
+	/* device < 0: every GPU (pinned host memory is mapped into all of them) */
 	std::vector<ParkedSession> parked;
 	for (oimgpu_lun *L : g.handles) {
-		if (L == except || L->device != device) continue;
+		if (L == except || (device >= 0 && L->device != device)) continue;
 		L->mu.lock();
 		const bool was = L->poller_active;
 		if (was) oimgpu_lun_stop_poller(L);
@@ -1079,7 +1080,12 @@ extern "C" int oimgpu_mem_unregister(void *addr)
 	std::lock_guard<std::mutex> lk(g.mu);
 	auto it = g.registered.find(addr);
 	if (it == g.registered.end()) return -ENOENT;
+	/* cuMemHostUnregister waits for the GPUs to go idle while holding a driver lock that every launch
+	 * needs: with a resident poller anywhere that is a deadlock, not a delay (seen: one VM's teardown
+	 * against another VM's poller restart).  Same remedy as for cudaFree. */
+	auto parked = park_pollers_locked(-1);
 	cudaHostUnregister(addr);
+	unpark_pollers_locked(parked);
 	g.registered.erase(it);
 	return 0;
 }
@@ -1307,6 +1313,10 @@ extern "C" int oimgpu_submit_batch(oimgpu_lun *L, uint32_t nq, uint32_t per_q, c
 	const size_t n = (size_t)nq * per_q;
 	if (n > L->bs_cap_reqs || niovs > L->bs_cap_iovs) {
 		CU_OK(cudaStreamSynchronize(L->stream));
+		/* growing the staging arrays frees the old ones: see park_pollers_locked */
+		std::lock_guard<std::mutex> lk(g.mu);
+		auto parked = park_pollers_locked(L->device, L);
+		struct Unpark { std::vector<ParkedSession> &p; ~Unpark() { unpark_pollers_locked(p); } } unpark{parked};
 		if (n > L->bs_cap_reqs) {
 			cudaFree(L->bs_d_reqs); cudaFree(L->bs_d_cpls);
 			CU_OK(cudaMalloc((void **)&L->bs_d_reqs, n * sizeof(oimgpu_req)));

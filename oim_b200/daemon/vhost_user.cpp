@@ -21,8 +21,11 @@
 #include <thread>
 #include <vector>
 
+#include <execinfo.h>
 #include <fcntl.h>
 #include <poll.h>
+#include <pthread.h>
+#include <signal.h>
 #include <sys/eventfd.h>
 #include <sys/mman.h>
 #include <sys/socket.h>
@@ -88,6 +91,39 @@ Config g_cfg;
 std::mutex g_mu;
 const bool g_debug = getenv("OIM_VU_DEBUG") != nullptr;
 #define VU_DEBUG(...) do { if (g_debug) { fprintf(stderr, "vhost-user: " __VA_ARGS__); fputc('\n', stderr); } } while (0)
+
+/* diagnostics: `kill -USR2 <pid>` makes every transport thread print where it is (stderr) */
+std::mutex g_threads_mu;
+std::vector<pthread_t> g_threads;
+
+void on_usr1(int)
+{
+	void *bt[40];
+	const int n = backtrace(bt, 40);
+	backtrace_symbols_fd(bt, n, 2);
+	const char nl[] = "----\n";
+	(void)!write(2, nl, sizeof(nl) - 1);
+}
+
+void on_usr2(int)
+{
+	std::lock_guard<std::mutex> lk(g_threads_mu);
+	for (pthread_t t : g_threads) pthread_kill(t, SIGUSR1);
+}
+
+void register_thread()
+{
+	std::lock_guard<std::mutex> lk(g_threads_mu);
+	g_threads.push_back(pthread_self());
+}
+
+void unregister_thread()
+{
+	std::lock_guard<std::mutex> lk(g_threads_mu);
+	for (size_t i = 0; i < g_threads.size(); i++) {
+		if (pthread_equal(g_threads[i], pthread_self())) { g_threads.erase(g_threads.begin() + i); break; }
+	}
+}
 
 struct Server;
 
@@ -503,6 +539,7 @@ bool Session::start()
 			}
 			lun_queues = want;
 		}
+		VU_DEBUG("%s: session %d: data path open", srv->name.c_str(), fd);
 		std::vector<oimgpu_mem_region> tbl;
 		for (const Region &r : mem) tbl.push_back({r.gpa, r.size, r.dev});
 		int mrc = oimgpu_lun_set_mem_table(lun, tbl.data(), (uint32_t)tbl.size());
@@ -522,6 +559,7 @@ bool Session::start()
 			}
 			q.attached = true;
 		}
+		VU_DEBUG("%s: session %d: rings attached", srv->name.c_str(), fd);
 		if (g_cfg.poller) {
 			int rc = oimgpu_lun_start_poller(lun, 0, 0);
 			polling = rc >= 0;
@@ -538,6 +576,7 @@ bool Session::start()
 void Session::stop()
 {
 	if (!running) return;
+	VU_DEBUG("%s: session %d: stopping", srv->name.c_str(), fd);
 	if (lun) {
 		if (polling) { oimgpu_lun_stop_poller(lun); polling = false; }
 		oimgpu_lun_sync(lun);
@@ -771,9 +810,12 @@ bool Session::handle_message()
 
 void Session::teardown()
 {
+	VU_DEBUG("%s: session %d: teardown", srv->name.c_str(), fd);
 	stop();
 	if (lun) { oimgpu_lun_close(lun); lun = nullptr; }
+	VU_DEBUG("%s: session %d: data path closed", srv->name.c_str(), fd);
 	free_mem();
+	VU_DEBUG("%s: session %d: guest memory released", srv->name.c_str(), fd);
 	for (uint32_t i = 0; i < kMaxRegions; i++) if (has_new_table && new_fds[i] >= 0) close(new_fds[i]);
 	for (Vq &q : vq) { if (q.kickfd >= 0) close(q.kickfd); if (q.callfd >= 0) close(q.callfd); }
 	vq.clear();
@@ -783,6 +825,7 @@ void Session::teardown()
 
 void Session::run()
 {
+	register_thread();
 	for (int &f : new_fds) f = -1;
 	while (!srv->stop.load()) {
 		std::vector<pollfd> pf;
@@ -808,6 +851,7 @@ void Session::run()
 		if (polling && n == 0) usleep(20);
 	}
 	teardown();
+	unregister_thread();
 	done.store(true);
 }
 
@@ -864,7 +908,12 @@ static void stop_server(Server &s)
 
 }  // namespace
 
-void configure(const Config &cfg) { g_cfg = cfg; }
+void configure(const Config &cfg)
+{
+	g_cfg = cfg;
+	signal(SIGUSR1, on_usr1);
+	signal(SIGUSR2, on_usr2);
+}
 
 /* rte_vhost_driver_register + rte_vhost_driver_start (socket.c): the controller's listening socket */
 int listen_ctrlr(const std::string &name, const std::string &path)

@@ -28,6 +28,7 @@ class Slave:
     """one server process (ours or the reference) + its RPC client"""
 
     def __init__(self, kind: str, tmp, extra=()):
+        self.kind = kind
         self.dir = tmp / kind
         (self.dir / "vhost").mkdir(parents=True)
         self.rpc = str(self.dir / "rpc.sock")
@@ -51,6 +52,10 @@ class Slave:
         return str(self.dir / "vhost" / ctrlr)
 
     def close(self):
+        if self.kind != "ref" and self.p.poll() is None:
+            import signal
+            self.p.send_signal(signal.SIGUSR2)             # every transport thread reports where it is
+            time.sleep(0.3)
         self.p.terminate()
         try:
             self.p.wait(5)
@@ -246,6 +251,8 @@ def slaves(oracles, tmp_path):
     yield make
     for s in made:
         s.close()
+        print(f"---- {s.dir.name} server log (tail) ----")           # shown by pytest when the test failed
+        print(open(s.dir / "log.txt", errors="replace").read()[-3000:])
 
 
 def test_vhost_user_handshake_control_and_event_queues(slaves):
