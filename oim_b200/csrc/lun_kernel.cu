@@ -761,7 +761,7 @@ __device__ __forceinline__ int desc_get_next(VDesc &d, bool &have, const uint8_t
 
 /* spdk_vhost_vring_desc_to_iov (vhost.c:461-509): append the iovecs of one descriptor to the lane's
  * scratch SG row; split only where two sides of a 2 MiB boundary are not contiguous in device VA */
-__device__ __forceinline__ int desc_to_iov(const LunCtx &L, oimgpu_iov *row, uint32_t &iov_index, const VDesc &d)
+__device__ __forceinline__ int desc_to_iov(const LunCtx &L, oimgpu_iov *row, oimgpu_iov *srow, uint32_t &iov_index, const VDesc &d)
 {
 	const uint64_t MB2 = 2ull << 20;
 	uint32_t remaining = d.len;
@@ -784,6 +784,7 @@ __device__ __forceinline__ int desc_to_iov(const LunCtx &L, oimgpu_iov *row, uin
 		oimgpu_iov v;
 		v.addr = vva; v.len = len; v.flags = 0;
 		row[iov_index] = v;
+		if (iov_index < (uint32_t)kSmemIovs) srow[iov_index] = v;	/* short lists are read back from shared memory */
 		remaining -= len;
 		payload += len;
 		iov_index++;
@@ -795,7 +796,7 @@ __device__ __forceinline__ int desc_to_iov(const LunCtx &L, oimgpu_iov *row, uin
  * request slot `r` (virtio header + direction + SG row reference) and *resp (device address of the
  * guest's response buffer).  Returns false for every `goto invalid_task`. */
 __device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc &q, uint32_t head, VDesc d, oimgpu_req &r,
-						oimgpu_iov *row, uint32_t row_index, uint64_t *resp)
+						oimgpu_iov *row, oimgpu_iov *srow, uint32_t row_index, uint64_t *resp)
 {
 	*resp = 0;
 	/* spdk_vhost_vq_get_desc (vhost.c:219-247); `d` = desc[head], loaded one pass ahead by the caller */
@@ -831,13 +832,13 @@ __device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc
 		if (desc_get_next(d, have, table, table_size) != 0) return false;
 		while (have) {
 			if (!(d.flags & VD_WRITE)) return false;
-			if (desc_to_iov(L, row, iovcnt, d)) return false;
+			if (desc_to_iov(L, row, srow, iovcnt, d)) return false;
 			if (desc_get_next(d, have, table, table_size) != 0) return false;
 		}
 	} else {
 		/* TO_DEV: [RD_req][RD_buf0]...[RD_bufN][WR_resp] */
 		while (!(d.flags & VD_WRITE)) {
-			if (desc_to_iov(L, row, iovcnt, d)) return false;
+			if (desc_to_iov(L, row, srow, iovcnt, d)) return false;
 			desc_get_next(d, have, table, table_size);
 			if (!have) return false;	/* no response descriptor */
 		}
@@ -1078,6 +1079,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				q.iov_mask = 0xffffffffu;
 				q.iovs += (size_t)blockIdx.x * kPass * kIovRow;	/* this CTA's scratch SG rows */
 			}
+			const oimgpu_iov *const iov_base = q.iovs;
 			if (persistent) {
 				if (q.count == 0) continue;
 				progress = true;
@@ -1143,8 +1145,16 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					my_head = vq_head_cur;
 					VDesc d0 = {0, 0, 0, 0};
 					if (my_head < q.vq_size) d0 = vq_tbl_aligned ? decode_desc(vq_raw) : load_desc(q.vq_desc + (size_t)my_head * 16);
-					chain_ok = vq_task_data_setup(L, q, my_head, d0, sh.req[lane], const_cast<oimgpu_iov *>(q.iovs) + (size_t)lane * kIovRow,
-								      lane * kIovRow, &my_resp);
+					chain_ok = vq_task_data_setup(L, q, my_head, d0, sh.req[lane], const_cast<oimgpu_iov *>(iov_base) + (size_t)lane * kIovRow,
+								      sh.sg[lane], lane * kIovRow, &my_resp);
+					/* from here on this lane's `q.iovs` is its own SG list: on chip when it is short (the
+					 * usual case: one data buffer), else its row of the scratch table in HBM */
+					if (chain_ok && sh.req[lane].iovcnt <= kSmemIovs) {
+						q.iovs = sh.sg[lane];
+						sh.req[lane].iov_start = 0;
+					} else {
+						q.iovs = iov_base;
+					}
 				}
 				/* next pass's head descriptors: issued now, consumed after the hazard analysis, the
 				 * reap and the segment emission of this pass */

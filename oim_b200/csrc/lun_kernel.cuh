@@ -200,6 +200,7 @@ struct __align__(16) Stage {
  * space, one for the granules read, one for the granules written.  A request can only conflict with
  * the pass if one of its granules is set in the signature that matters for it, so the common case (no
  * conflict) costs a handful of shared-memory loads per request instead of a 32-entry range scan. */
+constexpr int kSmemIovs = 4;
 constexpr int kSigBits = 4096, kSigWords = kSigBits / 32, kSigMaxGranules = 32;
 
 struct __align__(16) HazPass {
@@ -214,6 +215,7 @@ struct __align__(16) CtaShared {
 	Stage stage[kStages];
 	HazPass hist[kStages];		/* ring: the pass being parsed + the kStages-1 before it */
 	oimgpu_req req[kPass];		/* parser-private: the pass being parsed */
+	oimgpu_iov sg[kPass][kSmemIovs];	/* virtqueue mode: the SG list of a request with few elements stays on chip */
 	LaneState lane[kPass];
 	uint64_t full[kStages];		/* mbarriers */
 	uint64_t empty[kStages];

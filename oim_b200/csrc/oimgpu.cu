@@ -976,6 +976,9 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	CU_OK(cudaMalloc((void **)&L->d_vq_state, sizeof(VqState) * num_queues));
 	CU_OK(cudaMemsetAsync(L->d_vq_state, 0, sizeof(VqState) * num_queues, L->stream));
 	CU_OK(cudaStreamSynchronize(L->stream));
+	/* more than the 48 KB a kernel gets without asking */
+	CU_OK(cudaFuncSetAttribute(oim_lun_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
+	CU_OK(cudaFuncSetAttribute(oim_lun_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
 	int per_sm = 0;
 	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes()));
 	if (per_sm < 1) per_sm = 1;
