@@ -674,7 +674,7 @@ bool Session::handle_message()
 		break;
 	case SET_FEATURES: {	/* vhost_user_set_features */
 		v = u64_of();
-		if (v & ~kFeatures) { ret = -1; break; }
+		if (v & ~kFeatures) break;	/* refused; the handler drops the status, so even a REPLY_ACK says 0 (vhost_user.c:1337-1339) */
 		if (running && features != v) stop();
 		features = v;
 		break;

@@ -288,7 +288,7 @@ def test_vhost_user_reconnect_and_odd_masters(slaves):
         m.recv()
     m.close()
     m = vu.Master(ours.sock("scsi0"))
-    assert m.set_u64(vu.SET_FEATURES, 1 << 40, need_reply=True) == 1      # unsupported feature bit: refused
+    assert m.set_u64(vu.SET_FEATURES, 1 << 40, need_reply=True) == 0      # unsupported feature bit: ignored, acked 0 like the reference
     assert m.get_u64(vu.GET_FEATURES) == 0x154000007
     m.close()
     # the RPC side is unaffected, and removing the controller removes its socket
@@ -389,3 +389,91 @@ def test_cuda_vhost_user_sessions_come_and_go(slaves, mode):
         assert (got[k] == want[k]).all(), f"VM {k}: guest memory differs at {np.nonzero(got[k] != want[k])[0][:16]}"
     assert got["a_base"] == want["a_base"] and got["c_base"] == want["c_base"]
     assert got["a_base"][2] == 64 - 0 or got["a_base"][2] > 0
+
+
+def fuzz_script(m: vu.Master, ram: vu.GuestRam, rng, nmsg=60):
+    """a random but reference-safe message sequence (queue indices allocated in order, GET_VRING_BASE only on
+    allocated queues: the reference dereferences unallocated rings); everything else is fair game - unsupported
+    feature bits, rings before memory, bad ring addresses, NOFD eventfds, REPLY_ACK on anything"""
+    allocated = 0
+    fds = []
+    regs = [(0x100000000, ram.size, vu.UVA_BASE, 0, ram.fd)]
+
+    def pick_index(may_allocate=True):
+        nonlocal allocated
+        if allocated == 0 or (may_allocate and allocated < 4 and rng.random() < 0.3):
+            allocated += 1
+            return allocated - 1
+        return int(rng.integers(0, allocated))
+
+    for _ in range(nmsg):
+        k = int(rng.integers(0, 16))
+        ack = bool(rng.integers(0, 2))
+        if k == 0:
+            m.get_u64(vu.GET_FEATURES)
+        elif k == 1:
+            m.get_u64(vu.GET_PROTOCOL_FEATURES)
+        elif k == 2:
+            m.get_u64(vu.GET_QUEUE_NUM)
+        elif k == 3:
+            f = int(rng.choice([0x154000007, 0x150000007, 0x100000000, 0x154000007 | 1 << 40, 0]))
+            m.set_u64(vu.SET_FEATURES, f, need_reply=ack)
+        elif k == 4:
+            m.set_u64(vu.SET_PROTOCOL_FEATURES, int(rng.choice([0x9, 0x21f, 0x400, 0])), need_reply=ack)
+        elif k == 5:
+            m.set_mem_table(regs, need_reply=ack)
+        elif k == 6:
+            m.vring_state(vu.SET_VRING_NUM, pick_index(), int(rng.choice([16, 256])))
+        elif k == 7:
+            m.vring_state(vu.SET_VRING_BASE, pick_index(), int(rng.integers(0, 4)))
+        elif k == 8:
+            i = pick_index()
+            base = vu.UVA_BASE + 65536 * i
+            if rng.random() < 0.2:
+                base = 0x1234000                              # not inside any region
+            m.set_vring_addr(i, base, base + 8192, base + 4096)
+        elif k in (9, 10):
+            i = pick_index()
+            req = vu.SET_VRING_KICK if k == 9 else vu.SET_VRING_CALL
+            if rng.random() < 0.25:
+                m.set_u64(req, i | vu.NOFD_MASK, need_reply=ack)
+            else:
+                fd = os.eventfd(0, os.EFD_NONBLOCK)
+                fds.append(fd)
+                m.set_u64(req, i, [fd], need_reply=ack)
+        elif k == 11:
+            m.vring_state(vu.SET_VRING_ENABLE, pick_index(), int(rng.integers(0, 2)))
+        elif k == 12 and allocated:
+            m.get_vring_base(pick_index(may_allocate=False))
+        elif k == 13:
+            m.get_config()
+        elif k == 14:
+            m.send(vu.SET_OWNER)
+            m.log.append((vu.SET_OWNER, None))
+        else:
+            m.set_u64(vu.SET_CONFIG, 0, need_reply=True)
+    for fd in fds:
+        os.close(fd)
+
+
+def test_vhost_user_random_message_sequences(slaves):
+    """differential fuzzing of the protocol state machine: same random sequences, same replies"""
+    ours, ref = slaves("ours", ["--control-only"]), slaves("ref")
+    agree = 0
+    for seed in range(150):
+        logs = []
+        for s in (ours, ref):
+            ram = vu.GuestRam(4 << 20)
+            m = vu.Master(s.sock("scsi0"))
+            try:
+                fuzz_script(m, ram, np.random.default_rng(seed))
+                logs.append(m.log)
+            except (ConnectionError, OSError, TimeoutError) as e:
+                logs.append(("dropped", type(e).__name__, len(m.log)))
+            finally:
+                m.close()
+                ram.close()
+            assert s.p.poll() is None, f"seed {seed}: the {s.kind} server died"
+        assert logs[0] == logs[1], f"seed {seed}: transcripts differ\nours {logs[0]}\nref  {logs[1]}"
+        agree += 1
+    assert agree == 150
