@@ -477,3 +477,75 @@ def test_vhost_user_random_message_sequences(slaves):
         assert logs[0] == logs[1], f"seed {seed}: transcripts differ\nours {logs[0]}\nref  {logs[1]}"
         agree += 1
     assert agree == 150
+
+
+def random_control_requests(ram, img, ring, rng):
+    """8 control-queue requests of random type / subtype / target and random chain shape -> heads"""
+    d = ram.mem[ring[0]:ring[0] + 16 * 16].view(vring.desc_dtype)
+    heads = []
+    for k in range(8):
+        o = ring[3] + 64 * k
+        typ = int(rng.choice([0, 0, 0, 1, 2, 9]))
+        sub = int(rng.integers(0, 8))
+        lun = bytes([int(rng.choice([1, 1, 1, 0])), int(rng.choice([0, 0, 1, 5, 9])), 0, int(rng.choice([0, 0, 1])), 0, 0, 0, 0])
+        ram.mem[o:o + 24] = np.frombuffer(struct.pack("<II8sQ", typ, sub, lun, 0x2000 + k), np.uint8)
+        ram.mem[o + 32:o + 48] = 0xEE
+        shape = int(rng.integers(0, 8))
+        req = (gpa_of(img, o), 24, 0)
+        resp = (gpa_of(img, o + 32), int(rng.choice([1, 5, 5, 4, 0])), vring.F_WRITE)
+        if shape == 0:
+            req = (0x9_0000_0000, 24, 0)                                  # request unmapped
+        elif shape == 1:
+            resp = (0x9_0000_0000, resp[1], vring.F_WRITE)                # response unmapped
+        chain = [req] if shape == 2 else [req, resp]                       # shape 2: no response descriptor
+        s0 = 2 * k
+        if shape == 3:                                                     # INDIRECT table
+            tbl_off = o + 48 - (o + 48) % 16 + 16
+            tbl = ram.mem[tbl_off:tbl_off + 32].view(vring.desc_dtype)
+            for j, (a, ln, fl) in enumerate(chain):
+                last = j + 1 == len(chain)
+                tbl[j] = (a, ln, fl | (0 if last else vring.F_NEXT), 0 if last else j + 1)
+            d[s0] = (gpa_of(img, tbl_off), 16 * len(chain), vring.F_INDIRECT, 0)
+        else:
+            for j, (a, ln, fl) in enumerate(chain):
+                last = j + 1 == len(chain)
+                nxt = 0 if last else s0 + j + 1
+                if shape == 4 and not last:
+                    nxt = 99                                               # next index beyond the table
+                d[s0 + j] = (a, ln, fl | (0 if last else vring.F_NEXT), nxt)
+        heads.append(s0 if shape != 5 else 16 + k)                          # shape 5: head beyond the ring
+    return heads
+
+
+def control_fuzz_script(s: Slave, seed: int):
+    img = vring.build_image([], ring_size=256, seed=1, mutate=False)
+    ram = vu.GuestRam(img.arena.size)
+    ram.mem[:] = img.arena
+    cq, eq = small_ring(0), small_ring(1)
+    for r in (cq, eq):
+        ram.mem[r[0]:r[0] + 8192] = 0
+    queues = [vu.Queue(0, 16, *cq[:3]), vu.Queue(1, 16, *eq[:3]), vu.Queue(2, img.ring_size, img.desc_off, img.avail_off, img.used_off)]
+    m = vu.Master(s.sock("scsi0"))
+    try:
+        handshake(m, ram, img, queues)
+        time.sleep(0.25)
+        publish(ram, cq, random_control_requests(ram, img, cq, np.random.default_rng(seed)))
+        queues[0].notify()
+        wait_used(ram, cq, 8)
+        time.sleep(0.05)
+        snap = ram.mem.copy()
+        return mask(snap, img, (cq, eq)), used_set(snap, cq, 8)
+    finally:
+        m.close()
+        for q in queues:
+            q.close()
+        ram.close()
+
+
+def test_vhost_user_control_queue_fuzz(slaves):
+    ours, ref = slaves("ours", ["--control-only"]), slaves("ref")
+    for seed in range(12):
+        a, ua = control_fuzz_script(ours, seed)
+        b, ub = control_fuzz_script(ref, seed)
+        assert ua == ub, f"seed {seed}: used elements differ\nours {ua}\nref  {ub}"
+        assert (a == b).all(), f"seed {seed}: guest memory differs at {np.nonzero(a != b)[0][:16]}"
