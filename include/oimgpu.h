@@ -194,6 +194,11 @@ int oimgpu_bdev_list(struct oimgpu_bdev_info *out, int max);	/* returns count */
  * whichever sessions and targets; -ENODEV if there is no such bdev.  kernel_launches is 0 here. */
 int oimgpu_bdev_iostat(const char *name, struct oimgpu_iostat *out);
 
+/* NBD export (S/lib/nbd/nbd.c:560-806): serve the kernel's NBD transmission protocol for `bdev_name` on a
+ * connected socket - the end of the socketpair that did NOT go to /dev/nbdX - until the peer disconnects.
+ * Blocking; run it on a thread of its own.  0 = orderly end, -EINVAL = bad request magic, -ENODEV = no bdev. */
+int oimgpu_nbd_serve(const char *bdev_name, int sock_fd);
+
 /* test/digest helpers: raw access to the backing store of replica r (synchronous) */
 int oimgpu_bdev_read_raw(const char *name, int replica, uint64_t offset, void *dst, uint64_t len);
 int oimgpu_bdev_write_raw(const char *name, int replica, uint64_t offset, const void *src, uint64_t len);

@@ -32,6 +32,11 @@
 #include <sys/un.h>
 #include <unistd.h>
 
+#include <linux/nbd.h>
+#include <sys/ioctl.h>
+#include <memory>
+#include <thread>
+
 #include "oimgpu.h"
 #include "vhost_user.h"
 
@@ -300,8 +305,69 @@ static std::string ctrlr_json(const oimgpu_ctrlr_info &c)
 	return s + "]}}";
 }
 
-struct NbdDisk { std::string dev, bdev; };
-static std::vector<NbdDisk> g_nbd;
+/* an exported bdev: /dev/nbdX <- kernel end of a socketpair; our end is served by oimgpu_nbd_serve */
+struct NbdDisk {
+	std::string dev, bdev;
+	int dev_fd = -1, kernel_fd = -1, our_fd = -1;
+	std::thread serve, doit;
+};
+static std::vector<std::unique_ptr<NbdDisk>> g_nbd;
+
+/* spdk_nbd_start + spdk_nbd_enable_kernel + spdk_nbd_start_complete (S/lib/nbd/nbd.c:867-1060): hand one end
+ * of a socketpair to the kernel NBD device, describe the disk, let a thread sit in NBD_DO_IT, serve the other
+ * end.  Returns 0 or -errno; every failure becomes "Invalid parameters" on the wire (nbd_rpc.c:63-70). */
+static int nbd_start(const std::string &bdev, const std::string &dev)
+{
+	oimgpu_bdev_info info;
+	if (oimgpu_bdev_get(bdev.c_str(), &info) != 0) return -EINVAL;
+	auto d = std::make_unique<NbdDisk>();
+	d->dev = dev;
+	d->bdev = bdev;
+	int sp[2];
+	if (socketpair(AF_UNIX, SOCK_STREAM, 0, sp) != 0) return -errno;
+	d->our_fd = sp[0];
+	d->kernel_fd = sp[1];
+	auto fail = [&](int rc) {
+		close(d->our_fd);
+		close(d->kernel_fd);
+		if (d->dev_fd >= 0) close(d->dev_fd);
+		return rc;
+	};
+	d->dev_fd = open(dev.c_str(), O_RDWR);
+	if (d->dev_fd < 0) return fail(-errno);
+	int rc = -1;
+	for (int tries = 0; tries < 1000; tries++) {	/* NBD_BUSY_WAITING_MS: the kernel may still be tearing a previous user down */
+		rc = ioctl(d->dev_fd, NBD_SET_SOCK, d->kernel_fd);
+		if (rc == 0 || errno != EBUSY) break;
+		usleep(1000);
+	}
+	if (rc != 0) return fail(-errno);
+	if (ioctl(d->dev_fd, NBD_SET_BLKSIZE, (unsigned long)info.block_size) != 0 ||
+	    ioctl(d->dev_fd, NBD_SET_SIZE_BLOCKS, (unsigned long)info.num_blocks) != 0 ||
+	    ioctl(d->dev_fd, NBD_SET_FLAGS, (unsigned long)NBD_FLAG_SEND_TRIM) != 0) {
+		rc = -errno;
+		ioctl(d->dev_fd, NBD_CLEAR_SOCK);
+		return fail(rc);
+	}
+	NbdDisk *p = d.get();
+	d->doit = std::thread([p] { ioctl(p->dev_fd, NBD_DO_IT); });	/* blocks in the kernel until our end closes */
+	d->serve = std::thread([p] { oimgpu_nbd_serve(p->bdev.c_str(), p->our_fd); });
+	g_nbd.push_back(std::move(d));
+	return 0;
+}
+
+/* spdk_nbd_stop / _nbd_stop (nbd.c:346-395) */
+static void nbd_stop(NbdDisk &d)
+{
+	shutdown(d.our_fd, SHUT_RDWR);
+	if (d.serve.joinable()) d.serve.join();
+	close(d.our_fd);
+	close(d.kernel_fd);
+	ioctl(d.dev_fd, NBD_CLEAR_QUE);
+	ioctl(d.dev_fd, NBD_CLEAR_SOCK);
+	if (d.doit.joinable()) d.doit.join();
+	close(d.dev_fd);
+}
 static uint64_t g_rbd_default_size = 8ull << 30;
 static bool g_serve_vhost_user = true;
 
@@ -448,8 +514,8 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 		std::string out = "[";
 		bool first = true;
 		for (auto &n : g_nbd) {
-			if (a && n.dev != a->raw) continue;
-			out += std::string(first ? "" : ",") + "{\"nbd_device\":" + jstr(n.dev) + ",\"bdev_name\":" + jstr(n.bdev) + "}";
+			if (a && n->dev != a->raw) continue;
+			out += std::string(first ? "" : ",") + "{\"nbd_device\":" + jstr(n->dev) + ",\"bdev_name\":" + jstr(n->bdev) + "}";
 			first = false;
 		}
 		if (a && first) return bad;
@@ -457,10 +523,18 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 	}
 	if (method == "start_nbd_disk") {
 		if (!decode(params, {{"bdev_name", Json::Str, false, &a}, {"nbd_device", Json::Str, false, &b}})) return bad;
-		return error(id, E_INTERNAL, strerr(ENOTSUP));
+		for (auto &n : g_nbd) if (n->dev == b->raw) return bad;	/* already exported */
+		if (nbd_start(a->raw, b->raw) != 0) return bad;		/* nbd_rpc.c:63-70: whatever went wrong */
+		return result(id, jstr(b->raw));
 	}
 	if (method == "stop_nbd_disk") {
 		if (!decode(params, {{"nbd_device", Json::Str, false, &a}})) return bad;
+		for (size_t i = 0; i < g_nbd.size(); i++) {
+			if (g_nbd[i]->dev != a->raw) continue;
+			nbd_stop(*g_nbd[i]);
+			g_nbd.erase(g_nbd.begin() + i);
+			return result(id, "true");
+		}
 		return bad;	/* no such NBD device */
 	}
 	return error(id, E_METHOD_NOT_FOUND, "Method not found");
@@ -609,6 +683,8 @@ int main(int argc, char **argv)
 		}
 	}
 	for (auto &c : conns) close(c.fd);
+	for (auto &n : g_nbd) nbd_stop(*n);
+	g_nbd.clear();
 	vhost_user::shutdown();
 	close(lfd);
 	unlink(rpc_sock.c_str());

@@ -87,6 +87,7 @@ SYMBOLS = [
     ("oimgpu_submit_batch", _I, [_VP, _U32, _U32, _VP, _VP, _U32, _VP, _I]),
     ("oimgpu_submit_and_wait", _I, [_VP, _U32, _U32, _VP, _VP, _U32, _VP, _I]),
     ("oimgpu_bdev_iostat", _I, [C.c_char_p, C.POINTER(IoStat)]),
+    ("oimgpu_nbd_serve", _I, [C.c_char_p, _I]),
     ("oimgpu_lun_iostat", _I, [_VP, C.POINTER(IoStat)]),
     ("oimgpu_lun_target_iostat", _I, [_VP, _I, C.POINTER(IoStat)]),
     ("oimgpu_lun_stream", _VP, [_VP]),

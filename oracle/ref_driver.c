@@ -627,6 +627,22 @@ static void ref_segv(int sig)
 
 extern uint64_t ut_spdk_get_ticks;
 
+void oimref_enter(void)
+{
+	ref_global_init();
+	spdk_set_thread(g_thread);
+}
+
+/* run the SPDK thread's pollers and messages (what a reactor iteration does) */
+void oimref_thread_poll(int iterations)
+{
+	int i;
+	spdk_set_thread(g_thread);
+	for (i = 0; i < iterations; i++) spdk_thread_poll(g_thread, 0, 0);
+}
+
+const char *oimref_bdev_name(void *h) { return ((struct oimref *)h)->bdev_name; }
+
 int oimref_rpc_start(const char *sock_path, const char *vhost_socket_dir)
 {
 	if (getenv("OIMREF_VERBOSE")) signal(SIGSEGV, ref_segv);

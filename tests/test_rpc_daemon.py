@@ -150,6 +150,14 @@ def test_rpc_transcript_matches_reference_server(servers):
     assert len(both(servers, "get_bdevs_iostat", {"name": "MyVol"})["result"]) == 2
     assert both(servers, "get_bdevs_iostat", {"name": "nope"})["error"]["code"] == -32602
     both(servers, "get_bdevs_iostat", {"nam": "MyVol"})
+    # ---- NBD export of OIM's local mode (nbd_rpc.c): no /dev/nbd* in the build container, so the error paths
+    assert both(servers, "get_nbd_disks")["result"] == []
+    assert both(servers, "start_nbd_disk", {"bdev_name": "MyVol", "nbd_device": "/dev/nbd-does-not-exist"})["error"]["code"] == -32602
+    both(servers, "start_nbd_disk", {"bdev_name": "nope", "nbd_device": "/dev/null"})
+    both(servers, "start_nbd_disk", {"bdev_name": "MyVol", "nbd_device": "/dev/null"})               # opens, but is no NBD device
+    both(servers, "start_nbd_disk", {"bdev_name": "MyVol"})
+    both(servers, "stop_nbd_disk", {"nbd_device": "/dev/nbd0"})
+    both(servers, "get_nbd_disks", {"nbd_device": "/dev/nbd0"})
     # ---- teardown order of UnmapVolume (controller.go:159-212)
     assert both(servers, "remove_vhost_controller", {"ctrlr": "vhost.0"})["error"]["message"] == "Device or resource busy"
     assert both(servers, "remove_vhost_scsi_target", {"ctrlr": "vhost.0", "scsi_target_num": 0})["result"] is True
@@ -260,7 +268,8 @@ def test_daemon_on_gpu_config1(tmp_path):
         assert call("delete_bdev", {"name": "pvc-1234"})["result"] is True        # UnmapVolume deletes non-Malloc bdevs
         assert [x["name"] for x in call("get_bdevs")["result"]] == ["vol-64m"]
         assert call("get_nbd_disks")["result"] == []
-        assert call("start_nbd_disk", {"bdev_name": "vol-64m", "nbd_device": "/dev/nbd0"})["error"]["code"] == -32603
+        # no /dev/nbd0 on this box: whatever goes wrong in spdk_nbd_start is "Invalid parameters" (nbd_rpc.c:63-70)
+        assert call("start_nbd_disk", {"bdev_name": "vol-64m", "nbd_device": "/dev/nbd0"})["error"]["code"] == -32602
     finally:
         proc.terminate()
         proc.wait(10)
