@@ -549,3 +549,52 @@ def test_vhost_user_control_queue_fuzz(slaves):
         b, ub = control_fuzz_script(ref, seed)
         assert ua == ub, f"seed {seed}: used elements differ\nours {ua}\nref  {ub}"
         assert (a == b).all(), f"seed {seed}: guest memory differs at {np.nonzero(a != b)[0][:16]}"
+
+
+def test_vhost_user_many_masters_and_hot_plug_at_once(slaves):
+    """connections coming and going from several threads while targets are hot-plugged over RPC: the daemon
+    must keep answering both (no crash, no stuck thread, no leaked listening socket)"""
+    import threading
+    ours = slaves("ours", ["--control-only"])
+    errors = []
+
+    def vm(k):
+        try:
+            for i in range(12):
+                img = vring.build_image([], ring_size=64, seed=k * 100 + i, mutate=False, data_bytes=2 << 20)
+                ram = vu.GuestRam(img.arena.size)
+                ram.mem[:] = img.arena
+                cq, eq = small_ring(0), small_ring(1)
+                for r in (cq, eq):
+                    ram.mem[r[0]:r[0] + 8192] = 0
+                queues = [vu.Queue(0, 16, *cq[:3]), vu.Queue(1, 16, *eq[:3]), vu.Queue(2, 64, img.desc_off, img.avail_off, img.used_off)]
+                m = vu.Master(ours.sock("scsi0"))
+                handshake(m, ram, img, queues)
+                if i % 3 == 0:
+                    publish(ram, eq, event_buffers(ram, img, eq))
+                    publish(ram, cq, control_requests(ram, img, cq))
+                    queues[0].notify()
+                    wait_used(ram, cq, 8)
+                if i % 2:
+                    for q in queues:
+                        m.get_vring_base(q.index)
+                m.close()                                  # every other one just disappears
+                for q in queues:
+                    q.close()
+                ram.close()
+        except Exception as e:                              # noqa: BLE001
+            errors.append(f"vm {k}: {type(e).__name__}: {e}")
+
+    threads = [threading.Thread(target=vm, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    n = 0
+    while any(t.is_alive() for t in threads):
+        assert b'"result":1' in ours.call("add_vhost_scsi_lun", {"ctrlr": "scsi0", "scsi_target_num": 1, "bdev_name": "M1"})
+        assert b'"result":true' in ours.call("remove_vhost_scsi_target", {"ctrlr": "scsi0", "scsi_target_num": 1})
+        n += 1
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert n > 0 and ours.p.poll() is None
+    assert b'"scsi0"' in ours.call("get_vhost_controllers")
