@@ -805,6 +805,9 @@ __device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc
 	uint32_t table_size = q.vq_size;
 	if (d.flags & VD_INDIRECT) {
 		table_size = d.len / 16;
+		/* a table shorter than one descriptor: the reference reads 16 bytes it never checked; out of
+		 * bounds for us means a fault that takes the whole session down, so the chain is invalid */
+		if (table_size == 0) return false;
 		table = (const uint8_t *)(uintptr_t)gpa_to_dev_len(L, d.addr, 16ull * table_size);
 		if (table == nullptr) return false;
 		d = load_desc(table);

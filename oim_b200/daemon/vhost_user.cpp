@@ -341,6 +341,7 @@ bool Session::get_desc(Vq &q, uint16_t head, VringDesc **desc, VringDesc **table
 	*desc = (VringDesc *)q.desc + head;
 	if ((*desc)->flags & VD_INDIRECT) {
 		*table_size = (*desc)->len / sizeof(VringDesc);
+		if (*table_size == 0) return false;	/* the reference would read a descriptor out of a 0-byte table */
 		*table = (VringDesc *)gpa_to_host((*desc)->addr, sizeof(VringDesc) * (uint64_t)*table_size);
 		*desc = *table;
 		return *desc != nullptr;
@@ -504,6 +505,13 @@ bool Session::start()
 	for (const Region &r : mem) {
 		if (r.size & kMask2M) {
 			fprintf(stderr, "oim-gpu-vhost: %s: guest memory size is not a 2MB multiple\n", srv->name.c_str());
+			return false;
+		}
+		/* beyond the reference: its 2 MiB-page walk (vhost.c:461-509) stays inside a region only if the region
+		 * also STARTS on a 2 MiB boundary, which QEMU guarantees for hugepage-backed memory; on a GPU a stray
+		 * access is not a SIGSEGV of one request but the end of the context, so insist on it */
+		if (r.gpa & kMask2M) {
+			fprintf(stderr, "oim-gpu-vhost: %s: guest memory region does not start on a 2MB boundary\n", srv->name.c_str());
 			return false;
 		}
 	}
