@@ -47,6 +47,7 @@ def parse_args():
     p.add_argument("--e2e-queues", type=int, default=256)
     p.add_argument("--e2e-per-queue", type=int, default=512)
     p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--ref-procs", type=int, default=0, help="reference reactors (processes) of the CPU legs; 0 = one per usable core, bounded by memory")
     p.add_argument("--no-seq", action="store_true", help="skip the 128 KiB sequential leg")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
@@ -181,22 +182,105 @@ class CpuLeg:
         self.o.close()
 
 
+def _cpu_worker(conn, io_blocks: int, pattern: str):
+    """one reference reactor: its own process, its own controller + 8 GiB Malloc bdev, its own trace"""
+    try:
+        leg = CpuLeg(io_blocks, pattern)
+        conn.send(("ready", leg.kind))
+        while True:
+            msg = conn.recv()
+            if msg[0] == "run":
+                v, info = leg.run(msg[1])
+                conn.send(("done", v, info))
+            else:
+                break
+        leg.close()
+    except Exception as e:  # noqa: BLE001
+        conn.send(("error", f"{type(e).__name__}: {e}"))
+
+
+def cpu_reactor_count() -> int:
+    """how many reference reactors the box can run side by side: one per usable core (SPDK pins one reactor
+    thread per core, one vhost controller's data path runs on exactly one of them), bounded by host memory -
+    every reactor gets its own 8 GiB bdev + 1 GiB of client buffers - and by 32"""
+    cores = len(os.sched_getaffinity(0))
+    avail = 0
+    for ln in open("/proc/meminfo"):
+        if ln.startswith("MemAvailable:"):
+            avail = int(ln.split()[1]) * 1024
+    by_mem = int(avail * 0.6 // ((NUM_BLOCKS * BLOCK) + (3 << 29)))
+    return max(1, min(cores, by_mem, 32))
+
+
+class CpuFarm:
+    """the reference on all the host cores it can use: P independent reactors, as `vhost -m <mask>` with one
+    controller per core would run them; the aggregate is the sum of their rates over the same wall interval"""
+
+    def __init__(self, nproc: int, io_blocks: int = 8, pattern: str = "randread"):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        self.workers = []
+        for _ in range(nproc):
+            parent, child = ctx.Pipe()
+            pr = ctx.Process(target=_cpu_worker, args=(child, io_blocks, pattern), daemon=True)
+            pr.start()
+            self.workers.append((pr, parent))
+        self.kind = None
+        for _, c in self.workers:
+            msg = c.recv()
+            if msg[0] != "ready":
+                raise RuntimeError(f"reference reactor failed to start: {msg}")
+            self.kind = msg[1]
+
+    def run(self, seconds: float):
+        for _, c in self.workers:
+            c.send(("run", seconds))
+        vals, info = [], None
+        for _, c in self.workers:
+            msg = c.recv()
+            if msg[0] != "done":
+                raise RuntimeError(f"reference reactor failed: {msg}")
+            vals.append(msg[1])
+            info = msg[2]
+        return vals, info
+
+    def close(self):
+        for pr, c in self.workers:
+            try:
+                c.send(("close",))
+            except Exception:  # noqa: BLE001
+                pass
+        for pr, _ in self.workers:
+            pr.join(20)
+            if pr.is_alive():
+                pr.kill()
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     per_step = max(0.5, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
-    leg = CpuLeg(8, "randread")
-    vals = []
+    # The configuration decides how many threads the reference can use: its data path for one vhost controller
+    # (= one LUN here) runs on exactly one reactor core (vhost_scsi.c:1311-1318), so a job of N LUNs - one per
+    # GPU in our arm - keeps N cores busy.  --ref-procs overrides (e.g. to see what every core together does).
+    nproc = args.ref_procs or max(1, args.gpus)
+    farm = CpuFarm(nproc, 8, "randread")
+    totals, singles = [], []
     for i in range(args.warmup + args.steps):
-        iops, info = leg.run(per_step)
+        vals, info = farm.run(per_step)
         if i >= args.warmup:
-            vals.append(iops)
-    leg.close()
-    v = statistics.mean(vals)
+            totals.append(sum(vals))
+            singles.append(statistics.mean(vals))
+    farm.close()
+    v = statistics.mean(totals)
+    info = {**info, "cores": nproc,
+            "sample": f"{nproc} reference reactors side by side (one process, one vhost controller + 8 GiB Malloc bdev each, as "
+                      f"SPDK scales: one reactor per core), each: " + info["sample"],
+            "per_core_value": statistics.mean(singles)}
     line = {"impl": "reference", "metric": "4KiB rand-read IOPS", "value": v, "unit": "IOPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C2: one 8 GiB Malloc bdev, 4 KiB random read, reference CPU poller"},
+            "config": {"workload": f"C2: 8 GiB Malloc bdev, 4 KiB random read, reference CPU poller x {nproc} reactors (cores)"},
             "cpu_baseline": {**info, "value": v},
             "e2e": {"value": v, "unit": "IOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -515,10 +599,23 @@ def run_ours(args, rank, world, local):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        # this configuration is ONE LUN behind one controller: the reference serves it from one reactor core
         leg = CpuLeg(8, "randread")
         v, info = leg.run(args.cpu_seconds)
         leg.close()
         cpu = {**info, "value": v}
+        # for scale: the same reference on every core the box can give it (one reactor = one more controller + LUN),
+        # i.e. what the host CPUs do when the job is as many LUNs as there are cores
+        try:
+            nproc = args.ref_procs or cpu_reactor_count()
+            farm = CpuFarm(nproc, 8, "randread")
+            vals, _ = farm.run(min(args.cpu_seconds, 8.0))
+            farm.close()
+            cpu["all_cores"] = {"value": sum(vals), "cores": nproc, "per_core_value": statistics.mean(vals),
+                                "note": f"{nproc} independent reference reactors (processes), each with its own controller and "
+                                        f"8 GiB Malloc bdev; bounded by cores, host memory and 32"}
+        except Exception as e:  # noqa: BLE001
+            cpu["all_cores"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     lun.close()
     lun_e2e.close()
