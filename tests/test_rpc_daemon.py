@@ -273,3 +273,46 @@ def test_daemon_on_gpu_config1(tmp_path):
     finally:
         proc.terminate()
         proc.wait(10)
+
+
+def test_rpc_random_call_sequences(servers):
+    """differential fuzzing of the bookkeeping: random create / attach / detach / delete / list sequences must
+    produce identical replies (auto-naming counters, SCSI device ids, listing order, error messages)"""
+    import random
+    for seed in range(12):
+        rng = random.Random(seed)
+        bdevs = ["A", "B", "C", "Malloc0", "Malloc1", "gone"]
+        ctrls = ["c0", "c1", "none"]
+        for step in range(60):
+            k = rng.randrange(11)
+            if k == 0:
+                p = {"num_blocks": rng.choice([2048, 4096, 0]), "block_size": rng.choice([512, 4096])}
+                if rng.random() < 0.6:
+                    p["name"] = rng.choice(bdevs[:3]) + f"_{seed}"
+                both(servers, "construct_malloc_bdev", p)
+            elif k == 1:
+                both(servers, "delete_bdev", {"name": rng.choice(bdevs[:3]) + f"_{seed}" if rng.random() < 0.7 else rng.choice(bdevs)})
+            elif k == 2:
+                both(servers, "construct_vhost_scsi_controller", {"ctrlr": rng.choice(ctrls[:2]) + f".{seed}"})
+            elif k == 3:
+                both(servers, "remove_vhost_controller", {"ctrlr": rng.choice(ctrls) + f".{seed}"})
+            elif k in (4, 5):
+                both(servers, "add_vhost_scsi_lun", {"ctrlr": rng.choice(ctrls) + f".{seed}", "scsi_target_num": rng.choice([-1, 0, 1, 2, 7, 8]),
+                                                     "bdev_name": rng.choice(bdevs[:3]) + f"_{seed}"})
+            elif k == 6:
+                both(servers, "remove_vhost_scsi_target", {"ctrlr": rng.choice(ctrls) + f".{seed}", "scsi_target_num": rng.choice([0, 1, 2, 7, 9])})
+            elif k == 7:
+                both(servers, "get_bdevs")
+            elif k == 8:
+                both(servers, "get_vhost_controllers")
+            elif k == 9:
+                both(servers, "get_bdevs", {"name": rng.choice(bdevs[:3]) + f"_{seed}"})
+            else:
+                both(servers, "get_bdevs_iostat")
+        # leave both servers empty for the next seed (same calls on both, so they stay in step)
+        for c in (f"c0.{seed}", f"c1.{seed}"):
+            for t in range(8):
+                both(servers, "remove_vhost_scsi_target", {"ctrlr": c, "scsi_target_num": t})
+            both(servers, "remove_vhost_controller", {"ctrlr": c})
+        for b in both(servers, "get_bdevs")["result"]:
+            both(servers, "delete_bdev", {"name": b["name"]})
