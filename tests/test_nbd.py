@@ -182,13 +182,15 @@ def test_cuda_nbd_matches_reference(gpu, oracles, seed):
         a, b = socket.socketpair()
         a.settimeout(20)
         rc = []
-        th = threading.Thread(target=lambda: rc.append(gpu.load().oimgpu_nbd_serve(name.encode(), b.fileno())), daemon=True)
+        def serve():
+            rc.append(gpu.load().oimgpu_nbd_serve(name.encode(), b.fileno()))
+            b.close()                                    # the caller owns the socket: the daemon closes it in nbd_stop
+        th = threading.Thread(target=serve, daemon=True)
         th.start()
         got = play(a, ops, lambda: None, tail)
         th.join(20)
         assert not th.is_alive()
         a.close()
-        b.close()
         assert rc == [0 if seed % 2 == 0 else -22]
         assert len(got) == len(want)
         for i, (g, w) in enumerate(zip(got, want)):
