@@ -47,7 +47,7 @@ def parse_args():
     p.add_argument("--e2e-queues", type=int, default=256)
     p.add_argument("--e2e-per-queue", type=int, default=512)
     p.add_argument("--cpu-seconds", type=float, default=12.0)
-    p.add_argument("--ref-procs", type=int, default=0, help="reference reactors (processes) of the CPU legs; 0 = one per usable core, bounded by memory")
+    p.add_argument("--ref-procs", type=int, default=0, help="reference reactors (processes) of --impl reference; 0 = one per LUN of the job (= --gpus); capped by cores, memory budget and 8")
     p.add_argument("--no-seq", action="store_true", help="skip the 128 KiB sequential leg")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
@@ -199,17 +199,29 @@ def _cpu_worker(conn, io_blocks: int, pattern: str):
         conn.send(("error", f"{type(e).__name__}: {e}"))
 
 
-def cpu_reactor_count() -> int:
-    """how many reference reactors the box can run side by side: one per usable core (SPDK pins one reactor
-    thread per core, one vhost controller's data path runs on exactly one of them), bounded by host memory -
-    every reactor gets its own 8 GiB bdev + 1 GiB of client buffers - and by 32"""
-    cores = len(os.sched_getaffinity(0))
-    avail = 0
+def host_memory_budget() -> int:
+    """bytes this process tree may safely take: the smaller of MemAvailable and the cgroup limit (a container's
+    /proc/meminfo shows the HOST's memory; exceeding the cgroup limit takes the whole box down), quartered"""
+    avail = 1 << 62
     for ln in open("/proc/meminfo"):
         if ln.startswith("MemAvailable:"):
             avail = int(ln.split()[1]) * 1024
-    by_mem = int(avail * 0.6 // ((NUM_BLOCKS * BLOCK) + (3 << 29)))
-    return max(1, min(cores, by_mem, 32))
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v.isdigit():
+                avail = min(avail, int(v))
+        except OSError:
+            pass
+    return avail // 4
+
+
+def cpu_reactor_count(want: int) -> int:
+    """how many reference reactors can run side by side: every reactor is a process with its own 8 GiB bdev and
+    1 GiB of client buffers; never more than the usable cores, the memory budget, or 8"""
+    cores = len(os.sched_getaffinity(0))
+    by_mem = int(host_memory_budget() // ((NUM_BLOCKS * BLOCK) + (3 << 29)))
+    return max(1, min(want, cores, by_mem, 8))
 
 
 class CpuFarm:
@@ -263,7 +275,7 @@ def run_reference(args, rank, world):
     # The configuration decides how many threads the reference can use: its data path for one vhost controller
     # (= one LUN here) runs on exactly one reactor core (vhost_scsi.c:1311-1318), so a job of N LUNs - one per
     # GPU in our arm - keeps N cores busy.  --ref-procs overrides (e.g. to see what every core together does).
-    nproc = args.ref_procs or max(1, args.gpus)
+    nproc = cpu_reactor_count(args.ref_procs or max(1, args.gpus))
     farm = CpuFarm(nproc, 8, "randread")
     totals, singles = [], []
     for i in range(args.warmup + args.steps):
@@ -604,18 +616,6 @@ def run_ours(args, rank, world, local):
         v, info = leg.run(args.cpu_seconds)
         leg.close()
         cpu = {**info, "value": v}
-        # for scale: the same reference on every core the box can give it (one reactor = one more controller + LUN),
-        # i.e. what the host CPUs do when the job is as many LUNs as there are cores
-        try:
-            nproc = args.ref_procs or cpu_reactor_count()
-            farm = CpuFarm(nproc, 8, "randread")
-            vals, _ = farm.run(min(args.cpu_seconds, 8.0))
-            farm.close()
-            cpu["all_cores"] = {"value": sum(vals), "cores": nproc, "per_core_value": statistics.mean(vals),
-                                "note": f"{nproc} independent reference reactors (processes), each with its own controller and "
-                                        f"8 GiB Malloc bdev; bounded by cores, host memory and 32"}
-        except Exception as e:  # noqa: BLE001
-            cpu["all_cores"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     lun.close()
     lun_e2e.close()
