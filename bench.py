@@ -55,6 +55,7 @@ def parse_args():
     p.add_argument("--no-mixed", action="store_true", help="skip the 70/30 mixed leg (config 4 shape)")
     p.add_argument("--no-lat", action="store_true", help="skip the single-queue qd=32 closed-loop leg")
     p.add_argument("--no-vu", action="store_true", help="skip the leg through the daemon's vhost-user socket")
+    p.add_argument("--no-extra", action="store_true", help="skip the 4 KiB random-write / 128 KiB sequential-read legs")
     return p.parse_args()
 
 
@@ -607,6 +608,17 @@ def run_ours(args, rank, world, local):
                "requests_per_step": n2, "queues": sq,
                "volume": "construct_rbd_bdev (Ceph RBD emulated in HBM), target 1 of the benchmark controller"}
 
+    # ---- the other two corners of the same shapes: 4 KiB random WRITE, 128 KiB sequential READ ----
+    extra = None
+    if not args.no_extra:
+        n3, ms3, _, _ = resident_leg(8, "randwrite", "single", nq, per_q // 4, args.steps, args.warmup, None)
+        w_iops = aggregate(n3, args.steps, world, ms3)
+        n4, ms4, _, _ = resident_leg(256, "seqread", "pages", args.seq_queues, args.seq_per_queue, args.steps, args.warmup, None)
+        r_gbs = n4 * args.steps * world * 131072 / (ms4 / 1e3) / 1e9
+        extra = {"rand4k_write": {"value": w_iops, "unit": "IOPS", "hbm_frac": 2 * 4096 * w_iops / world / 1e9 / peak,
+                                  "requests_per_step": n3, "note": "random LBAs over the whole device from 1024 queues"},
+                 "seq128k_read": {"value": r_gbs, "unit": "GB/s", "hbm_frac": 2 * r_gbs / world / peak, "requests_per_step": n4}}
+
     clocks = sampler.stop() if rank == 0 else {}
 
     cpu = None
@@ -644,7 +656,7 @@ def run_ours(args, rank, world, local):
                          "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
             "seq128k": seq, "virtqueue": vq, "mixed_70_30": mixed, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
-            "vhost_user": vuser,
+            "vhost_user": vuser, "more": extra,
         }
         print(json.dumps(line))
     if world > 1:
