@@ -1443,10 +1443,16 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			}
 			for (uint32_t w = 0; w < nw; w++) {
 				for (uint32_t u = mw; u < nunits; u += kMovers) {
-					uint32_t lo = 0, hi = nseg;	/* last segment with first_unit <= u */
-					while (hi - lo > 1) {
-						const uint32_t mid = (lo + hi) >> 1;
-						if (st.seg[mid].first_unit <= u) lo = mid; else hi = mid;
+					uint32_t lo = u, hi = nseg;	/* last segment with first_unit <= u */
+					/* as many units as segments: segment u IS unit u.  Taken for passes of small requests (the
+					 * 4 KiB case, +1.5 %); long SG lists of single pages keep the search - measured 1.5 %
+					 * faster there, the lookup's latency spreads the movers' loads */
+					if (nunits != nseg || nseg > (uint32_t)kPass) {
+						lo = 0;
+						while (hi - lo > 1) {
+							const uint32_t mid = (lo + hi) >> 1;
+							if (st.seg[mid].first_unit <= u) lo = mid; else hi = mid;
+						}
 					}
 					const Segment &g = st.seg[lo];
 					if (nw > 1 && (g.wave & kSegWaveMask) != w) continue;
