@@ -571,8 +571,17 @@ static void on_signal(int) { g_stop = 1; }
 
 static void usage(const char *argv0)
 {
-	fprintf(stderr, "usage: %s [-S vhost-socket-dir] [-r rpc-socket] [-f pidfile] [-m coremask] [-s MB] [-R] [--gpus 0,1,...]\n"
-			"       [--rbd-size BYTES]\n", argv0);
+	fprintf(stderr,
+		"usage: %s [-S vhost-socket-dir] [-r rpc-socket] [-f pidfile] [-m coremask] [-s MB] [-R]\n"
+		"       [--gpus 0,1,...] [--rbd-size BYTES] [--poller] [--no-vhost-user] [--control-only]\n"
+		"  -S -r -f -m -s -R   as SPDK's vhost app (S/app/vhost/vhost.c:43-48); -s and -R are accepted and ignored\n"
+		"  --gpus LIST         CUDA devices to serve bdevs from (default: the current device)\n"
+		"  --rbd-size BYTES    size of a construct_rbd_bdev volume (emulated in HBM; default 8 GiB)\n"
+		"  --poller            one resident GPU poller per vhost-user session instead of a launch per kick\n"
+		"  --no-vhost-user     JSON-RPC only: do not listen on <vhost-socket-dir>/<controller>\n"
+		"  --control-only      no CUDA at all: bookkeeping and wire protocols only (tests)\n"
+		"  environment: OIM_VU_DEBUG=1 logs session start/stop; SIGUSR2 prints the transport threads' backtraces\n",
+		argv0);
 }
 
 int main(int argc, char **argv)
