@@ -1593,8 +1593,8 @@ extern "C" int oimgpu_nbd_serve(const char *bdev_name, int sock_fd)
 		case 3:		/* NBD_CMD_FLUSH: the whole device, a no-op for RAM */
 			ok = true;
 			break;
-		case 4:		/* NBD_CMD_TRIM -> spdk_bdev_unmap: zero fill */
-			ok = range_ok;
+		case 4:		/* NBD_CMD_TRIM -> spdk_bdev_unmap: zero fill; "Can't unmap 0 bytes" (bdev.c:2796-2799) */
+			ok = range_ok && len != 0;
 			for (int r = 0; ok && len && r < nrep && e == cudaSuccess; r++) e = cudaMemsetAsync(stores[r] + from, 0, len, st);
 			break;
 		default:	/* unknown command: EIO (nbd.c:527-540) */

@@ -1248,3 +1248,94 @@ const char *oimorc_describe(void)
 {
 	return "port: plain-C restatement of SPDK v19.04-pre vhost-scsi/scsi/bdev/malloc path (oracle/oim_oracle.c)";
 }
+
+/* ------------------------------------------------------------------------------------------
+ * NBD export: the server side of the kernel's transmission protocol, restating spdk_nbd_poll
+ * (S/lib/nbd/nbd.c:560-806: spdk_nbd_io_recv_internal, nbd_submit_bdev_io, nbd_io_done,
+ * spdk_nbd_io_xmit_internal) on the restated bdev.  Blocking; one request at a time, which is
+ * also the order the reference answers in for a Malloc bdev (completions are immediate).
+ * Returns 0 when the peer disconnects (EOF or NBD_CMD_DISC), -EINVAL on a bad request magic.
+ * ---------------------------------------------------------------------------------------- */
+#include <unistd.h>
+#include <sys/socket.h>
+
+static int nbd_read_full(int fd, void *buf, size_t n)
+{
+	size_t got = 0;
+	while (got < n) {
+		ssize_t r = read(fd, (char *)buf + got, n - got);
+		if (r < 0 && errno == EINTR) continue;
+		if (r <= 0) return -1;
+		got += (size_t)r;
+	}
+	return 0;
+}
+
+static int nbd_write_full(int fd, const void *buf, size_t n)
+{
+	size_t put = 0;
+	while (put < n) {
+		ssize_t r = send(fd, (const char *)buf + put, n - put, MSG_NOSIGNAL);
+		if (r < 0 && errno == EINTR) continue;
+		if (r <= 0) return -1;
+		put += (size_t)r;
+	}
+	return 0;
+}
+
+int oimorc_nbd_serve(void *h, int fd)
+{
+	struct oimorc *o = h;
+	struct orc_bdev *b = &o->bdev;
+	uint8_t *payload = NULL;
+	size_t cap = 0;
+	int rc = 0;
+
+	for (;;) {
+		uint8_t req[28], resp[16];	/* struct nbd_request / struct nbd_reply (linux/nbd.h), big endian */
+		uint32_t type, len, psize;
+		uint64_t from, ob, nb;
+		bool ok = false;
+
+		if (nbd_read_full(fd, req, sizeof(req)) != 0) break;
+		if (be32(req) != 0x25609513u) { rc = -EINVAL; break; }	/* NBD_REQUEST_MAGIC */
+		type = be32(req + 4);
+		from = be64(req + 16);
+		len = be32(req + 24);
+		/* "io except read/write should ignore payload" (nbd.c:607-613) */
+		psize = (type == 0 || type == 1) ? len : 0;
+		if (psize > cap) {
+			free(payload);
+			payload = malloc(psize);
+			cap = psize;
+		}
+		if (type == 1 && psize && nbd_read_full(fd, payload, psize) != 0) break;
+		if (type == 2) break;	/* NBD_CMD_DISC: soft disconnect, nothing outstanding */
+		switch (type) {
+		case 0:	/* NBD_CMD_READ -> spdk_bdev_read */
+			ok = bdev_bytes_to_blocks(b, from, &ob, len, &nb) == 0 && bdev_valid_blocks(b, ob, nb);
+			if (ok && len) memcpy(payload, b->buf + from, len);
+			break;
+		case 1:	/* NBD_CMD_WRITE -> spdk_bdev_write */
+			ok = bdev_bytes_to_blocks(b, from, &ob, len, &nb) == 0 && bdev_valid_blocks(b, ob, nb);
+			if (ok && len) memcpy(b->buf + from, payload, len);
+			break;
+		case 3:	/* NBD_CMD_FLUSH -> spdk_bdev_flush over the whole device */
+			ok = true;
+			break;
+		case 4:	/* NBD_CMD_TRIM -> spdk_bdev_unmap */
+			ok = bdev_bytes_to_blocks(b, from, &ob, len, &nb) == 0 && bdev_unmap_blocks(b, ob, nb) == 0;
+			break;
+		default:	/* rc = -1 -> nbd_io_done(NULL, false, io) */
+			break;
+		}
+		memset(resp, 0, sizeof(resp));
+		to_be32(resp, 0x67446698u);		/* NBD_REPLY_MAGIC */
+		to_be32(resp + 4, ok ? 0 : EIO);
+		memcpy(resp + 8, req + 8, 8);
+		if (nbd_write_full(fd, resp, sizeof(resp)) != 0) break;
+		if (type == 0 && ok && len && nbd_write_full(fd, payload, len) != 0) break;
+	}
+	free(payload);
+	return rc;
+}

@@ -40,15 +40,17 @@ def script(seed: int):
         elif k == 8:
             ops.append((FLUSH, 0, 0, b""))
         elif k == 9:
-            bad = int(rng.integers(0, 4))
+            bad = int(rng.integers(0, 5))
             if bad == 0:
                 ops.append((READ, frm + 7, ln, b""))                              # offset not on a block
             elif bad == 1:
                 ops.append((WRITE, frm, ln - 100, b"\x5a" * (ln - 100)))          # length not whole blocks
             elif bad == 2:
                 ops.append((READ, NB * BS - BS, 4 * BS, b""))                     # runs off the end
-            else:
+            elif bad == 3:
                 ops.append((TRIM, NB * BS, BS, b""))                              # starts at the end
+            else:
+                ops.append((TRIM, frm, 0, b""))                                   # "Can't unmap 0 bytes": EIO
         elif k == 10:
             ops.append((9, frm, ln, b""))                                         # unknown command: EIO, no payload
         else:
@@ -167,14 +169,56 @@ def test_reference_nbd_loop_known_answers(oracles):
     assert (store[4096:4608] == 0).all() and (store[4608:5120] == 0xAB).all()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("seed", range(4))
-def test_cuda_nbd_matches_reference(gpu, oracles, seed):
+def run_restatement(oracles, ops, tail):
+    """the C restatement (oracle/oim_oracle.c: oimorc_nbd_serve), blocking, on a thread of its own"""
+    a, b = socket.socketpair()
+    a.settimeout(20)
+    o = oracles.PortOracle(NB, BS, 0)
+    try:
+        o.store[:] = traces.pattern_bytes(7, 0, o.store.size)
+        o.lib.oimorc_nbd_serve.restype = C.c_int
+        o.lib.oimorc_nbd_serve.argtypes = [C.c_void_p, C.c_int]
+        rc = []
+
+        def serve():
+            rc.append(o.lib.oimorc_nbd_serve(o.h, b.fileno()))
+            b.close()
+        th = threading.Thread(target=serve, daemon=True)
+        th.start()
+        out = play(a, ops, lambda: None, tail)
+        th.join(20)
+        assert not th.is_alive()
+        a.close()
+        return out, o.store.copy(), rc[0]
+    finally:
+        o.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_nbd_restatement_matches_reference(oracles, seed):
     if not oracles.ref_available():
-        pytest.skip("oracle/_ref not on this box")
+        pytest.skip("oracle/_ref not built here")
     ops = script(seed)
     tail = tails()["disc" if seed % 2 == 0 else "garbage"]
     want, want_store = run_reference(oracles, ops, tail)
+    got, got_store, rc = run_restatement(oracles, ops, tail)
+    assert rc == (0 if seed % 2 == 0 else -22)
+    assert len(got) == len(want)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g == w, f"reply {i} to {ops[i][:3] if i < len(ops) else 'tail'} differs: {g[:24]!r} vs {w[:24]!r}"
+    assert (got_store == want_store).all()
+    assert any(op[0] == TRIM and op[2] == 0 for s in range(8) for op in script(s)), "the zero-length TRIM case is in the scripts"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_cuda_nbd_matches_reference(gpu, oracles, seed):
+    ops = script(seed)
+    tail = tails()["disc" if seed % 2 == 0 else "garbage"]
+    if oracles.ref_available():
+        want, want_store = run_reference(oracles, ops, tail)
+    else:
+        want, want_store, _ = run_restatement(oracles, ops, tail)
     name = f"nbd{seed}"
     gpu.construct_malloc_bdev(NB, BS, name=name, device=0)
     try:
