@@ -1,13 +1,19 @@
 """Offline differential campaign: the C restatement against the compiled reference on many more seeds than the
 test-suite runs (CPU only; needs oracle/_ref).  python tools/oracle_campaign.py  ->  mismatch count per family."""
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+N = float(os.environ.get("CAMPAIGN_SCALE", "1"))      # CAMPAIGN_SCALE=0.02 for a smoke run
 import numpy as np
 from oracle import bindings
 from oim_b200 import traces, vring, abi
 import util
 bad=0; t0=time.time()
 # 1. fuzz traces, varied geometry
-for seed in range(2000, 2250):
+for seed in range(2000, 2000 + max(1, int(250 * N))):
     nb=[32768, 8192, 65536, 16384][seed%4]; bs=[512,512,4096,520][seed%4] if seed%7==0 else 512
     try:
         t=traces.fuzz_trace(400, nb, block_size=bs, seed=seed, max_io_blocks=[8,64,300,1024][seed%4], arena_bytes=(48<<20) if seed%4==3 else (16<<20))
@@ -22,7 +28,7 @@ for seed in range(2000, 2250):
         bad+=1; print("MISMATCH fuzz", seed, str(e)[:300], flush=True)
 print("fuzz done", time.time()-t0, "bad", bad, flush=True)
 # 2. primary commands
-for seed in range(3000, 3100):
+for seed in range(3000, 3000 + max(1, int(100 * N))):
     t=traces.primary_trace(300, seed=seed)
     a=util.run_oracle(bindings.RefOracle, t, 32768, name=f"camp{seed}")
     ro=None
@@ -37,7 +43,7 @@ print("primary done", time.time()-t0, "bad", bad, flush=True)
 # ---- virtqueue images (with malformed chains) and multi-target controllers ----
 import test_vring as TV, test_multi_target as TM
 class O: RefOracle=bindings.RefOracle; PortOracle=bindings.PortOracle
-for seed in range(5000, 5150):
+for seed in range(5000, 5000 + max(1, int(150 * N))):
     nb, rq = 32768, TV.make_requests(seed)
     ring = [64, 256, 1024][seed % 3]
     want, ws = TV.run_kicks_oracle(bindings.RefOracle, rq, nb, ring, seed)
@@ -45,7 +51,7 @@ for seed in range(5000, 5150):
     ok = len(got)==len(want) and all(g[2]==w[2] and g[1]==w[1] and (g[0]==w[0]).all() for g,w in zip(got,want)) and (gs==ws).all()
     if not ok: bad+=1; print("MISMATCH vring", seed, flush=True)
 print("vring done", time.time()-t0, "bad", bad, flush=True)
-for seed in range(6000, 6060):
+for seed in range(6000, 6000 + max(1, int(60 * N))):
     for kind in ("fuzz","primary"):
         t = TM.multi_trace(seed, kind=kind)
         names = {1: f"c{seed}a", 3: f"c{seed}b", 6: f"c{seed}c"}
