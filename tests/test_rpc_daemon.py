@@ -279,7 +279,7 @@ def test_rpc_random_call_sequences(servers):
     """differential fuzzing of the bookkeeping: random create / attach / detach / delete / list sequences must
     produce identical replies (auto-naming counters, SCSI device ids, listing order, error messages)"""
     import random
-    for seed in range(12):
+    for seed in range(int(os.environ.get("OIM_RPC_FUZZ_SEEDS", "12"))):
         rng = random.Random(seed)
         bdevs = ["A", "B", "C", "Malloc0", "Malloc1", "gone"]
         ctrls = ["c0", "c1", "none"]
