@@ -899,10 +899,9 @@ static void stop_server(Server &s)
 	if (s.th.joinable()) s.th.join();
 	{
 		std::lock_guard<std::mutex> lk(s.mu);
-		for (auto &ss : s.sessions) {
-			eventfd_write(ss->wake, 1);
-			if (ss->fd >= 0) ::shutdown(ss->fd, SHUT_RDWR);
-		}
+		/* the sessions watch srv->stop; their `wake` eventfd gets them out of poll().  (Their sockets are theirs
+		 * alone: touching ss->fd from here would race with a session that is closing it.) */
+		for (auto &ss : s.sessions) eventfd_write(ss->wake, 1);
 		for (auto &ss : s.sessions) {
 			if (ss->th.joinable()) ss->th.join();
 			close(ss->wake);

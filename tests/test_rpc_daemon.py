@@ -17,7 +17,7 @@ import time
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DAEMON = os.path.join(ROOT, "oim_b200", "oim-gpu-vhost")
+DAEMON = os.environ.get("OIM_DAEMON_PATH") or os.path.join(ROOT, "oim_b200", "oim-gpu-vhost")   # override: sanitizer builds
 
 
 class Client:

@@ -35,3 +35,8 @@ try:
     print("control queue fuzz done", time.time()-t0, "bad", bad, flush=True)
 finally:
     ours.close(); ref.close()
+    log = open(ours.dir / "log.txt", errors="replace").read()
+    hits = [ln for ln in log.splitlines() if "runtime error" in ln or "AddressSanitizer" in ln]
+    print("sanitizer reports in the daemon log:", len(hits))      # meaningful with OIM_DAEMON_PATH=<asan build>
+    for ln in hits[:10]:
+        print("  ", ln[:200])
