@@ -628,6 +628,13 @@ def run_ours(args, rank, world, local):
         v, info = leg.run(args.cpu_seconds)
         leg.close()
         cpu = {**info, "value": v}
+        # the same reference as a vhost-user slave, driven by the master script of the `vhost_user` leg: the
+        # like-for-like baseline of the path a VM takes (its transport, its poller, its memcpy; one reactor core)
+        if not args.no_vu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "liboim_ref_vhost.so")):
+            try:
+                cpu["vhost_user"] = vhost_user_leg(args, local, "reference")
+            except Exception as e:  # noqa: BLE001
+                cpu["vhost_user"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     lun.close()
     lun_e2e.close()
@@ -682,7 +689,12 @@ def vhost_user_leg(args, device: int, mode: str) -> dict:
     os.mkdir(os.path.join(tmp, "vhost"))
     rpc = os.path.join(tmp, "rpc.sock")
     log = open(os.path.join(tmp, "daemon.log"), "wb")
-    cmd = [build.DAEMON, "-r", rpc, "-S", os.path.join(tmp, "vhost"), "--gpus", str(device)] + (["--poller"] if mode == "poller" else [])
+    if mode == "reference":
+        # the reference's own vhost target (S/lib/vhost incl. its vhost-user transport, compiled into oracle/_ref) as the
+        # slave: one reactor core polling the rings, exactly what QEMU would talk to in an SPDK deployment
+        cmd = [sys.executable, os.path.join(ROOT, "tests", "ref_rpc_server.py"), rpc, os.path.join(tmp, "vhost"), "vhost", "busy"]
+    else:
+        cmd = [build.DAEMON, "-r", rpc, "-S", os.path.join(tmp, "vhost"), "--gpus", str(device)] + (["--poller"] if mode == "poller" else [])
     proc = subprocess.Popen(cmd, stdout=log, stderr=log)
     try:
         t0 = time.time()
