@@ -703,7 +703,12 @@ def vhost_user_leg(args, device: int, mode: str) -> dict:
                 raise RuntimeError("oim-gpu-vhost did not start: " + open(os.path.join(tmp, "daemon.log")).read()[-500:])
             time.sleep(0.02)
         c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        c.connect(rpc)
+        for _ in range(500):             # (the reference's server binds first and listens a moment later)
+            try:
+                c.connect(rpc)
+                break
+            except (ConnectionRefusedError, FileNotFoundError):
+                time.sleep(0.01)
 
         def call(i, method, params):
             c.sendall((_json.dumps({"jsonrpc": "2.0", "method": method, "params": params, "id": i}) + "\n").encode())

@@ -626,9 +626,13 @@ int main(int argc, char **argv)
 	int lfd = socket(AF_UNIX, SOCK_STREAM, 0);
 	sockaddr_un sa{};
 	sa.sun_family = AF_UNIX;
-	snprintf(sa.sun_path, sizeof(sa.sun_path), "%s", rpc_sock.c_str());
-	unlink(rpc_sock.c_str());
-	if (bind(lfd, (sockaddr *)&sa, sizeof(sa)) != 0 || listen(lfd, 64) != 0) {
+	/* bind under a temporary name and rename once listening: whoever waits for the socket file to appear
+	 * (test/pkg/spdk/spdk.go:121-133, start-stop.make:17) can connect the moment it does */
+	const std::string rpc_tmp = rpc_sock + ".starting";
+	snprintf(sa.sun_path, sizeof(sa.sun_path), "%s", rpc_tmp.c_str());
+	unlink(rpc_tmp.c_str());
+	if (rpc_tmp.size() >= sizeof(sa.sun_path) || bind(lfd, (sockaddr *)&sa, sizeof(sa)) != 0 || listen(lfd, 64) != 0 ||
+	    rename(rpc_tmp.c_str(), rpc_sock.c_str()) != 0) {
 		fprintf(stderr, "oim-gpu-vhost: cannot listen on %s: %s\n", rpc_sock.c_str(), strerror(errno));
 		return 1;
 	}

@@ -931,12 +931,17 @@ int listen_ctrlr(const std::string &name, const std::string &path)
 	if (g_servers.count(name)) return -EEXIST;
 	int fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
 	if (fd < 0) return -errno;
+	/* bound under a temporary name, renamed once listening: the file's appearance is what deployments wait
+	 * for (test/start-stop.make:20-23) */
+	const std::string tmp = path + ".starting";
+	if (tmp.size() >= sizeof(sa.sun_path)) { close(fd); return -ENAMETOOLONG; }
 	sa.sun_family = AF_UNIX;
-	snprintf(sa.sun_path, sizeof(sa.sun_path), "%s", path.c_str());
-	unlink(path.c_str());
-	if (bind(fd, (sockaddr *)&sa, sizeof(sa)) != 0 || listen(fd, 128) != 0) {
+	snprintf(sa.sun_path, sizeof(sa.sun_path), "%s", tmp.c_str());
+	unlink(tmp.c_str());
+	if (bind(fd, (sockaddr *)&sa, sizeof(sa)) != 0 || listen(fd, 128) != 0 || rename(tmp.c_str(), path.c_str()) != 0) {
 		int e = errno;
 		close(fd);
+		unlink(tmp.c_str());
 		return -e;
 	}
 	auto s = std::make_unique<Server>();

@@ -25,7 +25,15 @@ class Client:
 
     def __init__(self, path, pump=None):
         self.s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        self.s.connect(path)
+        t0 = time.time()
+        while True:                      # the socket file appears at bind(), connections are taken from listen() on
+            try:
+                self.s.connect(path)
+                break
+            except (ConnectionRefusedError, FileNotFoundError):
+                if time.time() - t0 > 10:
+                    raise
+                time.sleep(0.01)
         self.s.setblocking(False)
         self.pump = pump or (lambda: time.sleep(0.001))
         self.id = 0
