@@ -17,7 +17,7 @@ bench: build
 	$(PY) bench.py --steps 10 --warmup 3
 
 campaign: build   ## restatement vs reference and wire protocols on many more seeds (CPU)
-	$(PY) tools/oracle_campaign.py
-	$(PY) tools/transport_campaign.py
+	$(PY) tests/campaign_oracle.py
+	$(PY) tests/campaign_transport.py
 
 .PHONY: build test test-gpu smoke bench campaign

@@ -1,5 +1,5 @@
 """Offline differential campaign: the C restatement against the compiled reference on many more seeds than the
-test-suite runs (CPU only; needs oracle/_ref).  python tools/oracle_campaign.py  ->  mismatch count per family."""
+test-suite runs (CPU only; needs oracle/_ref).  python tests/campaign_oracle.py  ->  mismatch count per family."""
 import os
 import sys
 import time

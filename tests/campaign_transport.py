@@ -1,6 +1,6 @@
 """Offline differential campaign for the vhost-user slave (daemon with --control-only) against the reference's own
 transport: random protocol message sequences and random control-queue requests, far more seeds than the tests run.
-CPU only; needs oracle/_ref/liboim_ref_vhost.so.  python tools/transport_campaign.py"""
+CPU only; needs oracle/_ref/liboim_ref_vhost.so.  python tests/campaign_transport.py"""
 import os, sys, pathlib, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
