@@ -55,6 +55,7 @@ def parse_args():
     p.add_argument("--no-mixed", action="store_true", help="skip the 70/30 mixed leg (config 4 shape)")
     p.add_argument("--no-lat", action="store_true", help="skip the single-queue qd=32 closed-loop leg")
     p.add_argument("--no-vu", action="store_true", help="skip the leg through the daemon's vhost-user socket")
+    p.add_argument("--no-mirror", action="store_true", help="skip the mirrored-bdev leg (config 5; runs when --gpus >= 2)")
     p.add_argument("--no-extra", action="store_true", help="skip the 4 KiB random-write / 128 KiB sequential-read legs")
     return p.parse_args()
 
@@ -324,6 +325,143 @@ def device_pattern_fill(lun, store_ptr: int, nbytes: int, seed: int, torch):
         lun.copy(store_ptr + done * 8, z.data_ptr(), n * 8)
         lun.sync()
         done += n
+
+
+def pattern_fill_tensor(t, seed: int, torch):
+    """fill a uint8 CUDA tensor (length a multiple of 8) with traces.pattern_words(seed, 0, ...) in place"""
+    gamma = -7046029254386353131
+    m1, m2 = -4658895280553007687, -7723592293110705685
+
+    def lsr(x, k):
+        return (x >> k) & ((1 << (64 - k)) - 1)
+    words = t.view(torch.int64)
+    chunk = (256 << 20) // 8
+    for done in range(0, words.numel(), chunk):
+        n = min(chunk, words.numel() - done)
+        idx = torch.arange(done, done + n, dtype=torch.int64, device=t.device)
+        z = (idx ^ seed) * gamma + gamma
+        z = (z ^ lsr(z, 30)) * m1
+        z = (z ^ lsr(z, 27)) * m2
+        words[done:done + n] = z ^ lsr(z, 31)
+        del idx, z
+
+
+def nvlink_peak():
+    """GB/s per direction per GPU that a peer copy reaches on this pool (B200_PROFILING.md: measured 770, nominal 900);
+    profiles/nvlink.json (tools/nvlink_probe.cu on this pool) overrides when present"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "nvlink.json")))
+        return float(d["ce_peer_copy_gbs"]), "measured (profiles/nvlink.json, tools/nvlink_probe.cu: copy-engine peer copy)"
+    except (OSError, KeyError, ValueError):
+        return 770.0, "B200_PROFILING.md: measured peer copy 770 GB/s per direction (900 nominal)"
+
+
+def mirror_leg(args, rank, world, local, lib, torch, timer, barrier, max_over_ranks):
+    """BASELINE config 5: 2-way mirrored bdev, 128 KiB sequential write, write fan-out over NVLink.
+    One process per GPU: rank r is the PRIMARY of mirror r (store on its own GPU) and hosts the REPLICA of mirror r-1,
+    which rank r-1 reaches through a CUDA IPC mapping; the mover warps store every unit twice, to local HBM and by P2P
+    stores to the peer.  Two shapes: `pairs` - only even ranks write (N=2: one mirrored volume, N=4: two: SURVEY 8(d)
+    C5 literally) - and `ring` - every rank writes, every NVLink port carries one replica stream out and one in.
+    No reference implementation exists (S/lib/bdev/raid/bdev_raid.c:848-851 is RAID0 only), so parity is the contract
+    of SURVEY 8(c): every replica equals what the single-bdev oracle holds after the same write trace - checked here
+    on all 8 GiB of both replicas through position-keyed digests, and byte for byte against the oracle on a window."""
+    import torch.distributed as dist
+    nb = NUM_BLOCKS
+    hosted = lib.construct_malloc_bdev(nb, BLOCK, name=f"MirrorReplica{rank}", device=local)
+    ht = torch.frombuffer(bytearray(lib.bdev_export_store(hosted)), dtype=torch.uint8).cuda()
+    handles = [torch.empty_like(ht) for _ in range(world)]
+    dist.all_gather(handles, ht)
+    right, left = (rank + 1) % world, (rank - 1) % world
+    mname = lib.construct_mirror_bdev_remote(nb, BLOCK, local, [bytes(handles[right].cpu().numpy())], name=f"Mirror{rank}")
+    ctrlr = f"mirror.{rank}"
+    lib.construct_vhost_scsi_controller(ctrlr)
+    lib.add_vhost_scsi_lun(ctrlr, 0, mname)
+    sq, sp = args.seq_queues, args.seq_per_queue
+    n = sq * sp
+    t = traces.uniform_trace(n, nb, io_blocks=256, pattern="seqwrite", sg="pages", seed=0xC5000000 + rank)
+    assert n * 131072 == nb * BLOCK, "one step = one full pass over the device"
+    arena = torch.empty(t.arena_bytes, dtype=torch.uint8, device="cuda")
+    pattern_fill_tensor(arena, 0xC5000000 + rank, torch)
+    d_reqs = torch.from_numpy(t.reqs.view(np.uint8)).cuda()
+    d_iovs = torch.from_numpy(t.bind(arena.data_ptr()).view(np.uint8)).cuda()
+    d_cpls = torch.zeros(n * 48, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    res = {}
+    with lib.Lun(ctrlr, 0, num_queues=sq, queue_size=32) as lun:
+        def step():
+            lun.submit_batch(sq, sp, d_reqs.data_ptr(), d_iovs.data_ptr(), len(t.iovs), d_cpls.data_ptr(), abi.MEM_DEVICE)
+        for shape in ("pairs", "ring"):
+            writer = shape == "ring" or rank % 2 == 0
+            writers = world if shape == "ring" else (world + 1) // 2
+            for _ in range(args.warmup):
+                if writer:
+                    step()
+            lun.sync()
+            barrier()
+            timer.start(lun)
+            for _ in range(args.steps):
+                if writer:
+                    step()
+            timer.stop(lun)
+            lun.sync()
+            barrier()
+            ms = max_over_ranks(timer.elapsed_ms() if writer else 0.0)
+            gbs = writers * n * args.steps * 131072 / (ms / 1e3) / 1e9
+            res[shape] = {"value": gbs, "unit": "GB/s of user writes, whole job", "mirrored_volumes": writers,
+                          "per_volume_gbs": gbs / writers, "ms_per_step": ms / args.steps}
+        c = np.frombuffer(d_cpls.cpu().numpy().tobytes(), dtype=abi.cpl_dtype)
+        assert not c["status"].any() and (c["used_len"] == 108).all(), "mirror leg: bad completions"
+        launches = lun.iostat()["kernel_launches"]
+    # ---- parity, every byte of both replicas of every mirror ----
+    barrier()
+    mine = lib.digest_device(local, arena.data_ptr(), arena.numel())       # store == arena after a full sequential pass
+    dg = torch.tensor([mine[0] & 0x7FFFFFFFFFFFFFFF, mine[1] & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+    all_dg = [torch.empty_like(dg) for _ in range(world)]
+    dist.all_gather(all_dg, dg)
+    prim = lib.bdev_digest(mname, 0)
+    repl = lib.bdev_digest(hosted, 0)
+    assert prim == mine, f"rank {rank}: primary store differs from the written payload"
+    want_left = tuple(int(x) for x in all_dg[left].cpu())
+    assert (repl[0] & 0x7FFFFFFFFFFFFFFF, repl[1] & 0x7FFFFFFFFFFFFFFF) == want_left, \
+        f"rank {rank}: the replica of mirror {left} hosted here differs from what rank {left} wrote"
+    oracle_window = None
+    if rank == 0:
+        # the oracle as CHECKER (never measured): the first 512 requests of the trace cover exactly the first 64 MiB
+        from oracle import bindings
+        try:
+            bindings.build()
+        except Exception:  # noqa: BLE001
+            pass
+        wreq, wblk = 512, 512 * 256
+        o = bindings.PortOracle(wblk, BLOCK)
+        harena = arena[:wreq * 131072].cpu().numpy()
+        sub = traces.Trace(t.reqs[:wreq].copy(), t.iovs[:wreq * 32].copy(), harena.size)
+        oc = o.submit(sub.reqs, sub.bind(harena.ctypes.data))
+        assert not oc["status"].any()
+        want = o.store.copy()
+        o.close()
+        for rep in (0, 1):
+            got = lib.bdev_read_raw(mname, 0, wblk * BLOCK, replica=rep)
+            assert (got == want).all(), f"replica {rep} differs from the oracle's store on the first 64 MiB"
+        oracle_window = "first 64 MiB (512 requests) of both replicas of mirror 0 == oracle (C restatement) store, byte for byte"
+    barrier()
+    lib.remove_vhost_scsi_target(ctrlr, 0)
+    lib.remove_vhost_controller(ctrlr)
+    lib.delete_bdev(mname)
+    barrier()                                   # every importer is gone before an exporter frees its store
+    lib.delete_bdev(hosted)
+    del arena, d_reqs, d_iovs, d_cpls
+    torch.cuda.empty_cache()
+    nv, nv_src = nvlink_peak()
+    for shape in res:
+        res[shape]["nvlink_frac"] = res[shape]["per_volume_gbs"] / nv    # R=2: one payload stream out of the primary
+    return {"metric": "128KiB seq-write GB/s on 2-way mirrored bdevs (32 x 4 KiB SG pages), replica on the next GPU, fan-out "
+                      "by P2P stores from the mover warps (oim_lun_queue_mirror_kernel)",
+            **res, "replicas": 2, "nvlink_peak_gbs": nv, "nvlink_peak_source": nv_src, "gpu_launches": launches,
+            "requests_per_step_per_volume": n,
+            "parity": "digest(primary) == digest(replica on the peer GPU) == digest(written payload) over all 8 GiB of every "
+                      "mirror (oimgpu_bdev_digest); " + (oracle_window or ""),
+            "transport": "cross-process: replica store exported with cudaIpcGetMemHandle, imported by the primary's process"}
 
 
 def run_ours(args, rank, world, local):
@@ -619,6 +757,11 @@ def run_ours(args, rank, world, local):
                                   "requests_per_step": n3, "note": "random LBAs over the whole device from 1024 queues"},
                  "seq128k_read": {"value": r_gbs, "unit": "GB/s", "hbm_frac": 2 * r_gbs / world / peak, "requests_per_step": n4}}
 
+    # ---- config 5: mirrored bdev across GPUs (needs a peer: N >= 2) ----
+    mirror = None
+    if world >= 2 and not args.no_mirror:
+        mirror = mirror_leg(args, rank, world, local, lib, torch, timer, barrier, max_over_ranks)
+
     clocks = sampler.stop() if rank == 0 else {}
 
     cpu = None
@@ -663,7 +806,7 @@ def run_ours(args, rank, world, local):
                          "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
             "seq128k": seq, "virtqueue": vq, "mixed_70_30": mixed, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
-            "vhost_user": vuser, "more": extra,
+            "vhost_user": vuser, "more": extra, "mirror": mirror,
         }
         print(json.dumps(line))
     if world > 1:

@@ -185,6 +185,22 @@ int oimgpu_bdev_create_rbd(const char *name, const char *pool_name, const char *
 /* R-way mirrored malloc bdev: replica r lives on devices[r]; writes fan out over NVLink. */
 int oimgpu_bdev_create_mirror(const char *name, uint64_t num_blocks, uint32_t block_size,
 			      const int *devices, int nreplicas, char *name_out, size_t name_cap);
+/* Mirrors across PROCESSES (one process per GPU, the way bench.py and a per-GPU daemon run): a replica's
+ * store is an ordinary bdev of the process that owns that GPU, exported as a CUDA IPC handle
+ * (OIMGPU_IPC_HANDLE_BYTES bytes, any byte transport); the primary's process imports the handles and
+ * builds the mirrored bdev on its own GPU.  Writes then fan out exactly as for an in-process mirror
+ * (P2P stores over NVLink from the mover warps).  No reference counterpart: S/lib/bdev/raid/bdev_raid.c:848-851
+ * is RAID0 only.  The exporting bdev must outlive every importer. */
+#define OIMGPU_IPC_HANDLE_BYTES 64
+int oimgpu_bdev_export_store(const char *name, int replica, void *handle_out);
+int oimgpu_bdev_create_mirror_remote(const char *name, uint64_t num_blocks, uint32_t block_size, int device,
+				     const void *peer_handles, int npeers, char *name_out, size_t name_cap);
+/* Position-keyed 128-bit digest of [offset, offset+nbytes) of one replica's store (offset and nbytes multiples of
+ * 8): out[0] = sum of w_i * (2i+1), out[1] = sum of mix64(w_i ^ i) over the 64-bit words w_i, i counted from the
+ * start of the range, all mod 2^64 (mix64 = the splitmix64 finaliser).  Test/bench infrastructure for the
+ * size-independent parity properties (replica == replica == expected content) at sizes a host copy is too slow for. */
+int oimgpu_bdev_digest(const char *name, int replica, uint64_t offset, uint64_t nbytes, uint64_t out[2]);
+int oimgpu_digest_device(int device, const void *dev_ptr, uint64_t nbytes, uint64_t out[2]);
 int oimgpu_bdev_delete(const char *name);			/* -ENODEV if unknown; attached targets are hot-removed
 								 * (as spdk_bdev_unregister does); -EBUSY while a
 								 * data path (oimgpu_lun) is open on it */

@@ -226,7 +226,8 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 	const uint32_t cnt = r.iovcnt;
 	const bool from_dev = (r.dir == OIMGPU_DIR_FROM_DEV) || cnt == 0;
 	const uint32_t dxfer_dir = from_dev ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV;
-	uint32_t len = 0, nonzero = 0, units = 0;
+	uint32_t nonzero = 0, units = 0;
+	uint64_t len64 = 0;
 
 	s.op = OP_NONE; s.nseg = 0; s.valid = 1; s.length = 0; s.off = 0; s.tgt = L.target;
 	s.store_lo = s.store_hi = 0;
@@ -240,9 +241,15 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 		if (q.iov_limit && r.iov_start + j >= q.iov_limit) { valid = false; break; }	/* index outside the SG table */
 		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
 		if (v.addr == 0) { valid = false; break; }
-		len += v.len;
+		len64 += v.len;
 		if (v.len) { nonzero++; units += units_of(v.len); }
 	}
+	/* The reference sums the element lengths in 32 bits (vhost_scsi.c:573, 596 `len += desc->len`): two
+	 * elements of 2 GiB + 4 KiB wrap to 4 KiB, every length check passes on the wrapped value, and the copy
+	 * then runs over the full elements.  There that overruns the target's own process; here it would cross
+	 * into other tenants' LUNs in the same HBM.  A payload that does not fit task->length is an invalid request. */
+	if (len64 > 0xffffffffull) valid = false;
+	const uint32_t len = (uint32_t)len64;
 	if (!valid) {
 		s.valid = 0;
 		s.used_len = 0;		/* invalid_request(): used element only (vhost_scsi.c:347-358) */
@@ -1525,6 +1532,26 @@ oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes)
 	} else {
 		for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < nbytes; i += (uint64_t)gridDim.x * 256) dst[i] = fill;
 	}
+}
+
+/* oimgpu_bdev_digest: position-keyed sums over 64-bit words (include/oimgpu.h) */
+__global__ void __launch_bounds__(256)
+oim_digest_kernel(const uint64_t *p, uint64_t nwords, unsigned long long *out)
+{
+	unsigned long long a = 0, b = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * 256) {
+		const uint64_t w = p[i];
+		a += w * (2 * i + 1);
+		uint64_t z = w ^ i;
+		z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+		z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+		b += z ^ (z >> 31);
+	}
+	for (int o = 16; o; o >>= 1) {
+		a += __shfl_xor_sync(0xffffffffu, a, o);
+		b += __shfl_xor_sync(0xffffffffu, b, o);
+	}
+	if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], a); atomicAdd(&out[1], b); }
 }
 
 size_t lun_kernel_smem_bytes() { return sizeof(CtaShared); }

@@ -72,8 +72,9 @@ struct Bdev {
 	uint32_t block_size = 0;
 	int claimed = 0;	/* number of SCSI targets built on it */
 	int open_luns = 0;	/* oimgpu_lun handles */
-	std::vector<int> devices;	/* replica r lives on devices[r] */
+	std::vector<int> devices;	/* replica r lives on devices[r] (an imported replica: the device it is reached from) */
 	std::vector<uint8_t *> stores;
+	std::vector<char> imported;	/* replica r is another process's store, opened from a CUDA IPC handle */
 	unsigned long long retired[8] = {};	/* counters of sessions that are gone (same layout as LunCtx::stats) */
 };
 
@@ -181,6 +182,7 @@ struct oimgpu_lun {
 	bool any_mirror = false;
 	VqState *d_vq_state = nullptr;		/* [num_queues] ring cursors */
 	oimgpu_iov *d_iov_scratch = nullptr;	/* [grid_cap][32][kIovRow] SG rows built by the parser lanes */
+	uint8_t *slab = nullptr;		/* the mapped pinned slab the per-queue rings are carved from */
 };
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -403,6 +405,15 @@ static void copy_str(char *dst, size_t cap, const std::string &s)
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 
+static void release_store(Bdev &b, size_t r)
+{
+	cudaSetDevice(b.devices[r]);
+	if (b.imported[r]) cudaIpcCloseMemHandle(b.stores[r]);
+	else cudaFree(b.stores[r]);
+	(void)cudaGetLastError();
+}
+
+
 extern "C" int oimgpu_abi_version(void) { return OIMGPU_ABI_VERSION; }
 
 extern "C" const char *oimgpu_version_string(void)
@@ -478,10 +489,7 @@ extern "C" void oimgpu_fini(void)
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (!g.inited) return;
 	for (auto &kv : g.bdevs) {
-		for (size_t r = 0; r < kv.second->stores.size() && !g.control_only; r++) {
-			cudaSetDevice(kv.second->devices[r]);
-			cudaFree(kv.second->stores[r]);
-		}
+		for (size_t r = 0; r < kv.second->stores.size() && !g.control_only; r++) release_store(*kv.second, r);
 	}
 	g.control_only = false;
 	g.bdevs.clear();
@@ -560,6 +568,7 @@ static int create_bdev_locked(const char *name, const char *uuid, uint64_t num_b
 		}
 		b->devices.push_back(d);
 		b->stores.push_back(p);
+		b->imported.push_back(0);
 	}
 	copy_str(name_out, name_cap, nm);
 	g.bdevs[nm] = std::move(b);
@@ -623,6 +632,106 @@ extern "C" int oimgpu_bdev_create_mirror(const char *name, uint64_t num_blocks, 
 	return rc;
 }
 
+extern "C" int oimgpu_bdev_export_store(const char *name, int replica, void *handle_out)
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == OIMGPU_IPC_HANDLE_BYTES, "IPC handle size");
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited || g.control_only) return -ENODEV;
+	if (!handle_out) return -EINVAL;
+	auto it = g.bdevs.find(name ? name : "");
+	if (it == g.bdevs.end()) return -ENODEV;
+	Bdev &b = *it->second;
+	if (replica < 0 || replica >= (int)b.stores.size() || b.imported[replica]) return -EINVAL;
+	CU_OK(cudaSetDevice(b.devices[replica]));
+	cudaIpcMemHandle_t h;
+	CU_OK(cudaIpcGetMemHandle(&h, b.stores[replica]));
+	memcpy(handle_out, &h, sizeof(h));
+	return 0;
+}
+
+extern "C" int oimgpu_bdev_create_mirror_remote(const char *name, uint64_t num_blocks, uint32_t block_size, int device,
+						 const void *peer_handles, int npeers, char *name_out, size_t name_cap)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited || g.control_only) return -ENODEV;
+	if (!peer_handles || npeers < 1 || npeers >= kMaxReplicas) return -EINVAL;
+	int d = pick_device(device);
+	if (d < 0) return -EINVAL;
+	std::string auto_name;
+	if (!(name && name[0])) auto_name = "Mirror" + std::to_string(g.malloc_disk_count);
+	char nm[64];
+	int rc = create_bdev_locked(name, nullptr, num_blocks, block_size, {d}, "Malloc disk", auto_name, nm, sizeof(nm));
+	if (rc) return rc;
+	if (!(name && name[0])) g.malloc_disk_count++;
+	Bdev &b = *g.bdevs[nm];
+	CU_OK(cudaSetDevice(d));
+	for (int r = 0; r < npeers; r++) {
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const uint8_t *)peer_handles + (size_t)r * sizeof(h), sizeof(h));
+		void *p = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) {
+			fprintf(stderr, "oimgpu: cudaIpcOpenMemHandle failed: %s\n", cudaGetErrorString(e));
+			(void)cudaGetLastError();
+			for (size_t k = 0; k < b.stores.size(); k++) release_store(b, k);
+			g.bdev_order.erase(std::remove(g.bdev_order.begin(), g.bdev_order.end(), std::string(nm)), g.bdev_order.end());
+			g.bdevs.erase(nm);
+			return -EIO;
+		}
+		b.devices.push_back(d);
+		b.stores.push_back((uint8_t *)p);
+		b.imported.push_back(1);
+	}
+	copy_str(name_out, name_cap, nm);
+	return 0;
+}
+
+namespace oimgpu { __global__ void oim_digest_kernel(const uint64_t *p, uint64_t nwords, unsigned long long *out); }
+
+static int digest_locked(int device, const void *dptr, uint64_t nbytes, uint64_t out[2])
+{
+	if (!dptr || !out || (nbytes & 7) || ((uintptr_t)dptr & 7)) return -EINVAL;
+	const int slot = find_device_slot(device);
+	if (slot < 0) return -EINVAL;
+	CU_OK(cudaSetDevice(device));
+	cudaStream_t st = g.devices[slot].util;
+	unsigned long long *d = nullptr;
+	CU_OK(cudaMalloc((void **)&d, 16));
+	CU_OK(cudaMemsetAsync(d, 0, 16, st));
+	oim_digest_kernel<<<g.devices[slot].sm_count * 4, 256, 0, st>>>((const uint64_t *)dptr, nbytes / 8, d);
+	unsigned long long h[2] = {0, 0};
+	cudaError_t e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	cudaFree(d);
+	if (e != cudaSuccess) { (void)cudaGetLastError(); return -EIO; }
+	out[0] = h[0]; out[1] = h[1];
+	return 0;
+}
+
+extern "C" int oimgpu_digest_device(int device, const void *dev_ptr, uint64_t nbytes, uint64_t out[2])
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited || g.control_only) return -ENODEV;
+	return digest_locked(device, dev_ptr, nbytes, out);
+}
+
+extern "C" int oimgpu_bdev_digest(const char *name, int replica, uint64_t offset, uint64_t nbytes, uint64_t out[2])
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited || g.control_only) return -ENODEV;
+	auto it = g.bdevs.find(name ? name : "");
+	if (it == g.bdevs.end()) return -ENODEV;
+	Bdev &b = *it->second;
+	if (replica < 0 || replica >= (int)b.stores.size()) return -EINVAL;
+	const uint64_t size = b.num_blocks * (uint64_t)b.block_size;
+	if (offset > size || nbytes > size - offset || (offset & 7)) return -EINVAL;
+	/* everything already launched on the sessions' streams comes first */
+	for (oimgpu_lun *L : g.handles) {
+		if (!L->poller_active) { CU_OK(cudaSetDevice(L->device)); CU_OK(cudaStreamSynchronize(L->stream)); }
+	}
+	return digest_locked(b.devices[replica], b.stores[replica] + offset, nbytes, out);
+}
+
 extern "C" int oimgpu_bdev_delete(const char *name)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
@@ -630,9 +739,14 @@ extern "C" int oimgpu_bdev_delete(const char *name)
 	auto it = g.bdevs.find(name ? name : "");
 	if (it == g.bdevs.end()) return -ENODEV;
 	/* a session opened on exactly this device pins it; controller-wide sessions let go of it below */
+	int peer_refs = 0;
 	for (oimgpu_lun *L : g.handles) {
 		if (L->bdev == it->first) return -EBUSY;
+		for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) peer_refs += L->peer_bdev[t] == it->first;
 	}
+	/* every other pin (an NBD export, oimgpu_nbd_serve) is checked BEFORE anything is taken apart: a failed
+	 * delete must leave the targets where they were */
+	if (it->second->open_luns > peer_refs) return -EBUSY;
 	/* spdk_bdev_unregister hot-removes the SCSI LUNs built on the bdev (lun.c:213-260): the targets go */
 	for (auto &kv : g.ctrlrs) {
 		bool touched = false;
@@ -649,10 +763,10 @@ extern "C" int oimgpu_bdev_delete(const char *name)
 	g.bdev_order.erase(std::remove(g.bdev_order.begin(), g.bdev_order.end(), it->first), g.bdev_order.end());
 	for (size_t r = 0; r < it->second->stores.size() && !g.control_only; r++) {
 		auto parked = park_pollers_locked(it->second->devices[r]);
-		cudaSetDevice(it->second->devices[r]);
-		cudaFree(it->second->stores[r]);
+		const bool own = !it->second->imported[r];
+		release_store(*it->second, r);
 		unpark_pollers_locked(parked);
-		g.devices[find_device_slot(it->second->devices[r])].bytes_allocated -=
+		if (own) g.devices[find_device_slot(it->second->devices[r])].bytes_allocated -=
 			it->second->num_blocks * (uint64_t)it->second->block_size;
 	}
 	g.bdevs.erase(it);
@@ -898,6 +1012,40 @@ extern "C" int oimgpu_vhost_ctrlr_list(oimgpu_ctrlr_info *out, int max)
 
 /* ---- data path ----------------------------------------------------------------------------------- */
 
+/* everything a session allocated, whether oimgpu_lun_open got through or not (every member starts null).
+ * Caller holds g.mu and has parked the other sessions' pollers (the frees wait for the device). */
+static void free_lun_resources(oimgpu_lun *L)
+{
+	cudaSetDevice(L->device);
+	if (L->h_door) cudaFreeHost((void *)L->h_door);
+	if (L->h_flags) cudaFreeHost((void *)L->h_flags);
+	if (L->slab) cudaFreeHost(L->slab);
+	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
+		if (L->h_kick[k]) cudaFreeHost(L->h_kick[k]);
+		if (L->kick_ev[k]) cudaEventDestroy(L->kick_ev[k]);
+	}
+	cudaFree(L->d_kick);
+	cudaFree(L->d_vq_state);
+	cudaFree(L->d_iov_scratch);
+	cudaFree(L->bs_d_reqs);
+	cudaFree(L->bs_d_iovs);
+	cudaFree(L->bs_d_cpls);
+	if (L->bs_h_pin) cudaFreeHost(L->bs_h_pin);
+	if (L->bs_uploaded) cudaEventDestroy(L->bs_uploaded);
+	if (L->copy_stream) cudaStreamDestroy(L->copy_stream);
+	cudaFree(L->d_ctx);
+	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+		cudaFree(L->d_peer[t]);
+		if (!L->peer_bdev[t].empty()) {
+			auto bi = g.bdevs.find(L->peer_bdev[t]);
+			if (bi != g.bdevs.end() && bi->second->open_luns > 0) bi->second->open_luns--;
+		}
+	}
+	if (L->done) cudaEventDestroy(L->done);
+	if (L->stream) cudaStreamDestroy(L->stream);
+	(void)cudaGetLastError();
+}
+
 extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t num_queues,
 			       uint32_t queue_size, oimgpu_lun **out)
 {
@@ -922,7 +1070,14 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 		if (!it->second->targets[t].empty()) { session_device = g.bdevs[it->second->targets[t]]->devices[0]; break; }
 	}
 
-	auto L = std::make_unique<oimgpu_lun>();
+	/* whatever a failed step leaves behind (streams, events, pinned and device allocations) is released here */
+	struct Guard {
+		oimgpu_lun *L;
+		~Guard() { if (L) { free_lun_resources(L); delete L; } }
+		oimgpu_lun *operator->() { return L; }
+		oimgpu_lun *get() { return L; }
+		oimgpu_lun *release() { oimgpu_lun *r = L; L = nullptr; return r; }
+	} L{new oimgpu_lun()};
 	L->ctrlr = it->first;
 	L->bdev = bn;
 	L->target = session ? 0xff : scsi_target_num;
@@ -956,6 +1111,7 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	const size_t per_q = sizeof(oimgpu_req) * queue_size + sizeof(oimgpu_iov) * L->iov_cap + sizeof(oimgpu_cpl) * queue_size;
 	uint8_t *slab = nullptr, *dslab = nullptr;
 	CU_OK(cudaHostAlloc((void **)&slab, per_q * num_queues, cudaHostAllocMapped));
+	L->slab = slab;
 	CU_OK(cudaHostGetDevicePointer((void **)&dslab, slab, 0));
 	memset(slab, 0, per_q * num_queues);
 	for (uint32_t q = 0; q < num_queues; q++) {
@@ -1010,34 +1166,8 @@ extern "C" int oimgpu_lun_close(oimgpu_lun *L)
 		if (!L->peer_bdev[t].empty()) retire_stats_locked(L->peer_bdev[t], L->device, L->d_peer[t]);
 	}
 	auto parked = park_pollers_locked(L->device, L);	/* other sessions' resident kernels: see park_pollers_locked */
-	cudaSetDevice(L->device);
-	cudaFreeHost((void *)L->h_door);
-	cudaFreeHost((void *)L->h_flags);
-	if (!L->queues.empty()) cudaFreeHost(L->queues[0].h_reqs);
-	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
-		cudaFreeHost(L->h_kick[k]);
-		cudaEventDestroy(L->kick_ev[k]);
-	}
-	cudaFree(L->d_kick);
-	cudaFree(L->d_vq_state);
-	cudaFree(L->d_iov_scratch);
-	cudaFree(L->bs_d_reqs);
-	cudaFree(L->bs_d_iovs);
-	cudaFree(L->bs_d_cpls);
-	cudaFreeHost(L->bs_h_pin);
-	cudaEventDestroy(L->bs_uploaded);
-	cudaStreamDestroy(L->copy_stream);
-	cudaFree(L->d_ctx);
-	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
-		cudaFree(L->d_peer[t]);
-		if (!L->peer_bdev[t].empty()) {
-			auto bi = g.bdevs.find(L->peer_bdev[t]);
-			if (bi != g.bdevs.end() && bi->second->open_luns > 0) bi->second->open_luns--;
-		}
-	}
+	free_lun_resources(L);
 	g.handles.erase(std::remove(g.handles.begin(), g.handles.end(), L), g.handles.end());
-	cudaEventDestroy(L->done);
-	cudaStreamDestroy(L->stream);
 	unpark_pollers_locked(parked);
 	g.open_luns--;
 	{
@@ -1346,7 +1476,13 @@ extern "C" int oimgpu_submit_batch(oimgpu_lun *L, uint32_t nq, uint32_t per_q, c
 			    (pin_out ? 0 : n * sizeof(oimgpu_cpl));
 	if (need > L->bs_h_cap) {
 		CU_OK(cudaStreamSynchronize(L->stream));
-		cudaFreeHost(L->bs_h_pin);
+		if (L->bs_h_pin) {
+			/* cudaFreeHost waits for every GPU the memory is mapped into: see park_pollers_locked */
+			std::lock_guard<std::mutex> lk(g.mu);
+			auto parked = park_pollers_locked(-1, L);
+			cudaFreeHost(L->bs_h_pin);
+			unpark_pollers_locked(parked);
+		}
 		L->bs_h_pin = nullptr;
 		CU_OK(cudaHostAlloc((void **)&L->bs_h_pin, need, cudaHostAllocDefault));
 		L->bs_h_cap = need;

@@ -443,7 +443,21 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 	}
 	if (method == "delete_bdev") {
 		if (!decode(params, {{"name", Json::Str, false, &a}})) return bad;
+		/* the SCSI targets built on the bdev go with it (spdk_bdev_unregister -> hot-remove, lun.c:213-260); connected
+		 * guests are told like for remove_vhost_scsi_target (TRANSPORT_RESET / REMOVED, vhost_scsi.c:236-289) */
+		std::vector<std::pair<std::string, int>> gone;
+		if (g_serve_vhost_user) {
+			int n = oimgpu_vhost_ctrlr_list(nullptr, 0);
+			std::vector<oimgpu_ctrlr_info> v(n > 0 ? n : 1);
+			n = oimgpu_vhost_ctrlr_list(v.data(), n);
+			for (int i = 0; i < n; i++) {
+				for (uint32_t t = 0; t < v[i].ntargets; t++) {
+					if (a->raw == v[i].targets[t].bdev_name) gone.push_back({v[i].ctrlr, v[i].targets[t].scsi_dev_num});
+				}
+			}
+		}
 		if (oimgpu_bdev_delete(a->raw.c_str()) != 0) return bad;
+		for (auto &g : gone) vhost_user::notify_target(g.first, g.second, false);
 		return result(id, "true");
 	}
 	if (method == "construct_vhost_scsi_controller") {
@@ -486,6 +500,8 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 		if (!decode(params, {{"ctrlr", Json::Str, false, &a}})) return error(id, E_INVALID_PARAMS, strerr(EINVAL));
 		oimgpu_ctrlr_info info;
 		const bool known = oimgpu_vhost_ctrlr_get(a->raw.c_str(), &info) == 0;
+		/* spdk_vhost_dev_unregister: "Controller %s has still valid connection" -> -EBUSY (S/lib/vhost/vhost.c:783-788) */
+		if (g_serve_vhost_user && known && vhost_user::active_sessions(info.ctrlr) > 0) return error(id, E_INVALID_PARAMS, strerr(EBUSY));
 		int rc = oimgpu_vhost_ctrlr_remove(a->raw.c_str());
 		if (rc < 0) return error(id, E_INVALID_PARAMS, strerr(rc));
 		if (g_serve_vhost_user && known) vhost_user::close_ctrlr(info.ctrlr);
@@ -662,6 +678,8 @@ int main(int argc, char **argv)
 				ssize_t n = read(c.fd, buf, sizeof(buf));
 				if (n > 0) c.in.append(buf, n);
 				else if (n == 0 || (errno != EAGAIN && errno != EINTR)) c.closing = true;
+				/* the peer is gone for good (not a half-close): whatever is still queued has nowhere to go */
+				if ((pfds[i + 1].revents & (POLLHUP | POLLERR)) && n <= 0) { c.closing = true; c.out.clear(); }
 			}
 			/* requests are processed in order per connection; one JSON value at a time */
 			while (!c.in.empty()) {
@@ -671,7 +689,13 @@ int main(int argc, char **argv)
 				ps.ws();
 				if (ps.p == ps.end) { c.in.clear(); break; }
 				bool ok = ps.value(v);
-				if (!ok && ps.incomplete) break;	/* wait for the rest */
+				if (!ok && ps.incomplete) {
+					/* wait for the rest - but not for ever: the reference's receive buffer is 32 KiB
+					 * (SPDK_JSONRPC_RECV_BUF_SIZE, jsonrpc_internal.h:43); a value that does not fit is a
+					 * parse error there, and the connection goes */
+					if (c.in.size() > 32 * 1024) { c.in.clear(); c.closing = true; }
+					break;
+				}
 				if (!ok) {
 					/* "Can't recover from parse error (no guaranteed resync point in streaming JSON)":
 					 * the reference queues a -32700 reply but closes the connection before it is
@@ -687,7 +711,7 @@ int main(int argc, char **argv)
 			if (!c.out.empty()) {
 				ssize_t n = write(c.fd, c.out.data(), c.out.size());
 				if (n > 0) c.out.erase(0, n);
-				else if (n < 0 && errno != EAGAIN && errno != EINTR) c.closing = true;
+				else if (n < 0 && errno != EAGAIN && errno != EINTR) { c.closing = true; c.out.clear(); }	/* EPIPE: drop the reply */
 			}
 		}
 		for (size_t i = 0; i < conns.size();) {

@@ -991,7 +991,7 @@ int active_sessions(const std::string &name)
 	if (it == g_servers.end()) return 0;
 	std::lock_guard<std::mutex> lk2(it->second->mu);
 	int n = 0;
-	for (auto &ss : it->second->sessions) n += !ss->done.load() && ss->running;
+	for (auto &ss : it->second->sessions) n += !ss->done.load();	/* every connected master counts (new_connection inserts into vdev->vsessions, vhost.c) */
 	return n;
 }
 

@@ -62,6 +62,10 @@ SYMBOLS = [
     ("oimgpu_bdev_create_malloc", _I, [C.c_char_p, C.c_char_p, _U64, _U32, _I, C.c_char_p, C.c_size_t]),
     ("oimgpu_bdev_create_rbd", _I, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _U32, _U64, _I, C.c_char_p, C.c_size_t]),
     ("oimgpu_bdev_create_mirror", _I, [C.c_char_p, _U64, _U32, C.POINTER(C.c_int), _I, C.c_char_p, C.c_size_t]),
+    ("oimgpu_bdev_export_store", _I, [C.c_char_p, _I, _VP]),
+    ("oimgpu_bdev_create_mirror_remote", _I, [C.c_char_p, _U64, _U32, _I, _VP, _I, C.c_char_p, C.c_size_t]),
+    ("oimgpu_bdev_digest", _I, [C.c_char_p, _I, _U64, _U64, C.POINTER(C.c_uint64)]),
+    ("oimgpu_digest_device", _I, [_I, _VP, _U64, C.POINTER(C.c_uint64)]),
     ("oimgpu_bdev_delete", _I, [C.c_char_p]),
     ("oimgpu_bdev_get", _I, [C.c_char_p, C.POINTER(BdevInfo)]),
     ("oimgpu_bdev_list", _I, [C.POINTER(BdevInfo), _I]),
@@ -174,6 +178,56 @@ def construct_mirror_bdev(num_blocks: int, block_size: int, devices: list[int], 
     _chk(load().oimgpu_bdev_create_mirror(_b(name), num_blocks, block_size, arr, len(devices), out, 64),
          "construct_mirror_bdev")
     return out.value.decode()
+
+
+IPC_HANDLE_BYTES = 64
+
+
+def bdev_export_store(name: str, replica: int = 0) -> bytes:
+    """CUDA IPC handle of a replica's store: what another process needs to mirror onto this GPU"""
+    out = C.create_string_buffer(IPC_HANDLE_BYTES)
+    _chk(load().oimgpu_bdev_export_store(_b(name), replica, out), "bdev_export_store")
+    return out.raw
+
+
+def construct_mirror_bdev_remote(num_blocks: int, block_size: int, device: int, peer_handles: list[bytes],
+                                 name: str | None = None) -> str:
+    """mirror whose replicas 1.. are stores of OTHER processes (one process per GPU), imported by IPC handle"""
+    out = C.create_string_buffer(64)
+    blob = C.create_string_buffer(b"".join(peer_handles), IPC_HANDLE_BYTES * len(peer_handles))
+    _chk(load().oimgpu_bdev_create_mirror_remote(_b(name), num_blocks, block_size, device, blob, len(peer_handles), out, 64),
+         "construct_mirror_bdev_remote")
+    return out.value.decode()
+
+
+def bdev_digest(name: str, replica: int = 0, offset: int = 0, nbytes: int | None = None) -> tuple[int, int]:
+    """position-keyed digest of a store range, computed on the GPU (include/oimgpu.h oimgpu_bdev_digest)"""
+    if nbytes is None:
+        b = get_bdevs(name)[0]
+        nbytes = b["num_blocks"] * b["block_size"] - offset
+    out = (C.c_uint64 * 2)()
+    _chk(load().oimgpu_bdev_digest(_b(name), replica, offset, nbytes, out), "bdev_digest")
+    return int(out[0]), int(out[1])
+
+
+def digest_device(device: int, ptr: int, nbytes: int) -> tuple[int, int]:
+    out = (C.c_uint64 * 2)()
+    _chk(load().oimgpu_digest_device(device, ptr, nbytes, out), "digest_device")
+    return int(out[0]), int(out[1])
+
+
+def digest_host(data: np.ndarray) -> tuple[int, int]:
+    """the same digest over a host array (numpy, wrapping arithmetic): the checker's side"""
+    w = np.ascontiguousarray(data).view(np.uint8).view(np.uint64)
+    with np.errstate(over="ignore"):
+        i = np.arange(len(w), dtype=np.uint64)
+        a = int((w * (np.uint64(2) * i + np.uint64(1))).sum(dtype=np.uint64))
+        z = w ^ i
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        b = int(z.sum(dtype=np.uint64))
+    return a, b
 
 
 def delete_bdev(name: str) -> None:
