@@ -106,7 +106,40 @@ struct KickHeader {
 	 * what the worker CTAs poll; it mirrors the stop flag the same way. */
 	uint32_t dispatcher;
 	volatile uint32_t stop_mirror;
+	/* Queue sharing (fewer queues than CTAs): a queue is no longer owned by one CTA; CTAs claim it a pass at a
+	 * time through share[queue] (struct QShare), so one deep queue - or the <= 254 request queues a vhost-user
+	 * controller can have (S/lib/vhost/vhost_internal.h:63) - still keeps every SM busy. */
+	uint32_t shared;
+	uint32_t pad;
+	struct QShare *share;			/* [nqueues], device memory, zeroed (launch) / preset (poller) by the host */
+	uint32_t workers_exited;		/* persistent + shared: worker CTAs that left; the last one writes the cursors back */
+	uint32_t pad2;
 };
+
+/* Per-queue coordination block of a shared queue.  All positions count requests from where this launch
+ * (or this poller) started on the queue: request x sits at ring position base_avail + x, its completion at
+ * base_used + x.
+ *   claim   handed out so far (CAS)                       -> which CTA serves which pass
+ *   parsed  parse results published, IN RING ORDER        -> a later pass learns whether earlier ones write
+ *   done    completions published, IN RING ORDER          -> used->idx / the host's completion counter stay
+ *                                                            monotonic; a writer can wait for "everything before me"
+ * Ordering between passes of DIFFERENT CTAs is coarse (a pass that writes waits for every earlier foreign pass,
+ * any pass waits for the last foreign pass that wrote); between passes of the SAME CTA the exact wave / drain
+ * logic of the exclusive path applies, so a queue served by one CTA at a time loses nothing. */
+struct QShare {
+	uint32_t claim;
+	uint32_t parsed;
+	uint32_t done;
+	uint32_t wr_end;		/* end position of the last published pass that contains a writer (0: none yet) */
+	uint32_t run_owner;		/* CTA (blockIdx.x + 1) of the current run of consecutively parsed passes */
+	uint32_t run_start;		/* where that run began */
+	uint32_t run_wr;		/* wr_end when it began: the last FOREIGN writer the run has to respect */
+	uint32_t latched;		/* launch + virtqueue: 0 unset, 2 being set, 1 count/base_* valid */
+	uint32_t count;			/* launch mode: requests this launch serves on the queue */
+	uint32_t base_avail, base_used;
+	uint32_t pad[5];
+};
+static_assert(sizeof(QShare) == 64, "QShare is one 64-byte line");
 
 /* ring cursors of an attached virtqueue, device-resident so they survive across launches */
 struct VqState {
@@ -193,6 +226,10 @@ struct __align__(16) Stage {
 	uint32_t drain;			/* d != 0: fill c-d must be finished before flagged units of this one move */
 	uint32_t drain_upfront;		/* ... before anything of this one moves (later fills of a split pass) */
 	uint32_t stop;
+	QShare  *share;			/* shared queue: publish in ring order through share->done (nullptr: exclusive) */
+	uint32_t share_pos;		/* position of this fill's first request */
+	uint32_t share_final;		/* launch + virtqueue: position at which the ring cursors are written back (count) */
+	uint32_t persistent;
 };
 
 /* Store ranges of one pass, for hazard detection against the passes after it (parser-private).
