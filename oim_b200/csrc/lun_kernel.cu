@@ -45,6 +45,46 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		"DONE_%=:\n\t}"
 		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+/* non-blocking: has the phase with this parity completed? */
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		"selp.u32 %0, 1, 0, p;\n\t}"
+		: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+
+/* ---- shared queues: position counters in device memory, handed from CTA to CTA ------------------- */
+
+__device__ __forceinline__ uint32_t ld_acquire32(const uint32_t *p)
+{
+	uint32_t r;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+	return r;
+}
+__device__ __forceinline__ void st_release32(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_vol64(const uint64_t *p)
+{
+	uint64_t r;
+	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+	return r;
+}
+__device__ __forceinline__ void st_vol64(uint64_t *p, uint64_t v)
+{
+	asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+/* wait until the in-order counter reaches exactly `pos` (its predecessor has published) */
+__device__ __forceinline__ void chain_wait(const uint32_t *ctr, uint32_t pos)
+{
+	while (ld_acquire32(ctr) != pos) __nanosleep(20);
+}
+
 __device__ __forceinline__ void movers_barrier()
 {
 	asm volatile("bar.sync 1, %0;" :: "n"(kMovers * 32) : "memory");
@@ -886,11 +926,21 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 			st_cg16(reinterpret_cast<int4 *>(&st.cpl_ring[slot]) + v % 3,
 				reinterpret_cast<const int4 *>(&st.cpl[v / 3])[v % 3]);
 		}
+		if (st.share) {
+			/* shared queue: the completion counter the host polls must stay monotonic, and `done` is what a
+			 * writer of another CTA waits on, so fills publish in ring order */
+			if (lane == 0) chain_wait(&st.share->done, st.share_pos);
+			__syncwarp();
+		}
 		if (st.done) {
 			/* persistent mode: make payload + records visible to the host, then bump the counter it polls */
 			__threadfence_system();
 			__syncwarp();
 			if (lane == 0 && n) *st.done = st.cpl_slot0 + n;
+		}
+		if (st.share) {
+			__syncwarp();
+			if (lane == 0) st_release32(&st.share->done, st.share_pos + n);	/* releases the records written by the whole warp */
 		}
 		return;
 	}
@@ -919,13 +969,26 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 	/* "Ensure the used ring is updated before we ... increment used->idx" (vhost.c:416-417).  Guest memory in
 	 * host RAM needs that at system scope (the guest's CPUs are watching); when the guest image lives in HBM
 	 * the observers are on this GPU and the cheaper scope does */
+	if (st.share) {
+		/* used->idx moves in ring order: wait for the fills before this one (other CTAs') to publish theirs */
+		if (lane == 0) chain_wait(&st.share->done, st.share_pos);
+		__syncwarp();
+	}
 	if (st.vq_in_hbm) __threadfence();
 	else __threadfence_system();
 	__syncwarp();
 	if (lane == 0 && n) {
 		const uint32_t idx = st.used_base + n;
 		*reinterpret_cast<volatile uint16_t *>(st.vq_used + 2) = (uint16_t)idx;
-		st.vq_state->last_used = idx & 0xffff;
+		if (!st.share) st.vq_state->last_used = idx & 0xffff;
+	}
+	if (st.share && lane == 0) {
+		if (!st.persistent && st.share_pos + n == st.share_final) {
+			/* last fill of this launch on the queue: everything before it is published - write the cursors back */
+			st.vq_state->last_avail = (st.share->base_avail + st.share_final) & 0xffff;
+			st.vq_state->last_used = (st.used_base + n) & 0xffff;
+		}
+		st_release32(&st.share->done, st.share_pos + n);
 	}
 }
 
@@ -944,10 +1007,84 @@ static __device__ __forceinline__ void mirror_unit(const LunCtx &L, uint8_t *dst
 	}
 }
 
+/* ---- shared queues: who takes which pass --------------------------------------------------------------- */
+
+/* lane 0: take the next pass (<= 32 requests) of a shared queue.  Returns its length (0: nothing unclaimed right
+ * now) and its position in *pos.  q.head = ring position of position 0; q.count = the launch's limit. */
+__device__ __forceinline__ uint32_t claim_pass(const QueueDesc &q, QShare &qs, bool persistent, bool hinted, uint32_t *pos,
+					       uint32_t *avail_seen)
+{
+	for (;;) {
+		const uint32_t c = ld_vol32(&qs.claim);
+		uint32_t avail;
+		if (!persistent) {
+			avail = q.count - c;
+		} else if (q.mode == QMODE_VRING) {
+			const uint16_t av = hinted ? (uint16_t)ld_vol32(&q.vq_state->hint) : ld_vol16(q.vq_avail + 2);
+			avail = (uint16_t)(av - (uint16_t)(q.head + c));
+			if (avail > q.vq_size) avail = 0;	/* "the queue is unrecoverably broken" */
+		} else {
+			avail = (hinted ? ld_vol32(&q.vq_state->hint) : ld_vol32(q.doorbell)) - (q.head + c);
+		}
+		if (avail == 0) return 0;
+		const uint32_t n = avail < (uint32_t)kPass ? avail : (uint32_t)kPass;
+		if (atomicCAS(&qs.claim, c, c + n) == c) {
+			*pos = c;
+			*avail_seen = avail;	/* positions [c, c + avail) are published: safe to read ahead */
+			return n;
+		}
+	}
+}
+
+/* one lane, one queue: is there something to claim?  A CTA that is not at home on the queue stays away while the
+ * queue is being written: passes of different CTAs are ordered coarsely (see QShare), two CTAs alternating on a
+ * write-heavy queue would mostly wait for each other, and its home CTA serves it at the exclusive path's speed. */
+__device__ __forceinline__ bool shared_queue_has_work(const QueueDesc &q, QShare &qs, bool persistent, bool hinted, bool home)
+{
+	const uint32_t c = ld_vol32(&qs.claim);
+	if (!home) {
+		const uint32_t we = (uint32_t)(ld_vol64(&qs.chain) >> 32);	/* end of the last pass that wrote */
+		if (we != 0 && c - we < 8192u) return false;
+	}
+	if (!persistent) {
+		if (q.mode == QMODE_VRING) {
+			if (ld_vol32(&qs.latched) != 1u) return true;	/* nobody has looked at avail->idx yet */
+			return c < ld_vol32(&qs.count);
+		}
+		return c < q.count;
+	}
+	const uint32_t ring = ld_vol32(&qs.base_avail) + c;
+	if (q.mode == QMODE_VRING) {
+		const uint16_t av = hinted ? (uint16_t)ld_vol32(&q.vq_state->hint) : ld_vol16(q.vq_avail + 2);
+		const uint16_t k = (uint16_t)(av - (uint16_t)ring);
+		return k != 0 && k <= q.vq_size;
+	}
+	return (hinted ? ld_vol32(&q.vq_state->hint) : ld_vol32(q.doorbell)) != ring;
+}
+
+/* warp-wide: first queue with unclaimed work in cyclic order from `from` (0xffffffff: none), 32 queues per step */
+__device__ __forceinline__ uint32_t find_shared_work(const KickHeader *hdr, const QueueDesc *queues, QShare *shares, uint32_t nq,
+						      uint32_t nworkers, uint32_t from, bool persistent, bool hinted, int lane)
+{
+	for (uint32_t base = 0; base < nq; base += 32) {
+		const uint32_t k = base + lane;
+		bool has = false;
+		uint32_t qi = 0;
+		if (k < nq) {
+			qi = from + k;
+			if (qi >= nq) qi -= nq;
+			has = shared_queue_has_work(queues[qi], shares[qi], persistent, hinted, qi % nworkers == blockIdx.x);
+		}
+		const uint32_t m = __ballot_sync(0xffffffffu, has);
+		if (m) return __shfl_sync(0xffffffffu, qi, __ffs(m) - 1);
+	}
+	return 0xffffffffu;
+}
+
 #ifndef OIM_MIN_BLOCKS
 #define OIM_MIN_BLOCKS 2	/* 128 registers: the mover loop must stay spill-free (80-register builds lose ~25%) */
 #endif
-template <bool kMirrored>
+template <bool kMirrored, bool kShared>
 __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1020,12 +1157,44 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		const bool persistent = hdr->persistent != 0;
 		const bool hinted = persistent && hdr->dispatcher != 0;
 		const uint32_t nworkers = hinted ? gridDim.x - 1 : gridDim.x;
+		constexpr bool shared = kShared;	/* compiled out of the one-CTA-per-queue kernels */
+		QShare *const shares = hdr->share;
+		uint32_t scan_from = blockIdx.x % nqueues;	/* shared: where the search for unclaimed work resumes */
+		uint32_t run_q = 0xffffffffu, run_start = 0, run_end = 0, run_wr = 0;	/* shared, lane 0: this CTA's current run */
 		uint32_t sweep_qi = blockIdx.x;
 		bool progress = false;
 		uint64_t last_progress = persistent ? globaltimer_ns() : 0;
 		for (;;) {
 			uint32_t qi = 0;
-			if (!persistent) {
+			if (shared) {
+				/* any queue with unclaimed requests, this CTA's home queue(s) first */
+				qi = find_shared_work(hdr, queues, shares, nqueues, nworkers, scan_from, persistent, hinted, lane);
+				if (qi == 0xffffffffu) {
+					if (!persistent) break;
+					if (progress) {
+						progress = false;
+						last_progress = globaltimer_ns();
+						continue;
+					}
+					/* idle: as below, publish what the pipeline still holds, then stop flag / watchdog */
+					while (reaped < fills) {
+						const uint32_t sidx = reaped % kStages;
+						mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
+						reap_stage(sh.stage[sidx], lane);
+						reaped++;
+					}
+					uint32_t quit = 0;
+					if (lane == 0) {
+						quit = (hinted ? ld_vol32(&hdr->stop_mirror) : ld_vol32(hdr->stop)) != 0;
+						if (!quit && hdr->idle_timeout_ms &&
+						    globaltimer_ns() - last_progress > (uint64_t)hdr->idle_timeout_ms * 1000000ull) quit = 1;
+					}
+					if (__shfl_sync(0xffffffffu, quit, 0)) break;
+					__nanosleep(OIM_IDLE_NS);
+					continue;
+				}
+				scan_from = qi;		/* stay on it while it has work */
+			} else if (!persistent) {
 				/* next queue: first one static (no atomic on the critical path), then work-stealing */
 				if (lane == 0) qi = first ? blockIdx.x : atomicAdd(&hdr->next, 1u);
 				qi = __shfl_sync(0xffffffffu, qi, 0);
@@ -1062,7 +1231,44 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				sweep_qi += nworkers;
 			}
 			QueueDesc q = queues[qi];
-			if (persistent && q.mode == QMODE_SLOTS) {
+			QShare *const qs = shared ? &shares[qi] : nullptr;
+			uint32_t vq_last_avail = 0, vq_last_used = 0;
+			if (shared) {
+				/* positions on a shared queue count from where this launch (this poller) started on it: request x
+				 * sits at ring position base_avail + x, its completion at base_used + x */
+				uint32_t ba = 0, bu = 0, cnt = 0xffffffffu;	/* poller: no fixed count, claims follow the doorbell */
+				if (lane == 0) {
+					if (!persistent && q.mode == QMODE_SLOTS) {
+						ba = q.head;
+						cnt = q.count;
+					} else {
+						if (!persistent) {
+							/* the first CTA on the queue fixes what this launch serves: everything up to avail->idx
+							 * (spdk_vhost_vq_avail_ring_get, vhost.c:178-211); the others wait for its word */
+							if (atomicCAS(&qs->latched, 0u, 2u) == 0u) {
+								const uint32_t la = q.vq_state->last_avail, lu = q.vq_state->last_used;
+								uint32_t c = (uint16_t)(ld_vol16(q.vq_avail + 2) - (uint16_t)la);
+								if (c > q.vq_size) c = 0;	/* "the queue is unrecoverably broken" */
+								qs->base_avail = la; qs->base_used = lu; qs->count = c;
+								st_release32(&qs->latched, 1u);
+							} else {
+								while (ld_acquire32(&qs->latched) != 1u) __nanosleep(20);
+							}
+							cnt = ld_vol32(&qs->count);
+						}
+						ba = ld_vol32(&qs->base_avail);
+						bu = ld_vol32(&qs->base_used);
+					}
+				}
+				q.head = __shfl_sync(0xffffffffu, ba, 0);
+				q.count = __shfl_sync(0xffffffffu, cnt, 0);
+				vq_last_avail = q.head;
+				vq_last_used = __shfl_sync(0xffffffffu, bu, 0);
+				if (q.mode == QMODE_VRING) {
+					q.iov_mask = 0xffffffffu;
+					q.iovs += (size_t)blockIdx.x * kPass * kIovRow;	/* this CTA's scratch SG rows */
+				}
+			} else if (persistent && q.mode == QMODE_SLOTS) {
 				/* new slots = host doorbell (tail) - consumed cursor */
 				uint32_t cnt = 0, consumed = 0;
 				if (lane == 0) {
@@ -1071,9 +1277,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				}
 				q.count = __shfl_sync(0xffffffffu, cnt, 0);
 				q.head = __shfl_sync(0xffffffffu, consumed, 0);
-			}
-			uint32_t vq_last_avail = 0, vq_last_used = 0;
-			if (q.mode == QMODE_VRING) {
+			} else if (q.mode == QMODE_VRING) {
 				/* spdk_vhost_vq_avail_ring_get (vhost.c:178-211): everything up to avail->idx */
 				uint32_t cnt = 0;
 				if (lane == 0) {
@@ -1090,14 +1294,15 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				q.iovs += (size_t)blockIdx.x * kPass * kIovRow;	/* this CTA's scratch SG rows */
 			}
 			const oimgpu_iov *const iov_base = q.iovs;
-			if (persistent) {
+			if (persistent && !shared) {
 				if (q.count == 0) continue;
 				progress = true;
 			}
 			/* request slots are prefetched one pass ahead: 4 x 16 B per lane, coalesced
-			 * (vector v = k*32+lane of the pass -> request v/4, quarter v%4) */
+			 * (vector v = k*32+lane of the pass -> request v/4, quarter v%4).  On a shared queue the next pass
+			 * is not known before it is claimed: there the slots are fetched right after the claim. */
 			int4 pre[4];
-			if (q.count && q.mode == QMODE_SLOTS) {
+			if (!shared && q.count && q.mode == QMODE_SLOTS) {
 				const uint32_t n0 = min((uint32_t)kPass, q.count);
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
@@ -1115,12 +1320,53 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			uint32_t vq_head_cur = 0, vq_head_nxt = 0;
 			int4 vq_raw = make_int4(0, 0, 0, 0);	/* desc[head] of the coming pass, still in flight */
 			const bool vq_tbl_aligned = ((uintptr_t)q.vq_desc & 15) == 0;
-			if (q.count && q.mode == QMODE_VRING && (uint32_t)lane < min((uint32_t)kPass, q.count)) {
+			if (!shared && q.count && q.mode == QMODE_VRING && (uint32_t)lane < min((uint32_t)kPass, q.count)) {
 				vq_head_cur = reinterpret_cast<const uint16_t *>(q.vq_avail + 4)[(q.head + lane) & (q.vq_size - 1)];
 				if (vq_tbl_aligned && vq_head_cur < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_cur * 16);
 			}
-			for (uint32_t done = 0; done < q.count; done += kPass) {
-				const uint32_t n = min((uint32_t)kPass, q.count - done);
+			uint32_t done = 0;	/* position of the current pass on the queue */
+			uint32_t share_guess = 0xffffffffu;	/* shared: position whose slots / heads were read ahead */
+			uint32_t share_guess_n = 0;		/* ... and how many of them */
+			uint32_t share_seen = 0;		/* shared: published requests from `done` on, as of the claim */
+			for (uint32_t it = 0;; it++) {
+				uint32_t n;
+				if (!shared) {
+					if (it) done += kPass;
+					if (done >= q.count) break;
+					n = min((uint32_t)kPass, q.count - done);
+				} else {
+					/* publish whatever the movers have finished: the fills other CTAs took after ours wait for it */
+					while (reaped < fills && mbar_test(&sh.empty[reaped % kStages], (reaped / kStages) & 1)) {
+						reap_stage(sh.stage[reaped % kStages], lane);
+						reaped++;
+					}
+					uint32_t pos = 0, got = 0, seen = 0;
+					if (lane == 0) got = claim_pass(q, *qs, persistent, hinted, &pos, &seen);
+					n = __shfl_sync(0xffffffffu, got, 0);
+					if (n == 0) break;
+					done = __shfl_sync(0xffffffffu, pos, 0);
+					share_seen = __shfl_sync(0xffffffffu, seen, 0);
+					progress = true;
+					/* the pass behind the previous one was read ahead on the guess that nobody else would claim
+					 * in between (true whenever this CTA has the queue to itself): use it if the guess held */
+					const bool guessed = done == share_guess && n <= share_guess_n;	/* (a poller may see more by now) */
+					share_guess = 0xffffffffu;
+					if (guessed) {
+						if (q.mode == QMODE_VRING) vq_head_cur = vq_head_nxt;
+					} else if (q.mode == QMODE_SLOTS) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							const uint32_t v = k * 32 + lane;
+							if ((v >> 2) < n) {
+								const uint32_t slot = (q.head + done + (v >> 2)) & q.ring_mask;
+								pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
+							}
+						}
+					} else if ((uint32_t)lane < n) {
+						vq_head_cur = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(q.head + done + lane) & (q.vq_size - 1)];
+						if (vq_tbl_aligned && vq_head_cur < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_cur * 16);
+					}
+				}
 				const uint32_t slot0 = q.head + done;
 				__syncwarp();
 				if (q.mode == QMODE_SLOTS) {
@@ -1131,13 +1377,16 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					}
 				}
 				__syncwarp();
-				if (q.mode == QMODE_SLOTS && done + kPass < q.count) {
-					const uint32_t n1 = min((uint32_t)kPass, q.count - done - kPass);
+				/* (shared: only what was already published when this pass was claimed may be read ahead) */
+				const uint32_t ahead = shared ? share_seen - n : (done + kPass < q.count ? q.count - done - kPass : 0u);
+				if (shared && ahead) { share_guess = done + n; share_guess_n = min((uint32_t)kPass, ahead); }
+				if (q.mode == QMODE_SLOTS && ahead) {
+					const uint32_t n1 = min((uint32_t)kPass, ahead);
 #pragma unroll
 					for (int k = 0; k < 4; k++) {
 						const uint32_t v = k * 32 + lane;
 						if ((v >> 2) < n1) {
-							const uint32_t slot = (slot0 + kPass + (v >> 2)) & q.ring_mask;
+							const uint32_t slot = (slot0 + n + (v >> 2)) & q.ring_mask;
 							pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
 						}
 					}
@@ -1147,10 +1396,9 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				uint64_t my_resp = 0;
 				uint32_t my_head = 0;
 				bool chain_ok = true;
-				const bool vq_more = q.mode == QMODE_VRING && done + kPass < q.count &&
-						     (uint32_t)lane < min((uint32_t)kPass, q.count - done - kPass);
+				const bool vq_more = q.mode == QMODE_VRING && (uint32_t)lane < min((uint32_t)kPass, ahead);
 				if (vq_more)	/* next pass's avail entries: in flight while this pass is walked */
-					vq_head_nxt = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(slot0 + kPass + lane) & (q.vq_size - 1)];
+					vq_head_nxt = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(slot0 + n + lane) & (q.vq_size - 1)];
 				if (q.mode == QMODE_VRING && active) {
 					my_head = vq_head_cur;
 					VDesc d0 = {0, 0, 0, 0};
@@ -1254,6 +1502,44 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					if (__any_sync(0xffffffffu, hit)) drain = (uint32_t)h;	/* nearest pass wins */
 				}
 				pass_no++;
+
+				if (shared) {
+					/* Passes of other CTAs on this queue.  Parse results are published in ring order; with them
+					 * a pass learns where the current run of passes parsed by ONE CTA began (inside a run the exact
+					 * logic above applies: same parser, same history) and where the last writer before that run
+					 * ended.  A pass that writes waits until everything before its run is complete, a pass that only
+					 * reads until the last foreign writer is.  (spdk_scsi_lun_execute_tasks runs a LUN's tasks one
+					 * after the other, lun.c:163-211: any interleaving that keeps every RAW/WAW/WAR pair in ring
+					 * order gives the same bytes.) */
+					uint32_t need = 0;
+					if (lane == 0) {
+						/* {parsed, wr_end} travel in ONE 64-bit word: nothing else is published with it, so the
+						 * hand-over needs no fence (which would wait for the parser's read-ahead loads) */
+						uint64_t w;
+						while ((uint32_t)(w = ld_vol64(&qs->chain)) != done) __nanosleep(20);
+						const uint32_t we = (uint32_t)(w >> 32);
+						/* a run = passes this CTA took back to back (nobody else claimed in between): known locally */
+						if (run_q != qi || run_end != done) { run_q = qi; run_start = done; run_wr = we; }
+						run_end = done + n;
+						st_vol64(&qs->chain, (uint64_t)(writers ? done + n : we) << 32 | (uint64_t)(done + n));
+						need = writers ? run_start : run_wr;
+						if (need && (int32_t)(ld_acquire32(&qs->done) - need) >= 0) need = 0;
+					}
+					need = __shfl_sync(0xffffffffu, need, 0);
+					if (need) {
+						/* our own fills first: the positions waited for may be behind some of them in the chain */
+						while (reaped < fills) {
+							const uint32_t sidx = reaped % kStages;
+							mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
+							reap_stage(sh.stage[sidx], lane);
+							reaped++;
+						}
+						if (lane == 0) {
+							while ((int32_t)(ld_acquire32(&qs->done) - need) < 0) __nanosleep(40);
+						}
+						__syncwarp();
+					}
+				}
 
 				/* hazards inside the pass -> waves.  Writers are visited in ring order; a writer is
 				 * pushed behind every earlier request it overlaps, every later overlapping request
@@ -1381,6 +1667,10 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						st.vq_in_hbm = q.vq_in_hbm;
 						st.used_base = vq_last_used + done + r0;
 						st.done = persistent ? q.done : nullptr;
+						st.share = qs;
+						st.share_pos = done + r0;
+						st.share_final = q.count;
+						st.persistent = persistent;
 					}
 					__syncwarp();
 					if (lane == 0) mbar_arrive(&sh.full[sidx]);
@@ -1389,8 +1679,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				}
 				vq_head_cur = vq_head_nxt;
 			}
-			if (q.mode == QMODE_VRING && lane == 0) q.vq_state->last_avail = (vq_last_avail + q.count) & 0xffff;
-			if (persistent && q.mode == QMODE_SLOTS && lane == 0) q.vq_state->last_avail = q.head + q.count;
+			if (!shared && q.mode == QMODE_VRING && lane == 0) q.vq_state->last_avail = (vq_last_avail + q.count) & 0xffff;
+			if (!shared && persistent && q.mode == QMODE_SLOTS && lane == 0) q.vq_state->last_avail = q.head + q.count;
 		}
 		/* tell the movers to stop, then publish the completions still in flight */
 		{
@@ -1402,7 +1692,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				reaped++;
 				__syncwarp();
 			}
-			if (lane == 0) { st.stop = 1; st.nunits = 0; st.nseg = 0; st.nwaves = 1; st.drain = 0; st.ncpl = 0; st.mode = QMODE_SLOTS; st.done = nullptr; }
+			if (lane == 0) { st.stop = 1; st.nunits = 0; st.nseg = 0; st.nwaves = 1; st.drain = 0; st.ncpl = 0; st.mode = QMODE_SLOTS; st.done = nullptr; st.share = nullptr; }
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&sh.full[sidx]);
 		}
@@ -1411,6 +1701,25 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
 			reap_stage(sh.stage[sidx], lane);
 			reaped++;
+		}
+		if (persistent && shared) {
+			/* the last worker to leave writes the ring cursors back: by then every claimed pass is published */
+			uint32_t last = 0;
+			if (lane == 0) last = atomicAdd(&hdr->workers_exited, 1u) == nworkers - 1;
+			if (__shfl_sync(0xffffffffu, last, 0)) {
+				__threadfence();
+				for (uint32_t k = lane; k < nqueues; k += 32) {
+					const QueueDesc &d = queues[k];
+					const uint32_t c = ld_vol32(&shares[k].claim);
+					if (d.mode == QMODE_VRING) {
+						d.vq_state->last_avail = (ld_vol32(&shares[k].base_avail) + c) & 0xffff;
+						d.vq_state->last_used = (ld_vol32(&shares[k].base_used) + c) & 0xffff;
+					} else {
+						d.vq_state->last_avail = ld_vol32(&shares[k].base_avail) + c;
+					}
+				}
+				__threadfence();
+			}
 		}
 		if (persistent && lane == 0) {
 			__threadfence_system();
@@ -1489,17 +1798,30 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 }
 
 /* the plain kernel carries no mirror code at all (a call in the mover loop costs it ~25 %: the
- * caller-saved data registers get spilled); mirrored bdevs use the second instantiation */
+ * caller-saved data registers get spilled); mirrored bdevs use the second instantiation.  Likewise queue
+ * sharing (KickHeader::shared) has its own pair, so the one-CTA-per-queue kernels carry none of its code. */
 __global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
 oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
-	lun_queue_body<false>(lun, hdr, queues);
+	lun_queue_body<false, false>(lun, hdr, queues);
 }
 
 __global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
 oim_lun_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
-	lun_queue_body<true>(lun, hdr, queues);
+	lun_queue_body<true, false>(lun, hdr, queues);
+}
+
+__global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
+oim_lun_shared_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
+{
+	lun_queue_body<false, true>(lun, hdr, queues);
+}
+
+__global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
+oim_lun_shared_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
+{
+	lun_queue_body<true, true>(lun, hdr, queues);
 }
 
 /* struct spdk_copy_engine.copy / .fill (S/include/spdk_internal/copy_engine.h:47-53) for

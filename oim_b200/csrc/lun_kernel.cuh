@@ -121,23 +121,21 @@ struct KickHeader {
  * base_used + x.
  *   claim   handed out so far (CAS)                       -> which CTA serves which pass
  *   parsed  parse results published, IN RING ORDER        -> a later pass learns whether earlier ones write
+ *           (low half of `chain`)
  *   done    completions published, IN RING ORDER          -> used->idx / the host's completion counter stay
  *                                                            monotonic; a writer can wait for "everything before me"
  * Ordering between passes of DIFFERENT CTAs is coarse (a pass that writes waits for every earlier foreign pass,
  * any pass waits for the last foreign pass that wrote); between passes of the SAME CTA the exact wave / drain
  * logic of the exclusive path applies, so a queue served by one CTA at a time loses nothing. */
 struct QShare {
+	uint64_t chain;			/* low 32 bits: `parsed`; high 32 bits: end of the last parsed pass that contains a
+					 * writer (0: none yet).  One word, one store: see the parser */
 	uint32_t claim;
-	uint32_t parsed;
 	uint32_t done;
-	uint32_t wr_end;		/* end position of the last published pass that contains a writer (0: none yet) */
-	uint32_t run_owner;		/* CTA (blockIdx.x + 1) of the current run of consecutively parsed passes */
-	uint32_t run_start;		/* where that run began */
-	uint32_t run_wr;		/* wr_end when it began: the last FOREIGN writer the run has to respect */
 	uint32_t latched;		/* launch + virtqueue: 0 unset, 2 being set, 1 count/base_* valid */
 	uint32_t count;			/* launch mode: requests this launch serves on the queue */
 	uint32_t base_avail, base_used;
-	uint32_t pad[5];
+	uint32_t pad[8];
 };
 static_assert(sizeof(QShare) == 64, "QShare is one 64-byte line");
 

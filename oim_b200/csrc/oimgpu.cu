@@ -30,6 +30,8 @@
 namespace oimgpu {
 __global__ void oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_lun_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
+__global__ void oim_lun_shared_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
+__global__ void oim_lun_shared_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_copy_kernel(uint8_t *dst, const uint8_t *src, uint64_t nbytes);
 __global__ void oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes);
 size_t lun_kernel_smem_bytes();
@@ -153,6 +155,8 @@ struct oimgpu_lun {
 	uint64_t kicks = 0;
 	uint8_t *d_kick = nullptr;
 	QueueDesc *d_desc = nullptr;
+	QShare *d_share = nullptr;		/* [3 x num_queues] coordination blocks of shared queues (lun_kernel.cuh) */
+	uint64_t shared_launches = 0;
 	uint64_t launches = 0;
 	int grid_cap = 0;
 	/* staged batch path (oimgpu_submit_batch with host arrays): metadata is uploaded by the copy
@@ -1025,6 +1029,7 @@ static void free_lun_resources(oimgpu_lun *L)
 		if (L->kick_ev[k]) cudaEventDestroy(L->kick_ev[k]);
 	}
 	cudaFree(L->d_kick);
+	cudaFree(L->d_share);
 	cudaFree(L->d_vq_state);
 	cudaFree(L->d_iov_scratch);
 	cudaFree(L->bs_d_reqs);
@@ -1106,6 +1111,7 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	}
 	CU_OK(cudaMalloc((void **)&L->d_kick, sizeof(KickHeader) + sizeof(QueueDesc) * num_queues * 3));	/* ring + device-array + virtqueue per queue */
 	L->d_desc = (QueueDesc *)(L->d_kick + sizeof(KickHeader));
+	CU_OK(cudaMalloc((void **)&L->d_share, sizeof(QShare) * num_queues * 3));
 	L->queues.resize(num_queues);
 	/* one mapped pinned slab per LUN, carved into per-queue rings: the "virtqueues" */
 	const size_t per_q = sizeof(oimgpu_req) * queue_size + sizeof(oimgpu_iov) * L->iov_cap + sizeof(oimgpu_cpl) * queue_size;
@@ -1138,6 +1144,8 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	/* more than the 48 KB a kernel gets without asking */
 	CU_OK(cudaFuncSetAttribute(oim_lun_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
 	CU_OK(cudaFuncSetAttribute(oim_lun_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
+	CU_OK(cudaFuncSetAttribute(oim_lun_shared_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
+	CU_OK(cudaFuncSetAttribute(oim_lun_shared_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
 	int per_sm = 0;
 	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes()));
 	if (per_sm < 1) per_sm = 1;
@@ -1273,6 +1281,16 @@ extern "C" int oimgpu_submit_device(oimgpu_lun *L, uint32_t q, const oimgpu_req 
 	return 0;
 }
 
+static void launch_lun_kernel(oimgpu_lun *L, uint32_t grid, bool shared)
+{
+	const size_t smem = lun_kernel_smem_bytes();
+	KickHeader *kh = (KickHeader *)L->d_kick;
+	if (shared && L->any_mirror) oim_lun_shared_queue_mirror_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
+	else if (shared) oim_lun_shared_queue_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
+	else if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
+	else oim_lun_queue_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
+}
+
 extern "C" int oimgpu_kick(oimgpu_lun *L)
 {
 	if (!L) return -EINVAL;
@@ -1297,11 +1315,14 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	if (L->kicks >= (uint64_t)oimgpu_lun::kKickSlots) CU_OK(cudaEventSynchronize(L->kick_ev[slot]));
 	QueueDesc *h_desc = (QueueDesc *)(L->h_kick[slot] + sizeof(KickHeader));
 	uint32_t nd = 0;
+	uint64_t passes = 0;	/* passes of <= 32 requests this kick will take (virtqueues: at most a ring full) */
 	for (uint32_t q = 0; q < L->num_queues; q++) {
 		Queue &Q = L->queues[q];
 		if (Q.dev_count) {
+			passes += (Q.dev_count + kPass - 1) / kPass;
 			QueueDesc &D = h_desc[nd++];
 			memset(&D, 0, sizeof(D));
+			D.vq_state = L->d_vq_state + q;
 			D.reqs = Q.dev_reqs;
 			D.iovs = Q.dev_iovs;
 			D.cpls = Q.dev_cpls ? Q.dev_cpls : Q.d_cpls;
@@ -1313,6 +1334,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 			Q.dev_count = 0;
 		}
 		if (Q.vq_pending) {
+			passes += (Q.vq_size + kPass - 1) / kPass;
 			QueueDesc &D = h_desc[nd++];
 			memset(&D, 0, sizeof(D));
 			D.mode = QMODE_VRING;
@@ -1326,8 +1348,10 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 			Q.vq_pending = false;
 		}
 		if (Q.tail != Q.kicked) {
+			passes += (Q.tail - Q.kicked + kPass - 1) / kPass;
 			QueueDesc &D = h_desc[nd++];
 			memset(&D, 0, sizeof(D));
+			D.vq_state = L->d_vq_state + q;
 			D.reqs = Q.d_reqs;
 			D.iovs = Q.d_iovs;
 			D.cpls = Q.d_cpls;
@@ -1339,16 +1363,25 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 		}
 	}
 	if (nd == 0) return 0;
-	const uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap);
+	/* One CTA per queue while there are at least as many queues as the GPU holds CTAs; with fewer queues the
+	 * CTAs SHARE them, a pass at a time (KickHeader::shared), so that a single deep queue - or the <= 254
+	 * request queues of a vhost controller - still fills the machine. */
+	const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nd, passes), (uint64_t)L->grid_cap);
+	const bool shared = nd < grid && !getenv("OIMGPU_NO_SHARED_QUEUES");
 	KickHeader *kh = (KickHeader *)L->h_kick[slot];
 	memset(kh, 0, sizeof(*kh));	/* run-to-completion: persistent = 0 (the staging buffer is recycled pinned memory) */
 	kh->next = grid;	/* queues 0..grid-1 are taken statically by CTA index */
 	kh->nqueues = nd;
+	if (shared) {
+		kh->shared = 1;
+		kh->share = L->d_share;
+		CU_OK(cudaMemsetAsync(L->d_share, 0, sizeof(QShare) * nd, L->stream));
+		L->shared_launches++;
+	}
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
 	L->kicks++;
-	if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
-	else oim_lun_queue_kernel<<<grid, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	launch_lun_kernel(L, grid, shared);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->done, L->stream));
 	L->launches++;
@@ -1912,10 +1945,28 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 	 * every doorbell starts at "nothing new" */
 	for (uint32_t q = 0; q < L->num_queues; q++) cursors[q].hint = cursors[q].last_avail;
 	CU_OK(h2d_sync(L, L->d_vq_state, cursors.data(), sizeof(VqState) * L->num_queues));
-	/* worker CTAs + one dispatcher CTA (KickHeader::dispatcher) */
-	uint32_t grid = std::min<uint32_t>(nd, (uint32_t)L->grid_cap - 1);
+	/* worker CTAs + one dispatcher CTA (KickHeader::dispatcher).  With fewer queues than that, the workers share
+	 * the queues a pass at a time: up to a ring's worth of passes per queue can be in flight at once. */
+	uint64_t want = 0;
+	for (uint32_t q = 0; q < L->num_queues; q++) {
+		const uint32_t depth = L->queues[q].vq_size ? L->queues[q].vq_size : L->queue_size;
+		want += std::max<uint32_t>(1, std::min<uint32_t>(8, (depth + kPass - 1) / kPass));
+	}
+	uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nd, want), (uint64_t)L->grid_cap - 1);
 	if (max_ctas) grid = std::min(grid, max_ctas);
 	if (grid == 0) grid = 1;
+	const bool shared = nd < grid && !getenv("OIMGPU_NO_SHARED_QUEUES");
+	if (!shared) grid = std::min(grid, nd);
+	if (shared) {
+		std::vector<QShare> sh(nd);
+		memset(sh.data(), 0, sizeof(QShare) * nd);
+		for (uint32_t k = 0; k < nd; k++) {	/* descriptor k = queue k here: one descriptor per queue */
+			sh[k].base_avail = cursors[k].last_avail;
+			sh[k].base_used = cursors[k].last_used;
+			sh[k].latched = 1;
+		}
+		CU_OK(h2d_sync(L, L->d_share, sh.data(), sizeof(QShare) * nd));
+	}
 	L->h_flags[0] = 0;
 	L->h_flags[16] = 0;
 	KickHeader *kh = (KickHeader *)L->h_kick[slot];
@@ -1927,9 +1978,10 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 	kh->stop = L->d_flags;
 	kh->exited = L->d_flags + 16;
 	kh->dispatcher = 1;
+	kh->shared = shared ? 1 : 0;
+	kh->share = shared ? L->d_share : nullptr;
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
-	if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid + 1, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
-	else oim_lun_queue_kernel<<<grid + 1, kThreads, lun_kernel_smem_bytes(), L->stream>>>(L->d_ctx, (KickHeader *)L->d_kick, L->d_desc);
+	launch_lun_kernel(L, grid + 1, shared);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
 	L->kicks++;

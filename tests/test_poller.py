@@ -45,7 +45,7 @@ def test_poller_serves_ring_doorbells(gpu, oracles):
         per_q = 32 * rounds
         got = np.zeros(len(t.reqs), dtype=abi.cpl_dtype)
         with gpu.Lun("pl0.ctl", 0, num_queues=nq, queue_size=64) as lun:
-            assert lun.start_poller(idle_timeout_ms=WATCHDOG_MS) == nq
+            assert lun.start_poller(idle_timeout_ms=WATCHDOG_MS) >= nq      # workers: one per queue, more when they share queues
             launches_before = None
             try:
                 for r in range(rounds):
