@@ -39,9 +39,10 @@ def parse_args():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    # 1024 queues x 4096 requests = the 2^22-request C2 trace of SURVEY.md 8(d) per step
-    p.add_argument("--queues", type=int, default=int(os.environ.get("OIM_BENCH_QUEUES", 1024)))
-    p.add_argument("--per-queue", type=int, default=int(os.environ.get("OIM_BENCH_PER_QUEUE", 4096)))
+    # 254 request queues = the most a vhost-scsi controller can have (256 virtqueues minus control and event queue,
+    # S/lib/vhost/vhost_internal.h:63, rte_vhost/vhost.h:130) x 16512 requests ~ the 2^22-request C2 trace of SURVEY.md 8(d)
+    p.add_argument("--queues", type=int, default=int(os.environ.get("OIM_BENCH_QUEUES", 254)))
+    p.add_argument("--per-queue", type=int, default=int(os.environ.get("OIM_BENCH_PER_QUEUE", 16512)))
     p.add_argument("--seq-queues", type=int, default=256)
     p.add_argument("--seq-per-queue", type=int, default=256)
     p.add_argument("--e2e-queues", type=int, default=256)
@@ -55,6 +56,8 @@ def parse_args():
     p.add_argument("--no-mixed", action="store_true", help="skip the 70/30 mixed leg (config 4 shape)")
     p.add_argument("--no-lat", action="store_true", help="skip the single-queue qd=32 closed-loop leg")
     p.add_argument("--no-vu", action="store_true", help="skip the leg through the daemon's vhost-user socket")
+    p.add_argument("--no-numa", action="store_true", help="do not bind the rank to the GPU's NUMA node")
+    p.add_argument("--no-sweep", action="store_true", help="skip the queue-count sweep (1..1024 request queues)")
     p.add_argument("--no-mirror", action="store_true", help="skip the mirrored-bdev leg (config 5; runs when --gpus >= 2)")
     p.add_argument("--no-extra", action="store_true", help="skip the 4 KiB random-write / 128 KiB sequential-read legs")
     return p.parse_args()
@@ -465,6 +468,9 @@ def mirror_leg(args, rank, world, local, lib, torch, timer, barrier, max_over_ra
 
 
 def run_ours(args, rank, world, local):
+    # host side of the PCIe paths: this rank's CPU threads and pinned memory on the GPU's own NUMA node
+    from oim_b200 import hostmem
+    placement = hostmem.bind_to_gpu_node(local) if not args.no_numa else {"note": "--no-numa"}
     import torch
     torch.cuda.set_device(local)
     torch.zeros(1, device="cuda")
@@ -498,7 +504,7 @@ def run_ours(args, rank, world, local):
     nq, per_q = args.queues, args.per_queue
     # two handles on the same target: the resident legs use caller-owned HBM arrays (tiny rings),
     # the e2e leg uses the library's host-visible rings
-    lun = lib.Lun(plan["ctrlr"], plan["target"], num_queues=max(nq, args.seq_queues), queue_size=32)
+    lun = lib.Lun(plan["ctrlr"], plan["target"], num_queues=max(nq, args.seq_queues, 1024), queue_size=32)
     lun_e2e = lib.Lun(plan["ctrlr"], plan["target"], num_queues=args.e2e_queues, queue_size=1024)
     device_pattern_fill(lun, store_ptr, NUM_BLOCKS * BLOCK, plan["store_seed"], torch)
     timer = lib.Timer()
@@ -561,6 +567,21 @@ def run_ours(args, rank, world, local):
     achieved = 2 * 4096 * n / (per_launch_ms / 1e3) / 1e9
     out["rand4k"] = (iops, ms / args.steps, launches)
 
+    # ---- what a guest with 1 .. 254 request queues gets (and 1024 library rings, beyond what vhost-user can carry) ----
+    sweep = None
+    if not args.no_sweep:
+        sweep = {"workload": "4 KiB random read, everything resident in HBM, 2^20 requests per step spread over Q request "
+                             "queues, one launch per step; with fewer queues than the GPU holds CTAs (296) the CTAs share "
+                             "the queues a pass of 32 at a time (KickHeader::shared)", "queues": {}}
+        s0 = lun.shared_launches
+        for q in (1, 2, 4, 8, 16, 64, 254, 1024):
+            pq = max(32, (1 << 20) // q // 32 * 32)
+            sn, sms, _, _ = resident_leg(8, "randread", "single", q, pq, max(3, args.steps // 2), 2, None)
+            v = aggregate(sn, max(3, args.steps // 2), world, sms)
+            sweep["queues"][str(q)] = {"value": v, "unit": "IOPS", "hbm_frac": 2 * 4096 * v / world / 1e9 / peak,
+                                       "requests_per_step": sn}
+        sweep["shared_queue_launches"] = lun.shared_launches - s0
+
     # ---- e2e: host request arrays through the C ABI, client buffers in pinned host memory ----
     e2e = None
     if not args.no_e2e:
@@ -606,7 +627,21 @@ def run_ours(args, rank, world, local):
         got = host[:4096].numpy()
         lba0 = int.from_bytes(bytes(t.reqs["cdb"][0][2:6]), "big")
         assert (got == traces.pattern_bytes(plan["store_seed"], lba0 * BLOCK, 4096)).all()
-        e2e = {"value": en * args.steps * world / wall, "unit": "IOPS",
+        # the box's host-side ceiling with every rank storing into host memory at once (explains e2e at N > 1)
+        probe = hostmem.concurrent_d2h_probe(torch, local, barrier)
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([probe["copy_engine_gbs"], probe["sm_stores_gbs"]], dtype=torch.float64, device="cuda")
+            allp = [torch.empty_like(tt) for _ in range(world)]
+            dist.all_gather(allp, tt)
+            per_rank = [[float(x[0]), float(x[1])] for x in allp]
+        else:
+            per_rank = [[probe["copy_engine_gbs"], probe["sm_stores_gbs"]]]
+        ceiling = {"copy_engine_gbs_total": sum(p[0] for p in per_rank), "sm_stores_gbs_total": sum(p[1] for p in per_rank),
+                   "copy_engine_gbs_per_gpu": [round(p[0], 1) for p in per_rank], "sm_stores_gbs_per_gpu": [round(p[1], 1) for p in per_rank],
+                   "how": "all ranks at once for 0.4 s each: cudaMemcpyAsync D2H and oim_copy_kernel stores of 256 MiB into this rank's "
+                          "pinned buffer (oim_b200/hostmem.py; tools/pcie_concurrent_probe.py runs the same with and without binding)"}
+        e2e = {"value": en * args.steps * world / wall, "unit": "IOPS", "host_placement": placement, "host_ceiling": ceiling,
                "h2d_bytes_per_step": int(en * 64 + len(iovs) * 16),
                "d2h_bytes_per_step": int(en * 4096 + en * 48),
                "ms_per_step": wall / args.steps * 1e3, "requests_per_step": en, "queues": eq,
@@ -746,6 +781,19 @@ def run_ours(args, rank, world, local):
                "requests_per_step": n2, "queues": sq,
                "volume": "construct_rbd_bdev (Ceph RBD emulated in HBM), target 1 of the benchmark controller"}
 
+    # ---- the same 128 KiB sequential write with the other two SG shapes ----
+    seq_sg = None
+    if not args.no_seq and not args.no_extra:
+        seq_sg = {}
+        for sg_name, label in (("single", "1 x 131072 B"),
+                               ("unaligned", "33 elements: 100 B + 31 x 4096 B + 3996 B (byte-granular head and tail, client "
+                                             "buffers aligned like the store)"),
+                               ("unaligned+3", "the same 33 elements with every client buffer 3 bytes off the store's "
+                                               "16-byte alignment (funnel-shift realignment in the movers)")):
+            n5, ms5, _, _ = resident_leg(256, "seqwrite", sg_name, args.seq_queues, args.seq_per_queue, args.steps, args.warmup, None, target=1)
+            g5 = n5 * args.steps * world * 131072 / (ms5 / 1e3) / 1e9
+            seq_sg[sg_name] = {"value": g5, "unit": "GB/s", "hbm_frac": 2 * g5 / world / peak, "sg": label}
+
     # ---- the other two corners of the same shapes: 4 KiB random WRITE, 128 KiB sequential READ ----
     extra = None
     if not args.no_extra:
@@ -798,6 +846,8 @@ def run_ours(args, rank, world, local):
             "config": {"workload": f"C2: one 8 GiB HBM Malloc bdev per GPU, 4 KiB random read, qd=32 per request "
                                    f"queue x {nq} queues, {per_q} requests/queue/step",
                        "queues": nq, "per_queue": per_q, "requests_per_step_per_gpu": n,
+                       "queue_limit": "254 request queues = the most one vhost-scsi controller can carry "
+                                      "(S/lib/vhost/vhost_internal.h:63); queue_sweep has 1..1024",
                        "l2": "inputs larger than L2: 8 GiB store + unique 4 KiB client buffer per request "
                              f"({n * 4096 >> 20} MiB) per step"},
             "gpu_launches": launches, "clocks": clocks,
@@ -806,7 +856,7 @@ def run_ours(args, rank, world, local):
                          "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
             "seq128k": seq, "virtqueue": vq, "mixed_70_30": mixed, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
-            "vhost_user": vuser, "more": extra, "mirror": mirror,
+            "vhost_user": vuser, "more": extra, "mirror": mirror, "queue_sweep": sweep, "seq128k_sg": seq_sg,
         }
         print(json.dumps(line))
     if world > 1:

@@ -249,6 +249,9 @@ int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t num_queues,
 		    uint32_t queue_size, oimgpu_lun **out);
 int oimgpu_lun_close(oimgpu_lun *lun);
 int oimgpu_lun_device(const oimgpu_lun *lun);
+/* launches so far in which the CTAs SHARED the queues a pass at a time (fewer queues than the GPU holds CTAs)
+ * instead of owning one queue each; diagnostics for tests and the bench */
+long long oimgpu_lun_shared_launches(const oimgpu_lun *lun);
 
 /* Pin + map a host buffer so SG elements may point into it (OIMGPU_MEM_HOST).  The analogue of
  * spdk_mem_register() on the guest's memory table (S/lib/vhost/vhost.c:1044-1100). */
@@ -338,6 +341,24 @@ void oimgpu_timer_destroy(void *start, void *stop);
  * stream; completion is observed with oimgpu_lun_sync(). */
 int oimgpu_copy_submit(oimgpu_lun *lun, void *dst, const void *src, uint64_t nbytes);
 int oimgpu_fill_submit(oimgpu_lun *lun, void *dst, uint8_t fill, uint64_t nbytes);
+
+/* The same operator as an ASYNCHRONOUS engine without a LUN behind it - what a `struct spdk_copy_engine`
+ * implementation needs (S/include/spdk_internal/copy_engine.h:47-53; model: the I/OAT engine,
+ * S/lib/copy/ioat/copy_engine_ioat.c:159-221: submit returns at once, a poller on the channel's thread reaps
+ * completions and calls the callbacks).  integration/spdk/copy_engine_oimgpu.c is that implementation.
+ * Pointers may be device memory or host memory; host memory is pinned for the GPU on first use
+ * (oimgpu_mem_ensure), the way SPDK's env layer registers its DMA memory with a device's IOMMU. */
+typedef struct oimgpu_copy_chan oimgpu_copy_chan;
+int oimgpu_copy_chan_open(int device, oimgpu_copy_chan **out);		/* device < 0: the first initialised GPU */
+int oimgpu_copy_chan_close(oimgpu_copy_chan *chan);			/* waits for what is in flight */
+int oimgpu_copy_chan_copy(oimgpu_copy_chan *chan, void *dst, const void *src, uint64_t nbytes, void *tag);
+int oimgpu_copy_chan_fill(oimgpu_copy_chan *chan, void *dst, uint8_t fill, uint64_t nbytes, void *tag);
+/* completed operations in submission order: their tags; returns how many (<= max), 0 if none yet */
+int oimgpu_copy_chan_poll(oimgpu_copy_chan *chan, void **tags, int max);
+unsigned long long oimgpu_copy_chan_launches(const oimgpu_copy_chan *chan);	/* kernels launched so far */
+/* make [addr, addr+len) of ordinary host memory accessible to the GPUs (page-granular, idempotent, already
+ * registered parts are skipped); -EFAULT if the range cannot be pinned */
+int oimgpu_mem_ensure(const void *addr, size_t len);
 
 #ifdef __cplusplus
 }

@@ -917,8 +917,11 @@ static_assert(kSigBits == 1 << 12, "sig_index produces 12 bits");
 /* ---- the kernel ----------------------------------------------------------------------------- */
 
 /* parser side: publish the completions of the fill that occupied `st` (all movers are done with it) */
-__device__ __forceinline__ void reap_stage(Stage &st, int lane)
+/* pub_q / pub_end (shared kernels): the queue and end position this CTA published last - a fill that starts right
+ * there has nothing of anybody else's to wait for */
+__device__ __forceinline__ void reap_stage(Stage &st, int lane, QShare **pub_q = nullptr, uint32_t *pub_end = nullptr)
 {
+	const bool follows_own = pub_q && st.share && *pub_q == st.share && *pub_end == st.share_pos;
 	const uint32_t n = st.ncpl;
 	if (st.mode == QMODE_SLOTS) {
 		for (uint32_t v = lane; v < n * 3; v += 32) {
@@ -929,7 +932,7 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 		if (st.share) {
 			/* shared queue: the completion counter the host polls must stay monotonic, and `done` is what a
 			 * writer of another CTA waits on, so fills publish in ring order */
-			if (lane == 0) chain_wait(&st.share->done, st.share_pos);
+			if (lane == 0 && !follows_own) chain_wait(&st.share->done, st.share_pos);
 			__syncwarp();
 		}
 		if (st.done) {
@@ -940,7 +943,10 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 		}
 		if (st.share) {
 			__syncwarp();
-			if (lane == 0) st_release32(&st.share->done, st.share_pos + n);	/* releases the records written by the whole warp */
+			if (lane == 0) {
+				st_release32(&st.share->done, st.share_pos + n);	/* releases the records written by the whole warp */
+				if (pub_q) { *pub_q = st.share; *pub_end = st.share_pos + n; }
+			}
 		}
 		return;
 	}
@@ -971,7 +977,7 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 	 * the observers are on this GPU and the cheaper scope does */
 	if (st.share) {
 		/* used->idx moves in ring order: wait for the fills before this one (other CTAs') to publish theirs */
-		if (lane == 0) chain_wait(&st.share->done, st.share_pos);
+		if (lane == 0 && !follows_own) chain_wait(&st.share->done, st.share_pos);
 		__syncwarp();
 	}
 	if (st.vq_in_hbm) __threadfence();
@@ -989,6 +995,7 @@ __device__ __forceinline__ void reap_stage(Stage &st, int lane)
 			st.vq_state->last_used = (st.used_base + n) & 0xffff;
 		}
 		st_release32(&st.share->done, st.share_pos + n);
+		if (pub_q) { *pub_q = st.share; *pub_end = st.share_pos + n; }
 	}
 }
 
@@ -999,10 +1006,10 @@ static __device__ __forceinline__ void mirror_unit(const LunCtx &L, uint8_t *dst
 						uint32_t nbytes, int lane, uint32_t nrep)
 {
 	const uint64_t soff = (uint64_t)(dst - L.store[0]) + off;
-	if (src) move_unit(dst + off, src + off, nbytes, lane, L.store[1] + soff);
+	if (src) move_unit<true>(dst + off, src + off, nbytes, lane, L.store[1] + soff);
 	else { zero_unit(dst + off, nbytes, lane); zero_unit(L.store[1] + soff, nbytes, lane); }
 	for (uint32_t rep = 2; rep < nrep; rep++) {
-		if (src) move_unit(L.store[rep] + soff, src + off, nbytes, lane);
+		if (src) move_unit_call(L.store[rep] + soff, src + off, nbytes, lane);
 		else zero_unit(L.store[rep] + soff, nbytes, lane);
 	}
 }
@@ -1011,8 +1018,7 @@ static __device__ __forceinline__ void mirror_unit(const LunCtx &L, uint8_t *dst
 
 /* lane 0: take the next pass (<= 32 requests) of a shared queue.  Returns its length (0: nothing unclaimed right
  * now) and its position in *pos.  q.head = ring position of position 0; q.count = the launch's limit. */
-__device__ __forceinline__ uint32_t claim_pass(const QueueDesc &q, QShare &qs, bool persistent, bool hinted, uint32_t *pos,
-					       uint32_t *avail_seen)
+__device__ __forceinline__ uint32_t claim_pass(const QueueDesc &q, QShare &qs, bool persistent, bool hinted, uint32_t *pos)
 {
 	for (;;) {
 		const uint32_t c = ld_vol32(&qs.claim);
@@ -1030,7 +1036,6 @@ __device__ __forceinline__ uint32_t claim_pass(const QueueDesc &q, QShare &qs, b
 		const uint32_t n = avail < (uint32_t)kPass ? avail : (uint32_t)kPass;
 		if (atomicCAS(&qs.claim, c, c + n) == c) {
 			*pos = c;
-			*avail_seen = avail;	/* positions [c, c + avail) are published: safe to read ahead */
 			return n;
 		}
 	}
@@ -1131,7 +1136,10 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		for (int s = 0; s < kStages; s++) {
 			mbar_init(&sh.full[s], 1);
 			mbar_init(&sh.empty[s], kMovers);
+			mbar_init(&sh.released[s], 1);
 		}
+		sh.pub_q = nullptr;
+		sh.pub_end = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -1152,6 +1160,19 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		uint32_t st_rd = 0, st_wr = 0, st_um = 0, st_er = 0;
 		unsigned long long st_rb = 0, st_wb = 0, st_ub = 0;
 		bool first = true;
+		/* Who publishes a fill's completions.  One CTA per queue: the parser, when it needs the stage again.
+		 * Shared queues: completions are published in ring order ACROSS CTAs, so a fill that waits for the
+		 * parser's convenience holds up every later pass of the queue - there mover warp 0 publishes as soon as
+		 * the movers are done with the fill, and the parser only waits for the stage to be released. */
+		auto retire = [&](uint32_t f) {
+			const uint32_t sidx_ = f % kStages;
+			if constexpr (kShared) {
+				mbar_wait(&sh.released[sidx_], (f / kStages) & 1);
+			} else {
+				mbar_wait(&sh.empty[sidx_], (f / kStages) & 1);
+				reap_stage(sh.stage[sidx_], lane);
+			}
+		};
 
 		const uint32_t nqueues = hdr->nqueues;
 		const bool persistent = hdr->persistent != 0;
@@ -1160,7 +1181,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		constexpr bool shared = kShared;	/* compiled out of the one-CTA-per-queue kernels */
 		QShare *const shares = hdr->share;
 		uint32_t scan_from = blockIdx.x % nqueues;	/* shared: where the search for unclaimed work resumes */
-		uint32_t run_q = 0xffffffffu, run_start = 0, run_end = 0, run_wr = 0;	/* shared, lane 0: this CTA's current run */
+		uint32_t run_q = 0xffffffffu, run_start = 0, run_end = 0, run_wr = 0, run_we = 0, run_ok = 0;	/* shared, lane 0: this CTA's current run */
+		bool run_ok_valid = false;
 		uint32_t sweep_qi = blockIdx.x;
 		bool progress = false;
 		uint64_t last_progress = persistent ? globaltimer_ns() : 0;
@@ -1177,12 +1199,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						continue;
 					}
 					/* idle: as below, publish what the pipeline still holds, then stop flag / watchdog */
-					while (reaped < fills) {
-						const uint32_t sidx = reaped % kStages;
-						mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
-						reap_stage(sh.stage[sidx], lane);
-						reaped++;
-					}
+					while (reaped < fills) retire(reaped++);
 					uint32_t quit = 0;
 					if (lane == 0) {
 						quit = (hinted ? ld_vol32(&hdr->stop_mirror) : ld_vol32(hdr->stop)) != 0;
@@ -1211,12 +1228,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					}
 					/* idle: publish every completion still held back by the pipeline, then look at the
 					 * stop flag / watchdog */
-					while (reaped < fills) {
-						const uint32_t sidx = reaped % kStages;
-						mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
-						reap_stage(sh.stage[sidx], lane);
-						reaped++;
-					}
+					while (reaped < fills) retire(reaped++);
 					uint32_t quit = 0;
 					if (lane == 0) {
 						quit = (hinted ? ld_vol32(&hdr->stop_mirror) : ld_vol32(hdr->stop)) != 0;
@@ -1325,9 +1337,10 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				if (vq_tbl_aligned && vq_head_cur < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_cur * 16);
 			}
 			uint32_t done = 0;	/* position of the current pass on the queue */
-			uint32_t share_guess = 0xffffffffu;	/* shared: position whose slots / heads were read ahead */
-			uint32_t share_guess_n = 0;		/* ... and how many of them */
-			uint32_t share_seen = 0;		/* shared: published requests from `done` on, as of the claim */
+			/* shared: the NEXT pass is claimed, and its slots / ring entries fetched, as soon as this pass's parse
+			 * results are published - before the emission, which may wait for a free stage - so that claim and
+			 * fetch latency stay off the parser's critical path */
+			uint32_t next_n = 0, next_done = 0;
 			for (uint32_t it = 0;; it++) {
 				uint32_t n;
 				if (!shared) {
@@ -1335,37 +1348,30 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					if (done >= q.count) break;
 					n = min((uint32_t)kPass, q.count - done);
 				} else {
-					/* publish whatever the movers have finished: the fills other CTAs took after ours wait for it */
-					while (reaped < fills && mbar_test(&sh.empty[reaped % kStages], (reaped / kStages) & 1)) {
-						reap_stage(sh.stage[reaped % kStages], lane);
-						reaped++;
-					}
-					uint32_t pos = 0, got = 0, seen = 0;
-					if (lane == 0) got = claim_pass(q, *qs, persistent, hinted, &pos, &seen);
-					n = __shfl_sync(0xffffffffu, got, 0);
-					if (n == 0) break;
-					done = __shfl_sync(0xffffffffu, pos, 0);
-					share_seen = __shfl_sync(0xffffffffu, seen, 0);
-					progress = true;
-					/* the pass behind the previous one was read ahead on the guess that nobody else would claim
-					 * in between (true whenever this CTA has the queue to itself): use it if the guess held */
-					const bool guessed = done == share_guess && n <= share_guess_n;	/* (a poller may see more by now) */
-					share_guess = 0xffffffffu;
-					if (guessed) {
-						if (q.mode == QMODE_VRING) vq_head_cur = vq_head_nxt;
-					} else if (q.mode == QMODE_SLOTS) {
+					if (next_n == 0) {
+						uint32_t pos = 0, got = 0;
+						if (lane == 0) got = claim_pass(q, *qs, persistent, hinted, &pos);
+						next_n = __shfl_sync(0xffffffffu, got, 0);
+						if (next_n == 0) break;
+						next_done = __shfl_sync(0xffffffffu, pos, 0);
+						if (q.mode == QMODE_SLOTS) {
 #pragma unroll
-						for (int k = 0; k < 4; k++) {
-							const uint32_t v = k * 32 + lane;
-							if ((v >> 2) < n) {
-								const uint32_t slot = (q.head + done + (v >> 2)) & q.ring_mask;
-								pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
+							for (int k = 0; k < 4; k++) {
+								const uint32_t v = k * 32 + lane;
+								if ((v >> 2) < next_n) {
+									const uint32_t slot = (q.head + next_done + (v >> 2)) & q.ring_mask;
+									pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
+								}
 							}
+						} else if ((uint32_t)lane < next_n) {
+							vq_head_cur = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(q.head + next_done + lane) & (q.vq_size - 1)];
+							if (vq_tbl_aligned && vq_head_cur < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_cur * 16);
 						}
-					} else if ((uint32_t)lane < n) {
-						vq_head_cur = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(q.head + done + lane) & (q.vq_size - 1)];
-						if (vq_tbl_aligned && vq_head_cur < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_cur * 16);
 					}
+					n = next_n;
+					done = next_done;
+					next_n = 0;
+					progress = true;
 				}
 				const uint32_t slot0 = q.head + done;
 				__syncwarp();
@@ -1377,9 +1383,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					}
 				}
 				__syncwarp();
-				/* (shared: only what was already published when this pass was claimed may be read ahead) */
-				const uint32_t ahead = shared ? share_seen - n : (done + kPass < q.count ? q.count - done - kPass : 0u);
-				if (shared && ahead) { share_guess = done + n; share_guess_n = min((uint32_t)kPass, ahead); }
+				const uint32_t ahead = shared ? 0u : (done + kPass < q.count ? q.count - done - kPass : 0u);
 				if (q.mode == QMODE_SLOTS && ahead) {
 					const uint32_t n1 = min((uint32_t)kPass, ahead);
 #pragma unroll
@@ -1515,29 +1519,55 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					if (lane == 0) {
 						/* {parsed, wr_end} travel in ONE 64-bit word: nothing else is published with it, so the
 						 * hand-over needs no fence (which would wait for the parser's read-ahead loads) */
-						uint64_t w;
-						while ((uint32_t)(w = ld_vol64(&qs->chain)) != done) __nanosleep(20);
-						const uint32_t we = (uint32_t)(w >> 32);
-						/* a run = passes this CTA took back to back (nobody else claimed in between): known locally */
-						if (run_q != qi || run_end != done) { run_q = qi; run_start = done; run_wr = we; }
+						/* a run = passes this CTA took back to back (nobody else claimed in between): known locally.
+						 * Inside a run the chain word is still the one this lane stored last - no need to read it */
+						uint32_t we;
+						if (run_q == qi && run_end == done) {
+							we = run_we;
+						} else {
+							uint64_t w;
+							while ((uint32_t)(w = ld_vol64(&qs->chain)) != done) __nanosleep(20);
+							we = (uint32_t)(w >> 32);
+							run_q = qi; run_start = done; run_wr = we; run_ok_valid = false;
+						}
 						run_end = done + n;
-						st_vol64(&qs->chain, (uint64_t)(writers ? done + n : we) << 32 | (uint64_t)(done + n));
+						run_we = writers ? done + n : we;
+						st_vol64(&qs->chain, (uint64_t)run_we << 32 | (uint64_t)(done + n));
 						need = writers ? run_start : run_wr;
-						if (need && (int32_t)(ld_acquire32(&qs->done) - need) >= 0) need = 0;
+						/* run_ok: the largest position of this run's foreign past already seen complete */
+						if (need && run_ok_valid && (int32_t)(run_ok - need) >= 0) need = 0;
+						else if (need && (int32_t)(ld_acquire32(&qs->done) - need) >= 0) { run_ok = need; run_ok_valid = true; need = 0; }
 					}
 					need = __shfl_sync(0xffffffffu, need, 0);
 					if (need) {
-						/* our own fills first: the positions waited for may be behind some of them in the chain */
-						while (reaped < fills) {
-							const uint32_t sidx = reaped % kStages;
-							mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
-							reap_stage(sh.stage[sidx], lane);
-							reaped++;
-						}
+						/* (our own earlier fills are published by mover warp 0 as they finish: nothing here may depend
+						 * on this parser, which holds a claimed pass while it waits) */
 						if (lane == 0) {
 							while ((int32_t)(ld_acquire32(&qs->done) - need) < 0) __nanosleep(40);
+							run_ok = need;
+							run_ok_valid = true;
 						}
 						__syncwarp();
+					}
+					/* the next pass: claim it and start its fetch now (pre[] / vq_raw / vq_head_nxt are free again) */
+					{
+						uint32_t pos = 0, got = 0;
+						if (lane == 0) got = claim_pass(q, *qs, persistent, hinted, &pos);
+						next_n = __shfl_sync(0xffffffffu, got, 0);
+						next_done = __shfl_sync(0xffffffffu, pos, 0);
+						if (next_n && q.mode == QMODE_SLOTS) {
+#pragma unroll
+							for (int k = 0; k < 4; k++) {
+								const uint32_t v = k * 32 + lane;
+								if ((v >> 2) < next_n) {
+									const uint32_t slot = (q.head + next_done + (v >> 2)) & q.ring_mask;
+									pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
+								}
+							}
+						} else if (next_n && (uint32_t)lane < next_n) {
+							vq_head_nxt = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(q.head + next_done + lane) & (q.vq_size - 1)];
+							if (vq_tbl_aligned && vq_head_nxt < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_nxt * 16);
+						}
 					}
 				}
 
@@ -1628,9 +1658,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					const uint32_t sidx = fills % kStages;
 					Stage &st = sh.stage[sidx];
 					if (fills >= kStages && reaped + kStages <= fills) {
-						mbar_wait(&sh.empty[sidx], ((fills / kStages) - 1) & 1);
-						reap_stage(st, lane);
-						reaped++;
+						retire(reaped++);
 						__syncwarp();
 					}
 					if (mine) {
@@ -1667,6 +1695,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						st.vq_in_hbm = q.vq_in_hbm;
 						st.used_base = vq_last_used + done + r0;
 						st.done = persistent ? q.done : nullptr;
+						st.unit_ctr = 0;
 						st.share = qs;
 						st.share_pos = done + r0;
 						st.share_final = q.count;
@@ -1687,21 +1716,14 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			const uint32_t sidx = fills % kStages;
 			Stage &st = sh.stage[sidx];
 			if (fills >= kStages && reaped + kStages <= fills) {
-				mbar_wait(&sh.empty[sidx], ((fills / kStages) - 1) & 1);
-				reap_stage(st, lane);
-				reaped++;
+				retire(reaped++);
 				__syncwarp();
 			}
 			if (lane == 0) { st.stop = 1; st.nunits = 0; st.nseg = 0; st.nwaves = 1; st.drain = 0; st.ncpl = 0; st.mode = QMODE_SLOTS; st.done = nullptr; st.share = nullptr; }
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&sh.full[sidx]);
 		}
-		while (reaped < fills) {
-			const uint32_t sidx = reaped % kStages;
-			mbar_wait(&sh.empty[sidx], (reaped / kStages) & 1);
-			reap_stage(sh.stage[sidx], lane);
-			reaped++;
-		}
+		while (reaped < fills) retire(reaped++);
 		if (persistent && shared) {
 			/* the last worker to leave writes the ring cursors back: by then every claimed pass is published */
 			uint32_t last = 0;
@@ -1757,8 +1779,17 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				mbar_wait(&sh.empty[p % kStages], (p / kStages) & 1);
 				drained = true;
 			}
+			/* shared kernels: units are drawn from a counter (mover 0 spends part of its time publishing) unless
+			 * the fill has waves, whose barrier wants every mover to walk the same list */
+			const bool dyn = kShared && nw == 1;
+			auto next_unit = [&](uint32_t u) -> uint32_t {
+				if (!dyn) return u + kMovers;
+				uint32_t v = 0;
+				if (lane == 0) v = atomicAdd(&st.unit_ctr, 1u);
+				return __shfl_sync(0xffffffffu, v, 0);
+			};
 			for (uint32_t w = 0; w < nw; w++) {
-				for (uint32_t u = mw; u < nunits; u += kMovers) {
+				for (uint32_t u = dyn ? next_unit(0) : (uint32_t)mw; u < nunits; u = next_unit(u)) {
 					uint32_t lo = u, hi = nseg;	/* last segment with first_unit <= u */
 					/* as many units as segments: segment u IS unit u.  Taken for passes of small requests (the
 					 * 4 KiB case, +1.5 %); long SG lists of single pages keep the search - measured 1.5 %
@@ -1782,7 +1813,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					const uint8_t *src = g.src;
 					uint8_t *dst = g.dst;
 					if (!kMirrored || !g.mirror) {
-						if (src) move_unit(dst + off, src + off, nbytes, lane);
+						if (src) move_unit<kMirrored>(dst + off, src + off, nbytes, lane);
 						else zero_unit(dst + off, nbytes, lane);
 					} else {
 						const LunCtx &T = (g.mirror - 1 == lun->target) ? *lun : *lun->peer[g.mirror - 1];
@@ -1793,6 +1824,16 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&sh.empty[sidx]);
+			if constexpr (kShared) {
+				if (mw == 0) {
+					/* every mover is done with the fill: publish its completions (in ring order across CTAs,
+					 * reap_stage waits for the fills before it) and hand the stage back to the parser */
+					mbar_wait(&sh.empty[sidx], (c / kStages) & 1);
+					reap_stage(st, lane, &sh.pub_q, &sh.pub_end);
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&sh.released[sidx]);
+				}
+			}
 		}
 	}
 }

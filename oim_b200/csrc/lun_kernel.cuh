@@ -228,6 +228,8 @@ struct __align__(16) Stage {
 	uint32_t share_pos;		/* position of this fill's first request */
 	uint32_t share_final;		/* launch + virtqueue: position at which the ring cursors are written back (count) */
 	uint32_t persistent;
+	uint32_t unit_ctr;		/* shared kernels: movers draw units from here (mover 0 also publishes, so it takes fewer) */
+	uint32_t pad_[3];
 };
 
 /* Store ranges of one pass, for hazard detection against the passes after it (parser-private).
@@ -254,6 +256,9 @@ struct __align__(16) CtaShared {
 	LaneState lane[kPass];
 	uint64_t full[kStages];		/* mbarriers */
 	uint64_t empty[kStages];
+	uint64_t released[kStages];	/* shared kernels: the fill's completions are published, the stage may be refilled */
+	QShare  *pub_q;			/* shared kernels, mover warp 0: queue and end position of its last publication */
+	uint32_t pub_end;
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -290,43 +295,87 @@ __device__ __forceinline__ uint32_t be32(const uint8_t *p)
 }
 __device__ __forceinline__ uint64_t be64(const uint8_t *p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
 
-/* byte-granular SG element (SURVEY.md §7 "unaligned SG elements"): peel to a 16-byte aligned
- * destination, then aligned 16-byte stores fed by the widest loads the source allows */
+/* byte-granular SG element (SURVEY.md §7 "unaligned SG elements"): peel to a 16-byte aligned destination, then
+ * aligned 16-byte stores.  A source that is misaligned against the destination by m bytes is read as the two
+ * ALIGNED 16-byte vectors that straddle each output vector and realigned in registers with funnel shifts
+ * (the second vector is the neighbour lane's first: an L2 hit, DRAM traffic stays 1x).  Aligned vectors never
+ * cross a page, and each one read holds at least one byte of the element, so the over-read of up to 15 bytes on
+ * either side stays inside mapped memory and is never stored. */
+__device__ __forceinline__ int4 realign16(const int4 &a, const int4 &b, uint32_t m)
+{
+	const uint32_t r = (m & 3) * 8;
+	uint32_t w0, w1, w2, w3, w4;
+	switch (m >> 2) {
+	case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+	case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+	case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+	default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+	}
+	return make_int4(__funnelshift_r(w0, w1, r), __funnelshift_r(w1, w2, r), __funnelshift_r(w2, w3, r), __funnelshift_r(w3, w4, r));
+}
+
 __device__ __forceinline__ void move_unit_unaligned(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
 {
 	uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
 	if (head > n) head = n;
 	if ((uint32_t)lane < head) dst[lane] = ld_cg8(src + lane);
 	dst += head; src += head; n -= head;
-	const uint32_t nv = n >> 4;
-	if (((uintptr_t)src & 15) == 0) {
-		for (uint32_t v = lane; v < nv; v += 32) st_cg16(dst + (size_t)v * 16, ld_cg16(src + (size_t)v * 16));
-	} else if (((uintptr_t)src & 3) == 0) {
-		for (uint32_t v = lane; v < nv; v += 32) {
-			const uint8_t *s = src + (size_t)v * 16;
-			int4 r;
-			r.x = ld_cg32(s); r.y = ld_cg32(s + 4); r.z = ld_cg32(s + 8); r.w = ld_cg32(s + 12);
-			st_cg16(dst + (size_t)v * 16, r);
+	const uint32_t nv = n >> 4;	/* <= 256 output vectors, vector v = lane + 32 k */
+	const uint32_t m = (uint32_t)((uintptr_t)src & 15);
+	constexpr int H = 4;		/* vectors per lane in flight per half: loads first, then stores, like the fast path */
+	if (m == 0) {
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			int4 r[H];
+#pragma unroll
+			for (int k = 0; k < H; k++) {
+				const uint32_t v = lane + 32 * (h * H + k);
+				if (v < nv) r[k] = ld_cg16(src + (size_t)v * 16);
+			}
+#pragma unroll
+			for (int k = 0; k < H; k++) {
+				const uint32_t v = lane + 32 * (h * H + k);
+				if (v < nv) st_cg16(dst + (size_t)v * 16, r[k]);
+			}
 		}
 	} else {
-		for (uint32_t v = lane; v < nv; v += 32) {
-			const uint8_t *s = src + (size_t)v * 16;
-			uint32_t w[4];
+		/* aligned source vector i (at sa + 16 i) is needed for i <= nv; output vector v = realign(i = v, i = v + 1).
+		 * Lane l holds i = l + 32 k; its right neighbour is lane l + 1's, and for lane 31 lane 0's next one. */
+		const uint8_t *sa = src - m;
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				w[j] = (uint32_t)ld_cg8(s + 4 * j) | (uint32_t)ld_cg8(s + 4 * j + 1) << 8 |
-				       (uint32_t)ld_cg8(s + 4 * j + 2) << 16 | (uint32_t)ld_cg8(s + 4 * j + 3) << 24;
+		for (int h = 0; h < 2; h++) {
+			int4 a[H + 1];
+#pragma unroll
+			for (int k = 0; k <= H; k++) {
+				const uint32_t i = lane + 32 * (h * H + k);
+				if (i <= nv && (k < H || lane == 0)) a[k] = ld_cg16(sa + (size_t)i * 16);
 			}
-			st_cg16(dst + (size_t)v * 16, make_int4(w[0], w[1], w[2], w[3]));
+#pragma unroll
+			for (int k = 0; k < H; k++) {
+				const uint32_t v = lane + 32 * (h * H + k);
+				int4 b;
+				b.x = __shfl_down_sync(0xffffffffu, a[k].x, 1); b.y = __shfl_down_sync(0xffffffffu, a[k].y, 1);
+				b.z = __shfl_down_sync(0xffffffffu, a[k].z, 1); b.w = __shfl_down_sync(0xffffffffu, a[k].w, 1);
+				const int nx = __shfl_sync(0xffffffffu, a[k + 1].x, 0), ny = __shfl_sync(0xffffffffu, a[k + 1].y, 0);
+				const int nz = __shfl_sync(0xffffffffu, a[k + 1].z, 0), nw = __shfl_sync(0xffffffffu, a[k + 1].w, 0);
+				if (lane == 31) b = make_int4(nx, ny, nz, nw);
+				if (v < nv) st_cg16(dst + (size_t)v * 16, realign16(a[k], b, m));
+			}
 		}
 	}
 	const uint32_t tail = n & 15;
 	if ((uint32_t)lane < tail) dst[(size_t)nv * 16 + lane] = ld_cg8(src + (size_t)nv * 16 + lane);
 }
 
+static __device__ __noinline__ void move_unit_unaligned_call(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
+{
+	move_unit_unaligned(dst, src, n, lane);
+}
+
 /* Move `n` (<= kUnitBytes) bytes with one warp.  Fast path: both sides 16-byte aligned.
  * dst2 != nullptr (mirrored bdev, same alignment as dst): the registers are stored twice, locally
  * and into the peer replica over NVLink - one load, two stores, no second pass. */
+template <bool kSlowPathOutOfLine = false>	/* mirror kernels: keeping the byte-granular path out of line keeps them spill-free */
 __device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint32_t n, int lane, uint8_t *dst2 = nullptr)
 {
 	if ((((uintptr_t)dst | (uintptr_t)src | n) & 15) == 0) {
@@ -351,8 +400,15 @@ __device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint
 		}
 		return;
 	}
-	move_unit_unaligned(dst, src, n, lane);
-	if (dst2) move_unit_unaligned(dst2, src, n, lane);
+	if constexpr (kSlowPathOutOfLine) move_unit_unaligned_call(dst, src, n, lane);
+	else move_unit_unaligned(dst, src, n, lane);
+	if (dst2) move_unit_unaligned_call(dst2, src, n, lane);
+}
+
+/* third and further replicas (R > 2): out of line as a whole */
+static __device__ __noinline__ void move_unit_call(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
+{
+	move_unit(dst, src, n, lane);
 }
 
 /* mem_copy_fill with fill == 0 (copy_engine.c:128-140): zero `n` bytes; block-aligned by construction */

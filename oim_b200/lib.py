@@ -80,6 +80,7 @@ SYMBOLS = [
     ("oimgpu_lun_open", _I, [C.c_char_p, _I, _U32, _U32, C.POINTER(_VP)]),
     ("oimgpu_lun_close", _I, [_VP]),
     ("oimgpu_lun_device", _I, [_VP]),
+    ("oimgpu_lun_shared_launches", C.c_longlong, [_VP]),
     ("oimgpu_mem_register", _I, [_VP, C.c_size_t]),
     ("oimgpu_mem_unregister", _I, [_VP]),
     ("oimgpu_mem_device_addr", _I, [_VP, C.POINTER(C.c_uint64)]),
@@ -107,6 +108,13 @@ SYMBOLS = [
     ("oimgpu_timer_record", _I, [_VP, _VP]),
     ("oimgpu_timer_elapsed_ms", _I, [_VP, _VP, C.POINTER(C.c_float)]),
     ("oimgpu_timer_destroy", None, [_VP, _VP]),
+    ("oimgpu_copy_chan_open", _I, [_I, C.POINTER(_VP)]),
+    ("oimgpu_copy_chan_close", _I, [_VP]),
+    ("oimgpu_copy_chan_copy", _I, [_VP, _VP, _VP, _U64, _VP]),
+    ("oimgpu_copy_chan_fill", _I, [_VP, _VP, C.c_uint8, _U64, _VP]),
+    ("oimgpu_copy_chan_poll", _I, [_VP, C.POINTER(_VP), _I]),
+    ("oimgpu_copy_chan_launches", C.c_ulonglong, [_VP]),
+    ("oimgpu_mem_ensure", _I, [_VP, C.c_size_t]),
     ("oimgpu_copy_submit", _I, [_VP, _VP, _VP, _U64]),
     ("oimgpu_fill_submit", _I, [_VP, _VP, C.c_uint8, _U64]),
 ]
@@ -361,6 +369,11 @@ class Lun:
     @property
     def device(self) -> int:
         return load().oimgpu_lun_device(self.h)
+
+    @property
+    def shared_launches(self) -> int:
+        """launches in which the CTAs shared the queues a pass at a time (include/oimgpu.h)"""
+        return load().oimgpu_lun_shared_launches(self.h)
 
     def submit(self, q: int, reqs: np.ndarray, iovs: np.ndarray) -> None:
         """host arrays -> queue q's ring (OIMGPU_MEM_HOST)."""

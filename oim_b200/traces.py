@@ -168,14 +168,17 @@ def uniform_trace(n: int, num_blocks: int, *, io_blocks: int = 8, block_size: in
     nblk = np.full(n, io_blocks, dtype=np.uint64)
     cdb = np.where(is_read[:, None], _rw_cdbs(abi.READ_10, abi.READ_16, lba, nblk),
                    _rw_cdbs(abi.WRITE_10, abi.WRITE_16, lba, nblk))
+    shift = 0
+    if sg.endswith("+3"):                    # client buffers 3 bytes off the store's alignment: the realign path
+        sg, shift = sg[:-2], 3
     lens = _sg_layout(n, io_bytes, sg)
     k = len(lens)
-    stride = -(-io_bytes // buf_align) * buf_align
+    stride = -(-(io_bytes + shift) // buf_align) * buf_align
     reqs = _finish(n, cdb, np.where(is_read, abi.DIR_FROM_DEV, abi.DIR_TO_DEV).astype(np.uint8),
                    np.full(n, k, dtype=np.uint16), target)
     iovs = np.zeros(n * k, dtype=abi.iov_dtype)
     within = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.uint64)
-    base = (np.arange(n, dtype=np.uint64) * np.uint64(stride))[:, None]
+    base = (np.arange(n, dtype=np.uint64) * np.uint64(stride) + np.uint64(shift))[:, None]
     iovs["addr"] = (base + within[None, :]).reshape(-1)
     iovs["len"] = np.tile(np.asarray(lens, dtype=np.uint32), n)
     return Trace(reqs, iovs, n * stride, f"{pattern}-{io_bytes}B-{sg}",

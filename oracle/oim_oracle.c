@@ -1,7 +1,7 @@
 /*
  * oim_oracle.c — TEST INFRASTRUCTURE: plain-C restatement of the reference's block-I/O hot path.
  *
- * Parity status: PINNED.  This file is checked (tests/test_oracle_vs_ref.py) against
+ * Parity status: PINNED.  This file is checked (tests/test_oracle.py) against
  * oracle/_ref/liboim_ref.so, which is the reference's own SPDK sources compiled from
  * /root/reference and driven through process_requestq() (oracle/ref_driver.c), on the golden
  * cases of SPDK's unit tests (scsi_bdev_ut.c:639-897, vhost_ut.c:153-235), the bdevio data-integrity
