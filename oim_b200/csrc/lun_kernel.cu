@@ -1018,7 +1018,8 @@ static __device__ __forceinline__ void mirror_unit(const LunCtx &L, uint8_t *dst
 
 /* lane 0: take the next pass (<= 32 requests) of a shared queue.  Returns its length (0: nothing unclaimed right
  * now) and its position in *pos.  q.head = ring position of position 0; q.count = the launch's limit. */
-__device__ __forceinline__ uint32_t claim_pass(const QueueDesc &q, QShare &qs, bool persistent, bool hinted, uint32_t *pos)
+__device__ __forceinline__ uint32_t claim_pass(const QueueDesc &q, QShare &qs, bool persistent, bool hinted, uint32_t *pos,
+					       uint32_t want = kPass)
 {
 	for (;;) {
 		const uint32_t c = ld_vol32(&qs.claim);
@@ -1033,7 +1034,7 @@ __device__ __forceinline__ uint32_t claim_pass(const QueueDesc &q, QShare &qs, b
 			avail = (hinted ? ld_vol32(&q.vq_state->hint) : ld_vol32(q.doorbell)) - (q.head + c);
 		}
 		if (avail == 0) return 0;
-		const uint32_t n = avail < (uint32_t)kPass ? avail : (uint32_t)kPass;
+		const uint32_t n = avail < want ? avail : want;
 		if (atomicCAS(&qs.claim, c, c + n) == c) {
 			*pos = c;
 			return n;
@@ -1341,6 +1342,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			 * results are published - before the emission, which may wait for a free stage - so that claim and
 			 * fetch latency stay off the parser's critical path */
 			uint32_t next_n = 0, next_done = 0;
+			uint32_t chunk_left = 0;	/* requests behind next_done + next_n that this CTA already owns */
+			uint32_t streak = 0;		/* consecutive claims that continued this CTA's own run */
 			for (uint32_t it = 0;; it++) {
 				uint32_t n;
 				if (!shared) {
@@ -1354,6 +1357,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						next_n = __shfl_sync(0xffffffffu, got, 0);
 						if (next_n == 0) break;
 						next_done = __shfl_sync(0xffffffffu, pos, 0);
+						chunk_left = 0;
+						streak = 0;
 						if (q.mode == QMODE_SLOTS) {
 #pragma unroll
 							for (int k = 0; k < 4; k++) {
@@ -1551,10 +1556,22 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					}
 					/* the next pass: claim it and start its fetch now (pre[] / vq_raw / vq_head_nxt are free again) */
 					{
-						uint32_t pos = 0, got = 0;
-						if (lane == 0) got = claim_pass(q, *qs, persistent, hinted, &pos);
-						next_n = __shfl_sync(0xffffffffu, got, 0);
-						next_done = __shfl_sync(0xffffffffu, pos, 0);
+						/* A CTA that has had the queue to itself for a few passes takes four passes' worth per claim
+						 * (one atomic round trip per 128 requests instead of per 32); the moment somebody else's claim
+						 * lands in between it is back to single passes, so that sharers interleave finely. */
+						if (chunk_left) {
+							next_done = done + n;
+							next_n = min((uint32_t)kPass, chunk_left);
+							chunk_left -= next_n;
+						} else {
+							uint32_t pos = 0, got = 0;
+							if (lane == 0) got = claim_pass(q, *qs, persistent, hinted, &pos, streak >= 2 ? 4u * kPass : (uint32_t)kPass);
+							got = __shfl_sync(0xffffffffu, got, 0);
+							next_done = __shfl_sync(0xffffffffu, pos, 0);
+							streak = (got && next_done == done + n) ? streak + 1 : 0;
+							next_n = min((uint32_t)kPass, got);
+							chunk_left = got - next_n;
+						}
 						if (next_n && q.mode == QMODE_SLOTS) {
 #pragma unroll
 							for (int k = 0; k < 4; k++) {
@@ -1789,7 +1806,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				return __shfl_sync(0xffffffffu, v, 0);
 			};
 			for (uint32_t w = 0; w < nw; w++) {
-				for (uint32_t u = dyn ? next_unit(0) : (uint32_t)mw; u < nunits; u = next_unit(u)) {
+				for (uint32_t u = dyn ? next_unit(0) : (uint32_t)mw, u_next = 0; u < nunits; u = u_next) {
+					u_next = next_unit(u);	/* drawn before this unit moves: the counter's latency hides behind the loads */
 					uint32_t lo = u, hi = nseg;	/* last segment with first_unit <= u */
 					/* as many units as segments: segment u IS unit u.  Taken for passes of small requests (the
 					 * 4 KiB case, +1.5 %); long SG lists of single pages keep the search - measured 1.5 %

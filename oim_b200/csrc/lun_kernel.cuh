@@ -316,13 +316,20 @@ __device__ __forceinline__ int4 realign16(const int4 &a, const int4 &b, uint32_t
 
 __device__ __forceinline__ void move_unit_unaligned(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
 {
+	/* loads of a half-unit are issued before its first store (a warp issues in order: a store waiting for its data
+	 * holds back the loads behind it).  Two halves of 4 vectors per lane, not one of 8 as in the fast path: the
+	 * 9 x 4 registers of a whole realigned unit made the mover loop spill and cost every path 3 %. */
 	uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
 	if (head > n) head = n;
-	if ((uint32_t)lane < head) dst[lane] = ld_cg8(src + lane);
+	uint8_t hb = 0, tb = 0;
+	if ((uint32_t)lane < head) hb = ld_cg8(src + lane);
+	uint8_t *const dst0 = dst;
 	dst += head; src += head; n -= head;
 	const uint32_t nv = n >> 4;	/* <= 256 output vectors, vector v = lane + 32 k */
+	const uint32_t tail = n & 15;
+	if ((uint32_t)lane < tail) tb = ld_cg8(src + (size_t)nv * 16 + lane);
 	const uint32_t m = (uint32_t)((uintptr_t)src & 15);
-	constexpr int H = 4;		/* vectors per lane in flight per half: loads first, then stores, like the fast path */
+	constexpr int H = 4;
 	if (m == 0) {
 #pragma unroll
 		for (int h = 0; h < 2; h++) {
@@ -332,6 +339,7 @@ __device__ __forceinline__ void move_unit_unaligned(uint8_t *dst, const uint8_t 
 				const uint32_t v = lane + 32 * (h * H + k);
 				if (v < nv) r[k] = ld_cg16(src + (size_t)v * 16);
 			}
+			if (h == 0 && (uint32_t)lane < head) dst0[lane] = hb;
 #pragma unroll
 			for (int k = 0; k < H; k++) {
 				const uint32_t v = lane + 32 * (h * H + k);
@@ -350,6 +358,7 @@ __device__ __forceinline__ void move_unit_unaligned(uint8_t *dst, const uint8_t 
 				const uint32_t i = lane + 32 * (h * H + k);
 				if (i <= nv && (k < H || lane == 0)) a[k] = ld_cg16(sa + (size_t)i * 16);
 			}
+			if (h == 0 && (uint32_t)lane < head) dst0[lane] = hb;
 #pragma unroll
 			for (int k = 0; k < H; k++) {
 				const uint32_t v = lane + 32 * (h * H + k);
@@ -363,8 +372,7 @@ __device__ __forceinline__ void move_unit_unaligned(uint8_t *dst, const uint8_t 
 			}
 		}
 	}
-	const uint32_t tail = n & 15;
-	if ((uint32_t)lane < tail) dst[(size_t)nv * 16 + lane] = ld_cg8(src + (size_t)nv * 16 + lane);
+	if ((uint32_t)lane < tail) dst[(size_t)nv * 16 + lane] = tb;
 }
 
 static __device__ __noinline__ void move_unit_unaligned_call(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)

@@ -1283,6 +1283,14 @@ extern "C" int oimgpu_submit_device(oimgpu_lun *L, uint32_t q, const oimgpu_req 
 	return 0;
 }
 
+/* most queues for which the CTAs share queues instead of owning one each (see oimgpu_kick) */
+static uint32_t share_max_queues(const oimgpu_lun *L)
+{
+	const char *e = getenv("OIMGPU_SHARE_MAX_QUEUES");
+	if (e && *e) return (uint32_t)strtoul(e, nullptr, 0);
+	return (uint32_t)L->grid_cap * 160 / 296;
+}
+
 static void launch_lun_kernel(oimgpu_lun *L, uint32_t grid, bool shared)
 {
 	const size_t smem = lun_kernel_smem_bytes();
@@ -1368,8 +1376,12 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	/* One CTA per queue while there are at least as many queues as the GPU holds CTAs; with fewer queues the
 	 * CTAs SHARE them, a pass at a time (KickHeader::shared), so that a single deep queue - or the <= 254
 	 * request queues of a vhost controller - still fills the machine. */
-	const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nd, passes), (uint64_t)L->grid_cap);
-	const bool shared = nd < grid && !getenv("OIMGPU_NO_SHARED_QUEUES");
+	uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nd, passes), (uint64_t)L->grid_cap);
+	/* Measured on B200 (tools/queue_sweep.py, 4 KiB random read, 2^21 requests): one CTA per queue reaches 0.68 / 0.80 /
+	 * 0.94 / 0.96 of the HBM peak at 100 / 148 / 200 / 254 queues (a CTA alone moves ~6 M IOPS; 200 of them saturate
+	 * HBM), sharing 0.82 / 0.91 / 0.87 / 0.95: sharing pays below ~160 queues, above that ownership is cheaper. */
+	const bool shared = nd < grid && nd <= share_max_queues(L) && !getenv("OIMGPU_NO_SHARED_QUEUES");
+	if (!shared) grid = std::min(grid, nd);
 	KickHeader *kh = (KickHeader *)L->h_kick[slot];
 	memset(kh, 0, sizeof(*kh));	/* run-to-completion: persistent = 0 (the staging buffer is recycled pinned memory) */
 	kh->next = grid;	/* queues 0..grid-1 are taken statically by CTA index */
@@ -1957,7 +1969,7 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 	uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nd, want), (uint64_t)L->grid_cap - 1);
 	if (max_ctas) grid = std::min(grid, max_ctas);
 	if (grid == 0) grid = 1;
-	const bool shared = nd < grid && !getenv("OIMGPU_NO_SHARED_QUEUES");
+	const bool shared = nd < grid && nd <= share_max_queues(L) && !getenv("OIMGPU_NO_SHARED_QUEUES");
 	if (!shared) grid = std::min(grid, nd);
 	if (shared) {
 		std::vector<QShare> sh(nd);

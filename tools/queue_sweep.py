@@ -19,12 +19,12 @@ name = lib.construct_malloc_bdev(NB, BLOCK, name="sweep0", device=0)
 lib.construct_vhost_scsi_controller("sweep.ctl")
 lib.add_vhost_scsi_lun("sweep.ctl", 0, name)
 timer = lib.Timer()
-out = {"slots": {}, "vring": {}, "mixed": {}}
+out = {"slots": {}, "vring": {}, "mixed": {}, "write": {}}
 total = int(os.environ.get("SWEEP_TOTAL", 1 << 20))
 steps = 5
 qs = [int(x) for x in os.environ.get("SWEEP_QUEUES", "1,2,4,8,16,64,254,1024").split(",")]
 with lib.Lun("sweep.ctl", 0, num_queues=1024, queue_size=32) as lun:
-    for pattern, key in (("randread", "slots"), ("randrw", "mixed")):
+    for pattern, key in (("randread", "slots"), ("randrw", "mixed"), ("randwrite", "write")):
         for nq in qs:
             per_q = max(32, total // nq // 32 * 32)
             n = nq * per_q
@@ -54,7 +54,7 @@ with lib.Lun("sweep.ctl", 0, num_queues=1024, queue_size=32) as lun:
             torch.cuda.empty_cache()
         print(json.dumps({key: out[key]}), file=sys.stderr, flush=True)
 # guest virtio rings in HBM
-for nq in [q for q in qs if q <= 254] + [4096]:
+for nq in ([] if os.environ.get("SWEEP_NO_VRING") else [q for q in qs if q <= 254] + [4096]):
     per, ring = 256, 1024            # 3-descriptor chains: a 1024-entry ring (SPDK_VHOST_MAX_VQ_SIZE) holds 341 requests
     g = vring.build_uniform_queues(nq, per, NB, ring_size=ring, seed=11)
     guest = torch.empty(g.total_bytes(), dtype=torch.uint8, device="cuda")
