@@ -227,6 +227,12 @@ int oimgpu_vhost_scsi_ctrlr_create(const char *ctrlr, const char *cpumask);	/* -
 int oimgpu_vhost_scsi_add_lun(const char *ctrlr, int scsi_target_num, const char *bdev_name);
 int oimgpu_vhost_scsi_remove_target(const char *ctrlr, int scsi_target_num);	/* -ENODEV */
 int oimgpu_vhost_ctrlr_remove(const char *ctrlr);	/* -ENODEV, -EBUSY (has targets) */
+/* set_vhost_controller_coalescing (S/lib/vhost/vhost_rpc.c:493-544, vhost.c:358-381): interrupt coalescing of the
+ * controller's sessions; -ENODEV unknown controller, -EINVAL threshold below 100 IOPS or delay beyond 32 bits of ticks */
+int oimgpu_vhost_ctrlr_set_coalescing(const char *ctrlr, uint32_t delay_base_us, uint32_t iops_threshold);
+/* get_subsystem_config for "bdev" / "vhost" (S/lib/event/rpc/subsystem_rpc.c:80-129): JSON array of the calls that
+ * rebuild the present state; returns the text length (text written if cap allows), -ENOENT unknown subsystem */
+long oimgpu_config_json(const char *subsystem, char *buf, size_t cap);
 int oimgpu_vhost_ctrlr_get(const char *ctrlr, struct oimgpu_ctrlr_info *out);
 int oimgpu_vhost_ctrlr_list(struct oimgpu_ctrlr_info *out, int max);
 

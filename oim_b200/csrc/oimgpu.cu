@@ -71,6 +71,7 @@ struct Device {
 
 struct Bdev {
 	std::string name, product, uuid;
+	std::string pool_name, rbd_name, user_id;	/* construct_rbd_bdev parameters, kept for the config dump */
 	uint64_t num_blocks = 0;
 	uint32_t block_size = 0;
 	int claimed = 0;	/* number of SCSI targets built on it */
@@ -83,6 +84,8 @@ struct Bdev {
 
 struct Ctrlr {
 	std::string name, cpumask;
+	uint32_t delay_base_us = 0;			/* interrupt coalescing (vhost.c:270-377) */
+	uint32_t iops_threshold = 60000;		/* SPDK_VHOST_VQ_IOPS_COALESCING_THRESHOLD */
 	std::string targets[OIMGPU_CTRLR_MAX_DEVS];	/* bdev name or "" */
 	int scsi_id[OIMGPU_CTRLR_MAX_DEVS] = {};	/* spdk_scsi_dev.id: slot in the global device table */
 };
@@ -612,6 +615,12 @@ extern "C" int oimgpu_bdev_create_rbd(const char *name, const char *pool_name, c
 	int rc = create_bdev_locked(name, nullptr, size_bytes / block_size, block_size, {d}, "Ceph Rbd Disk",
 				    auto_name, name_out, name_cap);
 	if (rc == 0 && !(name && name[0])) g.rbd_count++;
+	if (rc == 0) {
+		Bdev &b = *g.bdevs[name && name[0] ? std::string(name) : auto_name];
+		b.pool_name = pool_name;
+		b.rbd_name = rbd_name;
+		b.user_id = user_id ? user_id : "";
+	}
 	return rc;
 }
 
@@ -975,14 +984,90 @@ extern "C" int oimgpu_vhost_ctrlr_remove(const char *ctrlr)
 	return 0;
 }
 
+/* spdk_vhost_set_coalescing (S/lib/vhost/vhost.c:358-381): the threshold is kept as requests per statistics
+ * interval of 10 ms (SPDK_VHOST_STATS_CHECK_INTERVAL_MS), so fewer than 100 IOPS rounds to nothing and is refused;
+ * the delay must fit 32 bits of timer ticks (ours: nanoseconds) */
+extern "C" int oimgpu_vhost_ctrlr_set_coalescing(const char *ctrlr, uint32_t delay_base_us, uint32_t iops_threshold)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.ctrlrs.find(ctrlr_key(ctrlr));
+	if (it == g.ctrlrs.end()) return -ENODEV;
+	if ((uint64_t)delay_base_us * 1000ull >= UINT32_MAX) return -EINVAL;
+	if (iops_threshold * 10u / 1000u == 0) return -EINVAL;
+	it->second->delay_base_us = delay_base_us;
+	it->second->iops_threshold = iops_threshold;
+	return 0;
+}
+
+static std::string json_escape(const std::string &in)
+{
+	std::string o = "\"";
+	for (unsigned char c : in) {
+		if (c == '"' || c == '\\') { o += '\\'; o += (char)c; }
+		else if (c < 0x20) { char b[8]; snprintf(b, sizeof(b), "\\u%04x", c); o += b; }
+		else o += (char)c;
+	}
+	return o + "\"";
+}
+
+/* get_subsystem_config (S/lib/event/rpc/subsystem_rpc.c:80-129): the RPC calls that would rebuild the subsystem's
+ * present state, as a JSON array of {"method", "params"} - spdk_bdev_subsystem_config_json (S/lib/bdev/bdev.c:676-708)
+ * with bdev_malloc_write_json_config (bdev_malloc.c:350-368) / bdev_rbd_write_config_json (bdev_rbd.c:635-666), and
+ * spdk_vhost_config_json (vhost.c:1460-1494) with spdk_vhost_scsi_write_config_json (vhost_scsi.c:1459-1499).
+ * Returns the length of the text (written if it fits, NUL-terminated), -ENOENT for an unknown subsystem. */
+extern "C" long oimgpu_config_json(const char *subsystem, char *buf, size_t cap)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	std::string sub = subsystem ? subsystem : "", out = "[";
+	if (sub == "bdev") {
+		out += "{\"method\":\"set_bdev_options\",\"params\":{\"bdev_io_pool_size\":65536,\"bdev_io_cache_size\":256}}";
+		for (auto &nm : g.bdev_order) {
+			const Bdev &b = *g.bdevs[nm];
+			if (b.product == "Ceph Rbd Disk") {
+				out += ",{\"method\":\"construct_rbd_bdev\",\"params\":{\"name\":" + json_escape(b.name) + ",\"pool_name\":" +
+				       json_escape(b.pool_name) + ",\"rbd_name\":" + json_escape(b.rbd_name) + ",\"block_size\":" + std::to_string(b.block_size);
+				if (!b.user_id.empty()) out += ",\"user_id\":" + json_escape(b.user_id);
+				out += "}}";
+			} else {
+				out += ",{\"method\":\"construct_malloc_bdev\",\"params\":{\"name\":" + json_escape(b.name) + ",\"num_blocks\":" +
+				       std::to_string(b.num_blocks) + ",\"block_size\":" + std::to_string(b.block_size) + ",\"uuid\":" + json_escape(b.uuid) + "}}";
+			}
+		}
+	} else if (sub == "vhost") {
+		bool first = true;
+		for (auto &nm : g.ctrlr_order) {
+			const Ctrlr &c = *g.ctrlrs[nm];
+			out += std::string(first ? "" : ",") + "{\"method\":\"construct_vhost_scsi_controller\",\"params\":{\"ctrlr\":" +
+			       json_escape(c.name) + ",\"cpumask\":" + json_escape(c.cpumask) + "}}";
+			first = false;
+			for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+				if (c.targets[t].empty()) continue;
+				out += ",{\"method\":\"add_vhost_scsi_lun\",\"params\":{\"ctrlr\":" + json_escape(c.name) + ",\"scsi_target_num\":" +
+				       std::to_string(t) + ",\"bdev_name\":" + json_escape(c.targets[t]) + "}}";
+			}
+			if (c.delay_base_us) {
+				out += ",{\"method\":\"set_vhost_controller_coalescing\",\"params\":{\"ctrlr\":" + json_escape(c.name) +
+				       ",\"delay_base_us\":" + std::to_string(c.delay_base_us) + ",\"iops_threshold\":" + std::to_string(c.iops_threshold) + "}}";
+			}
+		}
+	} else {
+		return -ENOENT;
+	}
+	out += "]";
+	if (buf && cap > out.size()) memcpy(buf, out.c_str(), out.size() + 1);
+	return (long)out.size();
+}
+
 static void fill_ctrlr_info(const Ctrlr &c, oimgpu_ctrlr_info *o)
 {
 	memset(o, 0, sizeof(*o));
 	copy_str(o->ctrlr, sizeof(o->ctrlr), c.name);
 	copy_str(o->cpumask, sizeof(o->cpumask), c.cpumask);
 	copy_str(o->socket, sizeof(o->socket), g.socket_dir + c.name);
-	o->delay_base_us = 0;
-	o->iops_threshold = 60000;	/* SPDK_VHOST_VQ_IOPS_COALESCING_THRESHOLD */
+	o->delay_base_us = c.delay_base_us;
+	o->iops_threshold = c.iops_threshold;
 	for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
 		if (c.targets[t].empty()) continue;
 		oimgpu_target_info &ti = o->targets[o->ntargets++];

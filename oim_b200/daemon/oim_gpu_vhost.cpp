@@ -507,6 +507,31 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 		if (g_serve_vhost_user && known) vhost_user::close_ctrlr(info.ctrlr);
 		return result(id, "true");
 	}
+	if (method == "set_vhost_controller_coalescing") {
+		/* S/lib/vhost/vhost_rpc.c:493-544 */
+		uint64_t delay = 0, thr = 0;
+		if (!decode(params, {{"ctrlr", Json::Str, false, &a}, {"delay_base_us", Json::Num, false, &b}, {"iops_threshold", Json::Num, false, &c}}) ||
+		    !to_u64(b, &delay) || !to_u64(c, &thr) || delay > UINT32_MAX || thr > UINT32_MAX)
+			return error(id, E_INVALID_PARAMS, strerr(EINVAL));
+		int rc = oimgpu_vhost_ctrlr_set_coalescing(a->raw.c_str(), (uint32_t)delay, (uint32_t)thr);
+		if (rc < 0) return error(id, E_INVALID_PARAMS, strerr(rc));
+		return result(id, "true");
+	}
+	if (method == "get_subsystems") {
+		/* S/lib/event/rpc/subsystem_rpc.c:40-78, the subsystems this daemon has */
+		return result(id, "[{\"subsystem\":\"copy\",\"depends_on\":[]},{\"subsystem\":\"bdev\",\"depends_on\":[\"copy\"]},"
+				  "{\"subsystem\":\"scsi\",\"depends_on\":[\"bdev\"]},{\"subsystem\":\"vhost\",\"depends_on\":[\"scsi\"]}]");
+	}
+	if (method == "get_subsystem_config") {
+		if (!decode(params, {{"name", Json::Str, false, &a}})) return error(id, E_INVALID_PARAMS, "Invalid arguments");
+		if (a->raw == "copy" || a->raw == "scsi") return result(id, "[]");
+		long n = oimgpu_config_json(a->raw.c_str(), nullptr, 0);
+		if (n < 0) return error(id, E_INVALID_PARAMS, "Subsystem '" + a->raw + "' not found");
+		std::string buf((size_t)n + 1, '\0');
+		oimgpu_config_json(a->raw.c_str(), &buf[0], buf.size());
+		buf.resize((size_t)n);
+		return result(id, buf);
+	}
 	if (method == "get_vhost_controllers") {
 		if (params && !decode(params, {{"name", Json::Str, true, &a}})) return error(id, E_INTERNAL, strerr(EINVAL));
 		std::string out = "[";

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -52,8 +53,17 @@ constexpr uint32_t kMaxVring = 0x100, kMaxQueuePairs = 0x80, kMaxRegions = 8;
 constexpr uint32_t kMaxPayload = 64 + 4096;	/* the largest member of VhostUserMsg.payload (nvme) */
 /* SPDK_VHOST_SCSI_FEATURES & ~SPDK_VHOST_SCSI_DISABLED_FEATURES (vhost_scsi.c:51-62, vhost_internal.h:86-94):
  * VIRTIO_SCSI_F_INOUT|HOTPLUG|CHANGE, VHOST_F_LOG_ALL(26), INDIRECT_DESC(28), PROTOCOL_FEATURES(30), VERSION_1(32) */
-constexpr uint64_t kFeatures = 0x7ull | 1ull << 26 | 1ull << 28 | 1ull << 30 | 1ull << 32;
-constexpr uint64_t kProtocolFeatures = 0x21f;	/* MQ, LOG_SHMFD, RARP, REPLY_ACK, NET_MTU, CONFIG (vhost_user.h:51-63) */
+/* What the reference offers (0x154000007 / 0x21f) minus dirty-page logging: VHOST_F_LOG_ALL (26) and the LOG_SHMFD
+ * protocol feature (1) are NOT offered.  The device writes guest memory from the GPU; logging those writes into the
+ * master's bitmap (vhost_user_set_log_base, rte_vhost/vhost_user.c:899-960; vhost_log_write, vhost.h) would need
+ * system-scope atomics into host memory that must not lose a bit against QEMU's concurrent test-and-clear, which PCIe
+ * only guarantees with AtomicOps routing.  Offering the bit without logging would let a live migration lose writes
+ * silently; without it QEMU registers a migration blocker, which is the honest answer.  A master that sets the
+ * bits anyway is accepted as the reference accepts it (nothing is logged). */
+constexpr uint64_t kFeaturesRef = 0x7ull | 1ull << 26 | 1ull << 28 | 1ull << 30 | 1ull << 32;
+constexpr uint64_t kFeatures = kFeaturesRef & ~(1ull << 26);
+constexpr uint64_t kProtocolFeaturesRef = 0x21f;	/* MQ, LOG_SHMFD, RARP, REPLY_ACK, NET_MTU, CONFIG (vhost_user.h:51-63) */
+constexpr uint64_t kProtocolFeatures = kProtocolFeaturesRef & ~(1ull << 1);
 constexpr int kFdUninit = -1, kFdInvalid = -2;	/* VIRTIO_UNINITIALIZED_EVENTFD / VIRTIO_INVALID_EVENTFD */
 constexpr uint64_t kMask2M = (2ull << 20) - 1;
 
@@ -70,6 +80,10 @@ struct Vq {
 	bool attached = false;		/* handed to the GPU for the current run */
 	uint16_t consumed = 0;		/* avail idx the GPU was last kicked for */
 	uint16_t signalled = 0;		/* used idx the guest was last interrupted for */
+	/* interrupt coalescing (S/lib/vhost/vhost.c:270-340): spdk_vhost_virtqueue::req_cnt / irq_delay_time / next_event_time */
+	uint16_t stat_used = 0;		/* used idx at the last statistics check */
+	uint32_t req_cnt = 0;
+	uint64_t irq_delay_ns = 0, next_event_ns = 0;
 };
 
 struct Region {
@@ -148,6 +162,10 @@ struct Session {
 	bool polling = false;
 	std::mutex ev_mu;
 	std::vector<std::pair<int, bool>> events;	/* hot-plug notifications from the RPC thread */
+	uint64_t next_stats_check_ns = 0;		/* check_session_io_stats: every SPDK_VHOST_STATS_CHECK_INTERVAL_MS = 10 ms */
+	uint32_t coalescing_delay_us = 0, coalescing_iops = 60000;
+	unsigned long long irqs_sent = 0, irqs_held = 0;
+	void check_io_stats(uint64_t now);
 
 	void run();
 	bool handle_message();
@@ -375,12 +393,54 @@ void Session::used_enqueue(Vq &q, uint16_t id, uint32_t len)
 }
 
 /* spdk_vhost_vq_used_signal (vhost.c:249-266): one interrupt for everything completed since the last one */
+static uint64_t now_ns()
+{
+	timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
+/* check_session_io_stats (vhost.c:270-297): every 10 ms, a queue whose request count since it last crossed the
+ * threshold exceeds the threshold gets an interrupt delay proportional to the excess; the count is only reset
+ * when it does (the reference's arithmetic, kept as is) */
+void Session::check_io_stats(uint64_t now)
+{
+	if (now < next_stats_check_ns) return;
+	next_stats_check_ns = now + 10000000ull;
+	oimgpu_ctrlr_info info;
+	if (oimgpu_vhost_ctrlr_get(srv->name.c_str(), &info) == 0) {	/* set_vhost_controller_coalescing reaches running sessions */
+		coalescing_delay_us = info.delay_base_us;
+		coalescing_iops = info.iops_threshold;
+	}
+	const uint32_t io_threshold = coalescing_iops * 10u / 1000u;
+	if (!coalescing_delay_us || !io_threshold) return;
+	for (Vq &q : vq) {
+		if (!q.used) continue;
+		const uint16_t idx = *(volatile uint16_t *)(q.used + 2);
+		q.req_cnt += (uint16_t)(idx - q.stat_used);
+		q.stat_used = idx;
+		if (q.req_cnt <= io_threshold) continue;
+		q.irq_delay_ns = (uint64_t)coalescing_delay_us * 1000ull * (q.req_cnt - io_threshold) / io_threshold;
+		q.req_cnt = 0;
+		q.next_event_ns = now;
+	}
+}
+
+/* spdk_vhost_session_used_signal / spdk_vhost_vq_used_signal (vhost.c:249-340): an interrupt when the used index
+ * moved, unless the guest masked them (VRING_AVAIL_F_NO_INTERRUPT) or the queue's coalescing delay has not passed */
 void Session::signal_used(Vq &q)
 {
 	if (!q.used) return;
 	const uint16_t idx = *(volatile uint16_t *)(q.used + 2);
 	if (idx == q.signalled) return;
+	if (q.avail && (*(volatile uint16_t *)q.avail & 1)) return;	/* stays pending: signalled is not advanced */
+	if (coalescing_delay_us) {
+		const uint64_t now = now_ns();
+		if (now < q.next_event_ns) { irqs_held++; return; }
+		q.next_event_ns = now + q.irq_delay_ns;
+	}
 	q.signalled = idx;
+	irqs_sent++;
 	if (q.callfd >= 0) eventfd_write(q.callfd, 1);
 }
 
@@ -616,6 +676,7 @@ void Session::service()
 	}
 	process_controlq();
 	if (!lun) return;
+	check_io_stats(now_ns());
 	if (!polling) {
 		for (int round = 0; round < 64; round++) {
 			bool work = false;
@@ -682,7 +743,7 @@ bool Session::handle_message()
 		break;
 	case SET_FEATURES: {	/* vhost_user_set_features */
 		v = u64_of();
-		if (v & ~kFeatures) break;	/* refused; the handler drops the status, so even a REPLY_ACK says 0 (vhost_user.c:1337-1339) */
+		if (v & ~kFeaturesRef) break;	/* refused; the handler drops the status, so even a REPLY_ACK says 0 (vhost_user.c:1337-1339) */
 		if (running && features != v) stop();
 		features = v;
 		break;
@@ -693,7 +754,7 @@ bool Session::handle_message()
 		break;
 	case SET_PROTOCOL_FEATURES:	/* vhost_user_set_protocol_features */
 		v = u64_of();
-		if (v & ~kProtocolFeatures) break;
+		if (v & ~kProtocolFeaturesRef) break;
 		stop();
 		protocol_features = v;
 		break;

@@ -75,6 +75,8 @@ SYMBOLS = [
     ("oimgpu_vhost_scsi_add_lun", _I, [C.c_char_p, _I, C.c_char_p]),
     ("oimgpu_vhost_scsi_remove_target", _I, [C.c_char_p, _I]),
     ("oimgpu_vhost_ctrlr_remove", _I, [C.c_char_p]),
+    ("oimgpu_vhost_ctrlr_set_coalescing", _I, [C.c_char_p, _U32, _U32]),
+    ("oimgpu_config_json", C.c_long, [C.c_char_p, C.c_char_p, C.c_size_t]),
     ("oimgpu_vhost_ctrlr_get", _I, [C.c_char_p, C.POINTER(CtrlrInfo)]),
     ("oimgpu_vhost_ctrlr_list", _I, [C.POINTER(CtrlrInfo), _I]),
     ("oimgpu_lun_open", _I, [C.c_char_p, _I, _U32, _U32, C.POINTER(_VP)]),

@@ -150,6 +150,16 @@ def test_rpc_transcript_matches_reference_server(servers):
                                                       "luns": [{"id": 0, "bdev_name": "MyVol"}]}
     both(servers, "get_vhost_controllers", {"name": "vhost.1"})
     assert both(servers, "get_vhost_controllers", {"name": "nope"})["error"]["code"] == -32603
+    # ---- interrupt coalescing (vhost_rpc.c:493-544, vhost.c:358-381)
+    assert both(servers, "set_vhost_controller_coalescing", {"ctrlr": "vhost.1", "delay_base_us": 50, "iops_threshold": 100000})["result"] is True
+    assert both(servers, "set_vhost_controller_coalescing", {"ctrlr": "vhost.1", "delay_base_us": 50, "iops_threshold": 99})["error"]["message"] == "Invalid argument"
+    assert both(servers, "set_vhost_controller_coalescing", {"ctrlr": "nope", "delay_base_us": 50, "iops_threshold": 100000})["error"]["message"] == "No such device"
+    both(servers, "set_vhost_controller_coalescing", {"ctrlr": "vhost.1", "delay_base_us": 50})
+    both(servers, "set_vhost_controller_coalescing", {"ctrlr": "vhost.1", "delay_base_us": -1, "iops_threshold": 100000})
+    both(servers, "set_vhost_controller_coalescing", {"ctrlr": vdir + "/vhost.1", "delay_base_us": 0, "iops_threshold": 1000})
+    c1 = both(servers, "get_vhost_controllers", {"name": "vhost.1"})["result"][0]
+    assert (c1["delay_base_us"], c1["iops_threshold"]) == (0, 1000)
+    both(servers, "set_vhost_controller_coalescing", {"ctrlr": "vhost.1", "delay_base_us": 25, "iops_threshold": 70000})
     # ---- get_bdevs_iostat (bdev_rpc.c:50-205): member names and order, one object per bdev in registration order
     st = both(servers, "get_bdevs_iostat")["result"]
     assert [x.get("name") for x in st[1:]] == ["Malloc0", "MyVol", "Malloc1", "WithUuid"] and "tick_rate" in st[0]
@@ -324,3 +334,61 @@ def test_rpc_random_call_sequences(servers):
             both(servers, "remove_vhost_controller", {"ctrlr": c})
         for b in both(servers, "get_bdevs")["result"]:
             both(servers, "delete_bdev", {"name": b["name"]})
+
+
+def test_config_dump_and_restore(tmp_path):
+    """get_subsystems / get_subsystem_config + tools/oimcfg.py: the {method, params} lists of
+    spdk_bdev_subsystem_config_json (S/lib/bdev/bdev.c:676-708; bdev_malloc.c:350-368, bdev_rbd.c:635-666) and
+    spdk_vhost_config_json (S/lib/vhost/vhost.c:1460-1494; vhost_scsi.c:1459-1499), replayed into a fresh daemon"""
+    from oim_b200 import build
+    build.build()
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import oimcfg
+
+    def daemon(tag):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "vhost").mkdir()
+        p = subprocess.Popen([DAEMON, "-r", str(d / "rpc.sock"), "-S", str(d / "vhost"), "--control-only"], stderr=subprocess.PIPE)
+        for _ in range(500):
+            if os.path.exists(d / "rpc.sock"):
+                break
+            time.sleep(0.01)
+        return p, oimcfg.Rpc(str(d / "rpc.sock"))
+    pa, a = daemon("a")
+    pb, b = daemon("b")
+    try:
+        a.call("construct_malloc_bdev", {"num_blocks": 131072, "block_size": 512})
+        a.call("construct_malloc_bdev", {"num_blocks": 4096, "block_size": 4096, "name": "Vol", "uuid": "11111111-2222-3333-4444-555555555555"})
+        a.call("construct_rbd_bdev", {"block_size": 512, "pool_name": "rbd", "rbd_name": "pvc-1", "user_id": "admin", "name": "Rbd0"})
+        a.call("construct_vhost_scsi_controller", {"ctrlr": "vhost.0"})
+        a.call("construct_vhost_scsi_controller", {"ctrlr": "vhost.1", "cpumask": "0x1"})
+        a.call("add_vhost_scsi_lun", {"ctrlr": "vhost.0", "scsi_target_num": 0, "bdev_name": "Malloc0"})
+        a.call("add_vhost_scsi_lun", {"ctrlr": "vhost.0", "scsi_target_num": 5, "bdev_name": "Rbd0"})
+        a.call("set_vhost_controller_coalescing", {"ctrlr": "vhost.1", "delay_base_us": 40, "iops_threshold": 80000})
+        assert [s["subsystem"] for s in a.call("get_subsystems")] == ["copy", "bdev", "scsi", "vhost"]
+        bd = a.call("get_subsystem_config", {"name": "bdev"})
+        assert bd[0] == {"method": "set_bdev_options", "params": {"bdev_io_pool_size": 65536, "bdev_io_cache_size": 256}}
+        assert bd[2] == {"method": "construct_malloc_bdev", "params": {"name": "Vol", "num_blocks": 4096, "block_size": 4096,
+                                                                       "uuid": "11111111-2222-3333-4444-555555555555"}}
+        assert bd[3] == {"method": "construct_rbd_bdev", "params": {"name": "Rbd0", "pool_name": "rbd", "rbd_name": "pvc-1",
+                                                                    "block_size": 512, "user_id": "admin"}}
+        vh = a.call("get_subsystem_config", {"name": "vhost"})
+        assert [x["method"] for x in vh] == ["construct_vhost_scsi_controller", "add_vhost_scsi_lun", "add_vhost_scsi_lun",
+                                             "construct_vhost_scsi_controller", "set_vhost_controller_coalescing"]
+        with pytest.raises(RuntimeError, match="Subsystem 'nope' not found"):
+            a.call("get_subsystem_config", {"name": "nope"})
+        cfg = oimcfg.save(a)
+        assert oimcfg.load(b, json.loads(json.dumps(cfg))) == 8
+
+        def strip(lst):                          # socket paths differ by directory
+            return [{k: v for k, v in c.items() if k != "socket"} for c in lst]
+        def bdevs(r):                            # construct_rbd_bdev carries no uuid (bdev_rbd.c:635-666): a restored RBD bdev gets a new one
+            return [{k: (v if k != "uuid" or x["product_name"] != "Ceph Rbd Disk" else "<new>") for k, v in x.items()} for x in r.call("get_bdevs")]
+        assert bdevs(a) == bdevs(b)
+        assert strip(a.call("get_vhost_controllers")) == strip(b.call("get_vhost_controllers"))
+        assert oimcfg.save(b) == cfg
+    finally:
+        for p in (pa, pb):
+            p.terminate()
+            p.wait(5)
