@@ -150,6 +150,10 @@ struct oimgpu_iostat {
 	uint64_t bytes_read, bytes_written, bytes_unmapped;
 	uint64_t num_errors;
 	uint64_t kernel_launches;	/* launches of our kernels on this LUN's stream */
+	/* get_bdevs_iostat read/write/unmap_latency_ticks (S/lib/bdev/rpc/bdev_rpc.c:51-105) in nanoseconds of the GPU's
+	 * global timer (tick_rate 1e9): per completed request, from the moment its pass was fetched to the moment its
+	 * data had moved, summed */
+	uint64_t read_latency_ns, write_latency_ns, unmap_latency_ns;
 };
 
 /* ---- lifecycle -------------------------------------------------------------------------- */

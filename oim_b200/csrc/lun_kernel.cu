@@ -1141,6 +1141,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		}
 		sh.pub_q = nullptr;
 		sh.pub_end = 0;
+		for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) sh.lat_ns[t][0] = sh.lat_ns[t][1] = sh.lat_ns[t][2] = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -1379,6 +1380,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					progress = true;
 				}
 				const uint32_t slot0 = q.head + done;
+				const uint64_t pass_t0 = globaltimer_ns();	/* the requests are in hand: their latency clock starts */
 				__syncwarp();
 				if (q.mode == QMODE_SLOTS) {
 #pragma unroll
@@ -1687,6 +1689,25 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 							st.vq_head[lane - r0] = (uint16_t)my_head;
 						}
 					}
+					/* latency accounting: the fill's good requests per target and kind (usually one target) */
+					{
+						uint32_t left = __ballot_sync(0xffffffffu, mine && good && s.op != OP_NONE);
+						uint32_t nt = 0;
+						while (left && nt < OIMGPU_CTRLR_MAX_DEVS) {
+							const uint32_t t = __shfl_sync(0xffffffffu, (uint32_t)s.tgt, __ffs(left) - 1);
+							const bool me = mine && good && s.op != OP_NONE && s.tgt == t;
+							const uint32_t rd = __ballot_sync(0xffffffffu, me && s.op == OP_READ);
+							const uint32_t wr = __ballot_sync(0xffffffffu, me && s.op == OP_WRITE);
+							const uint32_t um = __ballot_sync(0xffffffffu, me && s.op == OP_UNMAP);
+							if (lane == 0) {
+								st.lat_tgt[nt] = (uint8_t)t;
+								st.lat_n[nt][0] = (uint16_t)__popc(rd); st.lat_n[nt][1] = (uint16_t)__popc(wr); st.lat_n[nt][2] = (uint16_t)__popc(um);
+							}
+							left &= ~(rd | wr | um);
+							nt++;
+						}
+						if (lane == 0) st.lat_ntgt = (uint8_t)nt;
+					}
 					const uint32_t tot_seg = __shfl_sync(0xffffffffu, seg_incl, r1 - 1);
 					const uint32_t tot_unit = __shfl_sync(0xffffffffu, unit_incl, r1 - 1);
 					if (lane == 0) {
@@ -1713,6 +1734,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						st.used_base = vq_last_used + done + r0;
 						st.done = persistent ? q.done : nullptr;
 						st.unit_ctr = 0;
+						st.t0 = pass_t0;
 						st.share = qs;
 						st.share_pos = done + r0;
 						st.share_final = q.count;
@@ -1776,6 +1798,13 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			if (st_wr) { atomicAdd(&lun->stats[1], (unsigned long long)st_wr); atomicAdd(&lun->stats[5], st_wb); }
 			if (st_um) atomicAdd(&lun->stats[2], (unsigned long long)st_um);
 			if (st_er) atomicAdd(&lun->stats[7], (unsigned long long)st_er);
+			/* every fill is retired: mover warp 0 is done adding */
+			for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+				LunCtx *T = (t == lun->target) ? lun : lun->peer[t];
+				for (int k = 0; k < 3 && T; k++) {
+					if (sh.lat_ns[t][k]) atomicAdd(&T->stats[8 + k], sh.lat_ns[t][k]);
+				}
+			}
 		}
 	} else {
 		/* ======================= MOVERS ======================= */
@@ -1839,6 +1868,13 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					}
 				}
 				if (nw > 1) movers_barrier();
+			}
+			if (mw == 0 && lane == 0 && st.lat_ntgt) {
+				const unsigned long long dt = globaltimer_ns() - st.t0;
+				for (uint32_t i = 0; i < st.lat_ntgt; i++) {
+					unsigned long long *acc = sh.lat_ns[st.lat_tgt[i] & (OIMGPU_CTRLR_MAX_DEVS - 1)];
+					acc[0] += dt * st.lat_n[i][0]; acc[1] += dt * st.lat_n[i][1]; acc[2] += dt * st.lat_n[i][2];
+				}
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&sh.empty[sidx]);

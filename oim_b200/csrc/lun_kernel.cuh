@@ -82,7 +82,8 @@ struct LunCtx {
 	int32_t  scsi_dev_id;
 	uint16_t port_index;
 	uint8_t  protocol_id;
-	unsigned long long stats[8];	/* read ops, write ops, unmap ops, other, bytes r/w/unmapped, errors */
+	unsigned long long stats[12];	/* read ops, write ops, unmap ops, other, bytes r/w/unmapped, errors,
+					 * [8..10] summed latency in ns of reads / writes / unmaps (get_bdevs_iostat *_latency_ticks) */
 	/* the other SCSI devices of the same vhost controller (svdev->scsi_dev[8], vhost_scsi.c:80-94):
 	 * one set of virtqueues serves them all */
 	LunCtx *peer[OIMGPU_CTRLR_MAX_DEVS];
@@ -229,7 +230,12 @@ struct __align__(16) Stage {
 	uint32_t share_final;		/* launch + virtqueue: position at which the ring cursors are written back (count) */
 	uint32_t persistent;
 	uint32_t unit_ctr;		/* shared kernels: movers draw units from here (mover 0 also publishes, so it takes fewer) */
-	uint32_t pad_[3];
+	/* latency accounting (spdk_bdev_io_complete adds now - submit_tsc per I/O type, bdev.c:3316-3371): when the
+	 * pass was taken and how many of the fill's requests count as reads / writes / unmaps; mover warp 0 adds
+	 * (now - t0) x count when the fill's data has moved - the parser only stamps */
+	uint64_t t0;
+	uint8_t  lat_ntgt, lat_tgt[OIMGPU_CTRLR_MAX_DEVS];	/* the SCSI targets the fill's good requests went to ... */
+	uint16_t lat_n[OIMGPU_CTRLR_MAX_DEVS][3];		/* ... and how many reads / writes / unmaps each */
 };
 
 /* Store ranges of one pass, for hazard detection against the passes after it (parser-private).
@@ -259,6 +265,7 @@ struct __align__(16) CtaShared {
 	uint64_t released[kStages];	/* shared kernels: the fill's completions are published, the stage may be refilled */
 	QShare  *pub_q;			/* shared kernels, mover warp 0: queue and end position of its last publication */
 	uint32_t pub_end;
+	unsigned long long lat_ns[OIMGPU_CTRLR_MAX_DEVS][3];	/* mover warp 0, lane 0: summed latencies of this CTA per target (reads, writes, unmaps) */
 };
 
 /* ------------------------------------------------------------------------------------------ */

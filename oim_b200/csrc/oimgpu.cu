@@ -79,7 +79,7 @@ struct Bdev {
 	std::vector<int> devices;	/* replica r lives on devices[r] (an imported replica: the device it is reached from) */
 	std::vector<uint8_t *> stores;
 	std::vector<char> imported;	/* replica r is another process's store, opened from a CUDA IPC handle */
-	unsigned long long retired[8] = {};	/* counters of sessions that are gone (same layout as LunCtx::stats) */
+	unsigned long long retired[12] = {};	/* counters of sessions that are gone (same layout as LunCtx::stats) */
 };
 
 struct Ctrlr {
@@ -236,13 +236,13 @@ static void fill_lun_ctx(LunCtx &c, const Bdev &b, const Ctrlr &ctrlr, int targe
 }
 
 /* counters of one device-resident context, read on the housekeeping stream (works next to a resident poller) */
-static bool read_ctx_stats(int device, const LunCtx *d_ctx, unsigned long long out[8])
+static bool read_ctx_stats(int device, const LunCtx *d_ctx, unsigned long long out[12])
 {
 	const int slot = find_device_slot(device);
 	if (slot < 0 || !d_ctx) return false;
 	cudaSetDevice(device);
 	cudaStream_t st = g.devices[slot].util;
-	if (cudaMemcpyAsync(out, (const uint8_t *)d_ctx + offsetof(LunCtx, stats), sizeof(unsigned long long) * 8,
+	if (cudaMemcpyAsync(out, (const uint8_t *)d_ctx + offsetof(LunCtx, stats), sizeof(unsigned long long) * 12,
 			    cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
 	return cudaStreamSynchronize(st) == cudaSuccess;
 }
@@ -251,9 +251,9 @@ static bool read_ctx_stats(int device, const LunCtx *d_ctx, unsigned long long o
 static void retire_stats_locked(const std::string &bdev, int device, const LunCtx *d_ctx)
 {
 	auto bi = g.bdevs.find(bdev);
-	unsigned long long v[8];
+	unsigned long long v[12];
 	if (bi == g.bdevs.end() || !read_ctx_stats(device, d_ctx, v)) return;
-	for (int k = 0; k < 8; k++) bi->second->retired[k] += v[k];
+	for (int k = 0; k < 12; k++) bi->second->retired[k] += v[k];
 }
 
 static bool device_reachable(int from, int to)
@@ -1706,6 +1706,9 @@ static int read_iostat(oimgpu_lun *L, const LunCtx *d_ctx, oimgpu_iostat *out)
 	out->bytes_written = c.stats[5];
 	out->bytes_unmapped = c.stats[6];
 	out->num_errors = c.stats[7];
+	out->read_latency_ns = c.stats[8];
+	out->write_latency_ns = c.stats[9];
+	out->unmap_latency_ns = c.stats[10];
 	out->kernel_launches = L->launches;
 	return 0;
 }
@@ -1734,7 +1737,7 @@ extern "C" int oimgpu_bdev_iostat(const char *name, oimgpu_iostat *out)
 	if (!g.inited) return -ENODEV;
 	auto it = g.bdevs.find(name ? name : "");
 	if (it == g.bdevs.end()) return -ENODEV;
-	unsigned long long sum[8], v[8];
+	unsigned long long sum[12], v[12];
 	memcpy(sum, it->second->retired, sizeof(sum));
 	for (oimgpu_lun *L : g.handles) {
 		if (L->bdev == it->first && read_ctx_stats(L->device, L->d_ctx, v)) {
@@ -1755,6 +1758,9 @@ extern "C" int oimgpu_bdev_iostat(const char *name, oimgpu_iostat *out)
 	out->bytes_written = sum[5];
 	out->bytes_unmapped = sum[6];
 	out->num_errors = sum[7];
+	out->read_latency_ns = sum[8];
+	out->write_latency_ns = sum[9];
+	out->unmap_latency_ns = sum[10];
 	return 0;
 }
 

@@ -392,8 +392,8 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 		return result(id, out + "]");
 	}
 	if (method == "get_bdevs_iostat") {
-		/* S/lib/bdev/rpc/bdev_rpc.c:50-205.  Latencies are not tracked per request on the GPU path: the three
-		 * *_latency_ticks members are reported as 0; tick_rate is the GPU's global timer (1 GHz). */
+		/* S/lib/bdev/rpc/bdev_rpc.c:50-205.  tick_rate is the GPU's global timer (1 GHz); the *_latency_ticks are summed
+		 * per request by the mover warps (pass fetched -> data moved), see include/oimgpu.h struct oimgpu_iostat. */
 		if (params && !decode(params, {{"name", Json::Str, true, &a}})) return bad;
 		std::vector<std::string> names;
 		if (a) {
@@ -414,7 +414,8 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 			       ",\"num_read_ops\":" + std::to_string(st.num_read_ops) + ",\"bytes_written\":" + std::to_string(st.bytes_written) +
 			       ",\"num_write_ops\":" + std::to_string(st.num_write_ops) + ",\"bytes_unmapped\":" + std::to_string(st.bytes_unmapped) +
 			       ",\"num_unmap_ops\":" + std::to_string(st.num_unmap_ops) +
-			       ",\"read_latency_ticks\":0,\"write_latency_ticks\":0,\"unmap_latency_ticks\":0}";
+			       ",\"read_latency_ticks\":" + std::to_string(st.read_latency_ns) + ",\"write_latency_ticks\":" +
+			       std::to_string(st.write_latency_ns) + ",\"unmap_latency_ticks\":" + std::to_string(st.unmap_latency_ns) + "}";
 		}
 		return result(id, out + "]");
 	}

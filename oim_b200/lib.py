@@ -46,7 +46,7 @@ class CtrlrInfo(C.Structure):
 class IoStat(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("num_read_ops", "num_write_ops", "num_unmap_ops", "num_other_ops",
                                           "bytes_read", "bytes_written", "bytes_unmapped", "num_errors",
-                                          "kernel_launches")]
+                                          "kernel_launches", "read_latency_ns", "write_latency_ns", "unmap_latency_ns")]
 
 
 # every symbol include/oimgpu.h declares: (name, restype, argtypes)

@@ -209,6 +209,12 @@ def test_cuda_multi_queue_partitioned_mixed(gpu, oracles):
         assert stats["num_read_ops"] == t.meta["reads"]
         assert stats["num_write_ops"] == nq * per_q - t.meta["reads"]
         assert stats["bytes_read"] == t.meta["reads"] * 4096
+        # latency accounting (get_bdevs_iostat *_latency_ticks): summed per request by the mover warps, in ns;
+        # a request cannot complete faster than a memory round trip nor slower than the whole launch took
+        for kind, n in (("read", t.meta["reads"]), ("write", nq * per_q - t.meta["reads"])):
+            per = stats[f"{kind}_latency_ns"] / n
+            assert 300 < per < 50e6, f"{kind}: {per} ns per request"
+        assert stats["unmap_latency_ns"] == 0
     finally:
         gpu.remove_vhost_scsi_target("mq.ctl", 0)
         gpu.remove_vhost_controller("mq.ctl")

@@ -341,6 +341,8 @@ def test_cuda_vhost_user_io_matches_reference(slaves, mode):
     a = json.loads(re.sub(rb'"(tick_rate|\w+_latency_ticks)":\d+', rb'"\1":0', ours.call("get_bdevs_iostat")))["result"]
     b = json.loads(re.sub(rb'"(tick_rate|\w+_latency_ticks)":\d+', rb'"\1":0', ref.call("get_bdevs_iostat")))["result"]
     assert a == b, f"iostat differs:\nours {a}\nref  {b}"
+    raw = [x for x in json.loads(ours.call("get_bdevs_iostat"))["result"] if x.get("name") == "M0"][0]
+    assert raw["read_latency_ticks"] > 0 and raw["write_latency_ticks"] > 0, raw      # summed by the mover warps, 1 GHz ticks
     m0 = [x for x in a if x.get("name") == "M0"][0]
     assert m0["num_read_ops"] > 0 and m0["num_write_ops"] > 0 and [x for x in a if x.get("name") == "M1"][0]["num_read_ops"] == 1
 
