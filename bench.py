@@ -840,6 +840,26 @@ def run_ours(args, rank, world, local):
                                  "RAM (host memory, pinned by the daemon), 1 GiB Malloc bdev"}
         except Exception as e:                          # a leg that cannot run must not cost the headline line
             vuser = {"error": f"{type(e).__name__}: {e}"[:300]}
+    # ---- OIM's real attach shape on a multi-GPU box: ONE daemon owning all N GPUs, ONE controller with N targets (one
+    # volume per GPU), ONE vhost-user session whose request queues are dealt out over the GPUs ----
+    vuser_multi = None
+    if world >= 2 and not args.no_vu:
+        lib.fini()                                  # every rank lets go of its GPU's memory; rank 0's daemon takes all N GPUs
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                one = vhost_user_leg(args, local, "kick", (254,))
+                allg = vhost_user_leg(args, local, "kick", (254,), gpus=list(range(world)))
+                vuser_multi = {"one_gpu_one_lun": one, f"{world}_gpus_{world}_luns_one_controller": allg,
+                               "speedup": allg["value"] / one["value"],
+                               "workload": f"one oim-gpu-vhost --gpus 0..{world - 1}, one controller, {world} targets (1 GiB Malloc bdev each, placed "
+                                           "one per GPU), one vhost-user session with 254 request queues x 256 READ(10) of 4 KiB per round, requests "
+                                           "dealt out over the targets; queue r is served by GPU r mod N (any GPU reaches any target: own HBM or "
+                                           "a peer's over NVLink), so payload crosses all N PCIe links; single-process Python master"}
+            except Exception as e:  # noqa: BLE001
+                vuser_multi = {"error": f"{type(e).__name__}: {e}"[:300]}
+        barrier()
     if rank == 0:
         line = {
             "metric": "4KiB rand-read IOPS", "value": iops, "unit": "IOPS", "n_gpus": world, "steps": args.steps,
@@ -858,7 +878,7 @@ def run_ours(args, rank, world, local):
                          "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
             "seq128k": seq, "virtqueue": vq, "mixed_70_30": mixed, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
-            "vhost_user": vuser, "more": extra, "mirror": mirror, "queue_sweep": sweep, "seq128k_sg": seq_sg,
+            "vhost_user": vuser, "more": extra, "mirror": mirror, "queue_sweep": sweep, "seq128k_sg": seq_sg, "vhost_user_multi_gpu": vuser_multi,
         }
         print(json.dumps(line))
     if world > 1:
@@ -866,7 +886,7 @@ def run_ours(args, rank, world, local):
         dist.destroy_process_group()
 
 
-def vhost_user_leg(args, device: int, mode: str, queue_counts=(64,)) -> dict:
+def vhost_user_leg(args, device: int, mode: str, queue_counts=(64,), gpus=None) -> dict:
     """The path a VM takes: oim-gpu-vhost as a separate process, a vhost-user master (what QEMU is) connected
     to <socket dir>/scsi0, guest RAM in a shared memfd that the daemon pins for the GPU, 4 KiB random READs
     published on virtio rings and kicked through eventfds; completion = used index + call eventfd.
@@ -892,7 +912,8 @@ def vhost_user_leg(args, device: int, mode: str, queue_counts=(64,)) -> dict:
         # slave: one reactor core polling the rings, exactly what QEMU would talk to in an SPDK deployment
         cmd = [sys.executable, os.path.join(ROOT, "tests", "ref_rpc_server.py"), rpc, os.path.join(tmp, "vhost"), "vhost", "busy"]
     else:
-        cmd = [build.DAEMON, "-r", rpc, "-S", os.path.join(tmp, "vhost"), "--gpus", str(device)] + (["--poller"] if mode == "poller" else [])
+        cmd = ([build.DAEMON, "-r", rpc, "-S", os.path.join(tmp, "vhost"), "--gpus", ",".join(str(x) for x in (gpus or [device]))] +
+               (["--poller"] if mode == "poller" else []))
     proc = subprocess.Popen(cmd, stdout=log, stderr=log)
     try:
         t0 = time.time()
@@ -914,11 +935,15 @@ def vhost_user_leg(args, device: int, mode: str, queue_counts=(64,)) -> dict:
             while not buf.endswith(b"\n"):
                 buf += c.recv(65536)
             return _json.loads(buf)
-        assert call(1, "construct_malloc_bdev", {"num_blocks": nb, "block_size": BLOCK, "name": "M0"})["result"] == "M0"
+        # OIM's shape (MapVolume, controller.go:131-148): ONE controller, every volume another target of it; with several
+        # GPUs the daemon places the bdevs round-robin (least-loaded GPU) and deals the session's queues out over the GPUs
+        ntgt = len(gpus) if gpus else 1
         assert call(2, "construct_vhost_scsi_controller", {"ctrlr": "scsi0"})["result"] is True
-        assert call(3, "add_vhost_scsi_lun", {"ctrlr": "scsi0", "scsi_target_num": 0, "bdev_name": "M0"})["result"] == 0
+        for t in range(ntgt):
+            assert call(10 + t, "construct_malloc_bdev", {"num_blocks": nb, "block_size": BLOCK, "name": f"M{t}"})["result"] == f"M{t}"
+            assert call(30 + t, "add_vhost_scsi_lun", {"ctrlr": "scsi0", "scsi_target_num": t, "bdev_name": f"M{t}"})["result"] == t
 
-        g = vring.build_uniform_queues(max_q, per_q, nb, ring_size=ring, seed=77)
+        g = vring.build_uniform_queues(max_q, per_q, nb, ring_size=ring, seed=77, ntargets=ntgt)
         tail = 2 << 20                                   # control / event rings live behind the payload area
         total = -(-(g.total_bytes() + tail) // (2 << 20)) * (2 << 20)
         ram = vu.GuestRam(total)

@@ -257,6 +257,10 @@ typedef struct oimgpu_lun oimgpu_lun;	/* a data-path session on a vhost controll
  * session with no home device (what a vhost-user connection is): it may start with zero targets. */
 int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t num_queues,
 		    uint32_t queue_size, oimgpu_lun **out);
+/* the same controller-wide session (as scsi_target_num == -1) placed on GPU `device` instead of the first target's:
+ * one per GPU lets a single vhost-user connection use every GPU's PCIe link (see oim_b200/daemon/vhost_user.cpp) */
+int oimgpu_lun_open_on(const char *ctrlr, int device, uint32_t num_queues, uint32_t queue_size, oimgpu_lun **out);
+int oimgpu_device_ordinal(int index);		/* CUDA ordinal of the index-th initialised GPU (0 <= index < oimgpu_device_count()) */
 int oimgpu_lun_close(oimgpu_lun *lun);
 int oimgpu_lun_device(const oimgpu_lun *lun);
 /* launches so far in which the CTAs SHARED the queues a pass at a time (fewer queues than the GPU holds CTAs)

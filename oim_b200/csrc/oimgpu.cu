@@ -1137,8 +1137,32 @@ static void free_lun_resources(oimgpu_lun *L)
 	(void)cudaGetLastError();
 }
 
+static int lun_open_on(const char *ctrlr, int scsi_target_num, int on_device, uint32_t num_queues, uint32_t queue_size, oimgpu_lun **out);
+
 extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t num_queues,
 			       uint32_t queue_size, oimgpu_lun **out)
+{
+	return lun_open_on(ctrlr, scsi_target_num, -1, num_queues, queue_size, out);
+}
+
+/* a controller-wide session (scsi_target_num == -1) on a GPU of the caller's choice: every target of the controller
+ * is reached from there, local ones in its own HBM, the others over NVLink (peer mappings).  A daemon that owns
+ * several GPUs opens one such session per GPU for ONE vhost-user connection and deals the guest's request queues
+ * out among them, so that payload crosses every GPU's PCIe link, wherever the volumes live. */
+extern "C" int oimgpu_lun_open_on(const char *ctrlr, int device, uint32_t num_queues, uint32_t queue_size, oimgpu_lun **out)
+{
+	if (device < 0) return -EINVAL;
+	return lun_open_on(ctrlr, -1, device, num_queues, queue_size, out);
+}
+
+extern "C" int oimgpu_device_ordinal(int index)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (index < 0 || index >= (int)g.devices.size()) return -EINVAL;
+	return g.devices[index].ordinal;
+}
+
+static int lun_open_on(const char *ctrlr, int scsi_target_num, int on_device, uint32_t num_queues, uint32_t queue_size, oimgpu_lun **out)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (!g.inited || g.control_only) return -ENODEV;
@@ -1159,6 +1183,10 @@ extern "C" int oimgpu_lun_open(const char *ctrlr, int scsi_target_num, uint32_t 
 	int session_device = g.devices[0].ordinal;
 	for (int t = 0; session && t < OIMGPU_CTRLR_MAX_DEVS; t++) {
 		if (!it->second->targets[t].empty()) { session_device = g.bdevs[it->second->targets[t]]->devices[0]; break; }
+	}
+	if (on_device >= 0) {
+		if (!session || find_device_slot(on_device) < 0) return -EINVAL;
+		session_device = on_device;
 	}
 
 	/* whatever a failed step leaves behind (streams, events, pinned and device allocations) is released here */

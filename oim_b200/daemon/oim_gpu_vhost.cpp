@@ -644,6 +644,7 @@ int main(int argc, char **argv)
 		else if (a == "--control-only") control_only = true;	/* protocol tests without a GPU: no data path */
 		else if (a == "--poller") vu_cfg.poller = true;		/* a resident GPU poller per vhost-user session */
 		else if (a == "--no-vhost-user") g_serve_vhost_user = false;
+		else if (a == "--no-spread") vu_cfg.spread = false;	/* several GPUs: keep a session on the GPU of its first target */
 		else if (a == "--rbd-size") g_rbd_default_size = strtoull(next(), nullptr, 0);
 		else if (a == "--gpus") {
 			std::string l = next();

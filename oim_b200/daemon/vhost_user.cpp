@@ -9,6 +9,7 @@
  */
 #include "vhost_user.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cerrno>
 #include <cstdint>
@@ -157,8 +158,15 @@ struct Session {
 	std::vector<Vq> vq;
 	bool running = false;
 	uint32_t max_queues = 0;
-	oimgpu_lun *lun = nullptr;
+	/* One data-path session per GPU the daemon owns: request queue r is served by luns[r % G] as its queue r / G.
+	 * OIM attaches every volume as another target of the ONE controller (pkg/oim-controller/controller.go:131-148) and
+	 * the targets may live on different GPUs; any GPU reaches any target (its own HBM or a peer's over NVLink), so
+	 * dealing out the QUEUES spreads the guest-memory traffic over every GPU's PCIe link and keeps each used ring
+	 * single-writer. */
+	std::vector<oimgpu_lun *> luns;
+	oimgpu_lun *lun = nullptr;	/* luns[0]: "the data path is open" */
 	uint32_t lun_queues = 0;
+	void close_luns();
 	bool polling = false;
 	std::mutex ev_mu;
 	std::vector<std::pair<int, bool>> events;	/* hot-plug notifications from the RPC thread */
@@ -490,7 +498,7 @@ void Session::process_controlq()
 					/* mgmt_task_submit (vhost_scsi.c:340-346): everything in flight on the device
 					 * finishes, then FUNCTION COMPLETE; the used length of a management task is
 					 * whatever the slot's task last carried - zero */
-					if (lun && !polling) oimgpu_lun_sync(lun);
+					if (lun && !polling) { for (oimgpu_lun *l : luns) oimgpu_lun_sync(l); }
 					*resp = 0;	/* VIRTIO_SCSI_S_OK */
 					break;		/* used_len stays 0 */
 				} else {
@@ -597,29 +605,40 @@ bool Session::start()
 			r.dev = dev;
 		}
 		const uint32_t want = max_queues > 2 ? max_queues - 2 : 1;
-		if (lun && lun_queues != want) { oimgpu_lun_close(lun); lun = nullptr; }
+		const uint32_t ngpu = g_cfg.spread ? std::max(1, std::min(oimgpu_device_count(), (int)want)) : 1;
+		if (lun && (lun_queues != want || luns.size() != ngpu)) close_luns();
 		if (!lun) {
-			int rc = oimgpu_lun_open(srv->name.c_str(), -1, want, 32, &lun);
-			if (rc != 0) {
-				fprintf(stderr, "oim-gpu-vhost: %s: cannot open the data path: %s\n", srv->name.c_str(), strerror(-rc));
-				lun = nullptr;
-				return false;
+			for (uint32_t gidx = 0; gidx < ngpu; gidx++) {
+				oimgpu_lun *l = nullptr;
+				const uint32_t nq = (want + ngpu - 1 - gidx) / ngpu;	/* queues gidx, gidx + G, ... */
+				int rc = ngpu == 1 ? oimgpu_lun_open(srv->name.c_str(), -1, want, 32, &l)
+						   : oimgpu_lun_open_on(srv->name.c_str(), oimgpu_device_ordinal((int)gidx), nq ? nq : 1, 32, &l);
+				if (rc != 0) {
+					fprintf(stderr, "oim-gpu-vhost: %s: cannot open the data path: %s\n", srv->name.c_str(), strerror(-rc));
+					close_luns();
+					return false;
+				}
+				luns.push_back(l);
 			}
+			lun = luns[0];
 			lun_queues = want;
 		}
-		VU_DEBUG("%s: session %d: data path open", srv->name.c_str(), fd);
+		VU_DEBUG("%s: session %d: data path open on %zu GPU(s)", srv->name.c_str(), fd, luns.size());
 		std::vector<oimgpu_mem_region> tbl;
 		for (const Region &r : mem) tbl.push_back({r.gpa, r.size, r.dev});
-		int mrc = oimgpu_lun_set_mem_table(lun, tbl.data(), (uint32_t)tbl.size());
-		if (mrc != 0) {
-			fprintf(stderr, "oim-gpu-vhost: %s: memory table refused: %s\n", srv->name.c_str(), strerror(-mrc));
-			return false;
+		for (oimgpu_lun *l : luns) {
+			int mrc = oimgpu_lun_set_mem_table(l, tbl.data(), (uint32_t)tbl.size());
+			if (mrc != 0) {
+				fprintf(stderr, "oim-gpu-vhost: %s: memory table refused: %s\n", srv->name.c_str(), strerror(-mrc));
+				return false;
+			}
 		}
 		for (uint32_t i = 2; i < max_queues; i++) {
 			Vq &q = vq[i];
 			q.attached = false;
 			if (!q.desc || !q.size) continue;
-			int rc = oimgpu_vq_attach(lun, i - 2, (void *)(uintptr_t)host_to_dev(q.desc), (void *)(uintptr_t)host_to_dev(q.avail),
+			const uint32_t r = i - 2, G = (uint32_t)luns.size();
+			int rc = oimgpu_vq_attach(luns[r % G], r / G, (void *)(uintptr_t)host_to_dev(q.desc), (void *)(uintptr_t)host_to_dev(q.avail),
 						  (void *)(uintptr_t)host_to_dev(q.used), q.size, q.last_avail, q.last_used);
 			if (rc != 0) {
 				fprintf(stderr, "oim-gpu-vhost: %s: queue %u: %s\n", srv->name.c_str(), i, strerror(-rc));
@@ -629,9 +648,15 @@ bool Session::start()
 		}
 		VU_DEBUG("%s: session %d: rings attached", srv->name.c_str(), fd);
 		if (g_cfg.poller) {
-			int rc = oimgpu_lun_start_poller(lun, 0, 0);
-			polling = rc >= 0;
-			if (!polling) fprintf(stderr, "oim-gpu-vhost: %s: resident poller: %s\n", srv->name.c_str(), strerror(-rc));
+			polling = true;
+			for (oimgpu_lun *l : luns) {
+				int rc = oimgpu_lun_start_poller(l, 0, 0);
+				if (rc < 0) {
+					fprintf(stderr, "oim-gpu-vhost: %s: resident poller: %s\n", srv->name.c_str(), strerror(-rc));
+					polling = false;
+				}
+			}
+			if (!polling) { for (oimgpu_lun *l : luns) oimgpu_lun_stop_poller(l); }
 		}
 	}
 	running = true;
@@ -640,18 +665,26 @@ bool Session::start()
 	return true;
 }
 
+void Session::close_luns()
+{
+	for (oimgpu_lun *l : luns) oimgpu_lun_close(l);
+	luns.clear();
+	lun = nullptr;
+}
+
 /* stop_device (vhost.c:994-1041): quiesce, remember where every ring stopped */
 void Session::stop()
 {
 	if (!running) return;
 	VU_DEBUG("%s: session %d: stopping", srv->name.c_str(), fd);
 	if (lun) {
-		if (polling) { oimgpu_lun_stop_poller(lun); polling = false; }
-		oimgpu_lun_sync(lun);
+		if (polling) { for (oimgpu_lun *l : luns) oimgpu_lun_stop_poller(l); polling = false; }
+		for (oimgpu_lun *l : luns) oimgpu_lun_sync(l);
 		for (uint32_t i = 2; i < vq.size(); i++) {
 			if (!vq[i].attached) continue;
 			uint16_t la = 0, lu = 0;
-			if (oimgpu_vq_detach(lun, i - 2, &la, &lu) == 0) { vq[i].last_avail = la; vq[i].last_used = lu; }
+			const uint32_t r = i - 2, G = (uint32_t)luns.size();
+			if (oimgpu_vq_detach(luns[r % G], r / G, &la, &lu) == 0) { vq[i].last_avail = la; vq[i].last_used = lu; }
 			vq[i].attached = false;
 		}
 	}
@@ -687,8 +720,10 @@ void Session::service()
 				if (a != q.consumed) { q.consumed = a; work = true; }
 			}
 			if (!work) break;
-			if (oimgpu_vq_kick(lun) < 0) break;
-			oimgpu_lun_sync(lun);
+			bool failed = false;
+			for (oimgpu_lun *l : luns) failed |= oimgpu_vq_kick(l) < 0;	/* every GPU starts on its queues ... */
+			if (failed) break;
+			for (oimgpu_lun *l : luns) oimgpu_lun_sync(l);			/* ... before any is waited for */
 			for (uint32_t i = 2; i < vq.size(); i++) {
 				if (vq[i].attached) signal_used(vq[i]);
 			}
@@ -762,7 +797,7 @@ bool Session::handle_message()
 		break;
 	case RESET_OWNER:	/* vhost_user_reset_owner: back to the state of a fresh connection */
 		stop();
-		if (lun) { oimgpu_lun_close(lun); lun = nullptr; }
+		close_luns();
 		free_mem();
 		for (Vq &q : vq) { if (q.kickfd >= 0) close(q.kickfd); if (q.callfd >= 0) close(q.callfd); }
 		vq.clear();
@@ -881,7 +916,7 @@ void Session::teardown()
 {
 	VU_DEBUG("%s: session %d: teardown", srv->name.c_str(), fd);
 	stop();
-	if (lun) { oimgpu_lun_close(lun); lun = nullptr; }
+	close_luns();
 	VU_DEBUG("%s: session %d: data path closed", srv->name.c_str(), fd);
 	free_mem();
 	VU_DEBUG("%s: session %d: guest memory released", srv->name.c_str(), fd);

@@ -16,6 +16,7 @@ namespace vhost_user {
 struct Config {
 	bool control_only = false;	/* no CUDA: handshake only (protocol tests) */
 	bool poller = false;		/* resident GPU poller per session instead of one launch per kick */
+	bool spread = true;		/* several GPUs: a session's request queues are dealt out among all of them */
 };
 
 void configure(const Config &cfg);

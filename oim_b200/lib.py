@@ -80,6 +80,8 @@ SYMBOLS = [
     ("oimgpu_vhost_ctrlr_get", _I, [C.c_char_p, C.POINTER(CtrlrInfo)]),
     ("oimgpu_vhost_ctrlr_list", _I, [C.POINTER(CtrlrInfo), _I]),
     ("oimgpu_lun_open", _I, [C.c_char_p, _I, _U32, _U32, C.POINTER(_VP)]),
+    ("oimgpu_lun_open_on", _I, [C.c_char_p, _I, _U32, _U32, C.POINTER(_VP)]),
+    ("oimgpu_device_ordinal", _I, [_I]),
     ("oimgpu_lun_close", _I, [_VP]),
     ("oimgpu_lun_device", _I, [_VP]),
     ("oimgpu_lun_shared_launches", C.c_longlong, [_VP]),

@@ -277,7 +277,7 @@ class UniformGuest:
 
 
 def build_uniform_queues(nq: int, per_q: int, num_blocks: int, *, io_blocks: int = 8, ring_size: int = 1024,
-                         seed: int = 1, target: int = 0, gpa_base: int = R2_GPA) -> UniformGuest:
+                         seed: int = 1, target: int = 0, gpa_base: int = R2_GPA, ntargets: int = 1) -> UniformGuest:
     """nq virtqueues, each holding per_q READ(10) requests of io_blocks as 3-descriptor direct chains
     [RO req 51 B][WR resp 108 B][WR data], random LBAs over the whole device (reads only: no ordering
     question).  The avail ring is pre-filled with the heads repeated ring_size/per_q times, so bumping
@@ -319,6 +319,8 @@ def build_uniform_queues(nq: int, per_q: int, num_blocks: int, *, io_blocks: int
     lba = (rnd % np.uint64(num_blocks // io_blocks)) * np.uint64(io_blocks)
     hdr = np.zeros((nq, per_q, 64), dtype=np.uint8)
     hdr[:, :, 0:8] = abi.virtio_lun(target)
+    if ntargets > 1:                                     # requests dealt out over targets target .. target+ntargets-1 (lun[1])
+        hdr[:, :, 1] = (target + (np.arange(nq)[:, None] * per_q + np.arange(per_q)[None, :]) % ntargets).astype(np.uint8)
     hdr[:, :, 19] = abi.READ_10
     hdr[:, :, 21:25] = lba.astype(">u4").view(np.uint8).reshape(nq, per_q, 4)
     hdr[:, :, 26:28] = np.array([io_blocks >> 8, io_blocks & 0xFF], dtype=np.uint8)
