@@ -844,9 +844,13 @@ def run_ours(args, rank, world, local):
     # volume per GPU), ONE vhost-user session whose request queues are dealt out over the GPUs ----
     vuser_multi = None
     if world >= 2 and not args.no_vu:
+        import torch.distributed as dist
         lib.fini()                                  # every rank lets go of its GPU's memory; rank 0's daemon takes all N GPUs
         torch.cuda.empty_cache()
         barrier()
+        # the other ranks wait on the rendezvous store, on the CPU: an NCCL barrier would spin a kernel on their GPUs,
+        # which are the daemon's GPUs for this leg
+        store = dist.distributed_c10d._get_default_store()
         if rank == 0:
             try:
                 one = vhost_user_leg(args, local, "kick", (254,))
@@ -859,6 +863,9 @@ def run_ours(args, rank, world, local):
                                            "a peer's over NVLink), so payload crosses all N PCIe links; single-process Python master"}
             except Exception as e:  # noqa: BLE001
                 vuser_multi = {"error": f"{type(e).__name__}: {e}"[:300]}
+            store.set("oim_multi_gpu_leg_done", "1")
+        else:
+            store.wait(["oim_multi_gpu_leg_done"])
         barrier()
     if rank == 0:
         line = {
@@ -886,7 +893,7 @@ def run_ours(args, rank, world, local):
         dist.destroy_process_group()
 
 
-def vhost_user_leg(args, device: int, mode: str, queue_counts=(64,), gpus=None) -> dict:
+def vhost_user_leg(args, device: int, mode: str, queue_counts=(64,), gpus=None, daemon_args=(), env=None) -> dict:
     """The path a VM takes: oim-gpu-vhost as a separate process, a vhost-user master (what QEMU is) connected
     to <socket dir>/scsi0, guest RAM in a shared memfd that the daemon pins for the GPU, 4 KiB random READs
     published on virtio rings and kicked through eventfds; completion = used index + call eventfd.
@@ -913,8 +920,8 @@ def vhost_user_leg(args, device: int, mode: str, queue_counts=(64,), gpus=None) 
         cmd = [sys.executable, os.path.join(ROOT, "tests", "ref_rpc_server.py"), rpc, os.path.join(tmp, "vhost"), "vhost", "busy"]
     else:
         cmd = ([build.DAEMON, "-r", rpc, "-S", os.path.join(tmp, "vhost"), "--gpus", ",".join(str(x) for x in (gpus or [device]))] +
-               (["--poller"] if mode == "poller" else []))
-    proc = subprocess.Popen(cmd, stdout=log, stderr=log)
+               (["--poller"] if mode == "poller" else []) + list(daemon_args))
+    proc = subprocess.Popen(cmd, stdout=log, stderr=log, env={**os.environ, **(env or {})})
     try:
         t0 = time.time()
         while not os.path.exists(rpc):

@@ -1009,7 +1009,7 @@ static __device__ __forceinline__ void mirror_unit(const LunCtx &L, uint8_t *dst
 	if (src) move_unit<true>(dst + off, src + off, nbytes, lane, L.store[1] + soff);
 	else { zero_unit(dst + off, nbytes, lane); zero_unit(L.store[1] + soff, nbytes, lane); }
 	for (uint32_t rep = 2; rep < nrep; rep++) {
-		if (src) move_unit_call(L.store[rep] + soff, src + off, nbytes, lane);
+		if (src) move_unit<true>(L.store[rep] + soff, src + off, nbytes, lane);
 		else zero_unit(L.store[rep] + soff, nbytes, lane);
 	}
 }

@@ -382,15 +382,38 @@ __device__ __forceinline__ void move_unit_unaligned(uint8_t *dst, const uint8_t 
 	if ((uint32_t)lane < tail) dst[(size_t)nv * 16 + lane] = tb;
 }
 
-static __device__ __noinline__ void move_unit_unaligned_call(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
+/* the compact form of the same (one vector at a time, byte loads when the source disagrees with the destination modulo
+ * 4): the mirror kernels use it - they are bound by NVLink at a ninth of the HBM rate, and the batched path above,
+ * inlined or called, cost them 7 % through spills around it */
+__device__ __forceinline__ void move_unit_unaligned_compact(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
 {
-	move_unit_unaligned(dst, src, n, lane);
+	uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+	if (head > n) head = n;
+	if ((uint32_t)lane < head) dst[lane] = ld_cg8(src + lane);
+	dst += head; src += head; n -= head;
+	const uint32_t nv = n >> 4;
+	if (((uintptr_t)src & 15) == 0) {
+		for (uint32_t v = lane; v < nv; v += 32) st_cg16(dst + (size_t)v * 16, ld_cg16(src + (size_t)v * 16));
+	} else {
+		for (uint32_t v = lane; v < nv; v += 32) {
+			const uint8_t *sp = src + (size_t)v * 16;
+			uint32_t w[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				w[j] = (uint32_t)ld_cg8(sp + 4 * j) | (uint32_t)ld_cg8(sp + 4 * j + 1) << 8 |
+				       (uint32_t)ld_cg8(sp + 4 * j + 2) << 16 | (uint32_t)ld_cg8(sp + 4 * j + 3) << 24;
+			}
+			st_cg16(dst + (size_t)v * 16, make_int4(w[0], w[1], w[2], w[3]));
+		}
+	}
+	const uint32_t tail = n & 15;
+	if ((uint32_t)lane < tail) dst[(size_t)nv * 16 + lane] = ld_cg8(src + (size_t)nv * 16 + lane);
 }
 
 /* Move `n` (<= kUnitBytes) bytes with one warp.  Fast path: both sides 16-byte aligned.
  * dst2 != nullptr (mirrored bdev, same alignment as dst): the registers are stored twice, locally
  * and into the peer replica over NVLink - one load, two stores, no second pass. */
-template <bool kSlowPathOutOfLine = false>	/* mirror kernels: keeping the byte-granular path out of line keeps them spill-free */
+template <bool kCompactSlowPath = false>	/* mirror kernels: the compact byte-granular path */
 __device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint32_t n, int lane, uint8_t *dst2 = nullptr)
 {
 	if ((((uintptr_t)dst | (uintptr_t)src | n) & 15) == 0) {
@@ -415,15 +438,12 @@ __device__ __forceinline__ void move_unit(uint8_t *dst, const uint8_t *src, uint
 		}
 		return;
 	}
-	if constexpr (kSlowPathOutOfLine) move_unit_unaligned_call(dst, src, n, lane);
-	else move_unit_unaligned(dst, src, n, lane);
-	if (dst2) move_unit_unaligned_call(dst2, src, n, lane);
-}
-
-/* third and further replicas (R > 2): out of line as a whole */
-static __device__ __noinline__ void move_unit_call(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
-{
-	move_unit(dst, src, n, lane);
+	if constexpr (kCompactSlowPath) {
+		move_unit_unaligned_compact(dst, src, n, lane);
+		if (dst2) move_unit_unaligned_compact(dst2, src, n, lane);
+	} else {
+		move_unit_unaligned(dst, src, n, lane);
+	}
 }
 
 /* mem_copy_fill with fill == 0 (copy_engine.c:128-140): zero `n` bytes; block-aligned by construction */
