@@ -882,7 +882,7 @@ def run_ours(args, rank, world, local):
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("rand4k", n), "peak_source": peak_src,
-                         "traffic_source": "ncu --set full capture, profiles/r1_rand4k_ncu.md (bytes per launch)",
+                         "traffic_source": "ncu --set full capture, profiles/r2_rand4k_ncu.md (bytes per launch)",
                          "algorithmic_bytes_per_launch": 2 * 4096 * n, "kernel": "oim_lun_queue_kernel"},
             "seq128k": seq, "virtqueue": vq, "mixed_70_30": mixed, "e2e": e2e, "single_queue_qd32": lat, "cpu_baseline": cpu,
             "vhost_user": vuser, "more": extra, "mirror": mirror, "queue_sweep": sweep, "seq128k_sg": seq_sg, "vhost_user_multi_gpu": vuser_multi,
