@@ -1090,7 +1090,12 @@ __device__ __forceinline__ uint32_t find_shared_work(const KickHeader *hdr, cons
 #ifndef OIM_MIN_BLOCKS
 #define OIM_MIN_BLOCKS 2	/* 128 registers: the mover loop must stay spill-free (80-register builds lose ~25%) */
 #endif
-template <bool kMirrored, bool kShared>
+/* kMoverReap: mover warp 0 publishes the completions of a fill instead of the parser.  Always so with shared queues
+ * (§ QShare); also for launches that serve guest virtqueues only, where publishing means byte stores into 32 response
+ * buffers, 32 used elements and a fence that waits for every load the parser has in flight - 18 % of the time of the
+ * warp the virtqueue mode is bound by (profiles/r2_vq_ncu.md).  The slot-ring kernels keep the parser publishing: they
+ * are bound by the movers, and their publication is three coalesced vectors per request without a fence. */
+template <bool kMirrored, bool kShared, bool kMoverReap = kShared>
 __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1168,7 +1173,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		 * the movers are done with the fill, and the parser only waits for the stage to be released. */
 		auto retire = [&](uint32_t f) {
 			const uint32_t sidx_ = f % kStages;
-			if constexpr (kShared) {
+			if constexpr (kMoverReap) {
 				mbar_wait(&sh.released[sidx_], (f / kStages) & 1);
 			} else {
 				mbar_wait(&sh.empty[sidx_], (f / kStages) & 1);
@@ -1827,7 +1832,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			}
 			/* shared kernels: units are drawn from a counter (mover 0 spends part of its time publishing) unless
 			 * the fill has waves, whose barrier wants every mover to walk the same list */
-			const bool dyn = kShared && nw == 1;
+			const bool dyn = kMoverReap && nw == 1;
 			auto next_unit = [&](uint32_t u) -> uint32_t {
 				if (!dyn) return u + kMovers;
 				uint32_t v = 0;
@@ -1878,7 +1883,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&sh.empty[sidx]);
-			if constexpr (kShared) {
+			if constexpr (kMoverReap) {
 				if (mw == 0) {
 					/* every mover is done with the fill: publish its completions (in ring order across CTAs,
 					 * reap_stage waits for the fills before it) and hand the stage back to the parser */
@@ -1905,6 +1910,13 @@ __global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
 oim_lun_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
 	lun_queue_body<true, false>(lun, hdr, queues);
+}
+
+/* one CTA per queue, guest virtqueues only: mover warp 0 publishes (see kMoverReap) */
+__global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
+oim_lun_vring_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
+{
+	lun_queue_body<false, false, true>(lun, hdr, queues);
 }
 
 __global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)

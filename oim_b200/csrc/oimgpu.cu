@@ -32,6 +32,7 @@ namespace oimgpu {
 __global__ void oim_lun_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_lun_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_lun_shared_queue_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
+__global__ void oim_lun_vring_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_lun_shared_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_copy_kernel(uint8_t *dst, const uint8_t *src, uint64_t nbytes);
 __global__ void oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes);
@@ -1259,6 +1260,7 @@ static int lun_open_on(const char *ctrlr, int scsi_target_num, int on_device, ui
 	CU_OK(cudaFuncSetAttribute(oim_lun_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
 	CU_OK(cudaFuncSetAttribute(oim_lun_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
 	CU_OK(cudaFuncSetAttribute(oim_lun_shared_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
+	CU_OK(cudaFuncSetAttribute(oim_lun_vring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
 	CU_OK(cudaFuncSetAttribute(oim_lun_shared_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
 	int per_sm = 0;
 	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes()));
@@ -1404,10 +1406,14 @@ static uint32_t share_max_queues(const oimgpu_lun *L)
 	return (uint32_t)L->grid_cap * 160 / 296;
 }
 
-static void launch_lun_kernel(oimgpu_lun *L, uint32_t grid, bool shared)
+static void launch_lun_kernel(oimgpu_lun *L, uint32_t grid, bool shared, bool vrings_only = false)
 {
 	const size_t smem = lun_kernel_smem_bytes();
 	KickHeader *kh = (KickHeader *)L->d_kick;
+	if (!shared && !L->any_mirror && vrings_only && !getenv("OIMGPU_NO_VRING_KERNEL")) {
+		oim_lun_vring_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
+		return;
+	}
 	if (shared && L->any_mirror) oim_lun_shared_queue_mirror_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
 	else if (shared) oim_lun_shared_queue_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
 	else if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
@@ -1437,7 +1443,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	const int slot = (int)(L->kicks % oimgpu_lun::kKickSlots);
 	if (L->kicks >= (uint64_t)oimgpu_lun::kKickSlots) CU_OK(cudaEventSynchronize(L->kick_ev[slot]));
 	QueueDesc *h_desc = (QueueDesc *)(L->h_kick[slot] + sizeof(KickHeader));
-	uint32_t nd = 0;
+	uint32_t nd = 0, nvring = 0;
 	uint64_t passes = 0;	/* passes of <= 32 requests this kick will take (virtqueues: at most a ring full) */
 	for (uint32_t q = 0; q < L->num_queues; q++) {
 		Queue &Q = L->queues[q];
@@ -1458,6 +1464,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 		}
 		if (Q.vq_pending) {
 			passes += (Q.vq_size + kPass - 1) / kPass;
+			nvring++;
 			QueueDesc &D = h_desc[nd++];
 			memset(&D, 0, sizeof(D));
 			D.mode = QMODE_VRING;
@@ -1508,7 +1515,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));
 	L->kicks++;
-	launch_lun_kernel(L, grid, shared);
+	launch_lun_kernel(L, grid, shared, nvring == nd);
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->done, L->stream));
 	L->launches++;
@@ -2116,7 +2123,11 @@ extern "C" int oimgpu_lun_start_poller(oimgpu_lun *L, uint32_t max_ctas, uint32_
 	kh->shared = shared ? 1 : 0;
 	kh->share = shared ? L->d_share : nullptr;
 	CU_OK(cudaMemcpyAsync(L->d_kick, L->h_kick[slot], sizeof(KickHeader) + sizeof(QueueDesc) * nd, cudaMemcpyHostToDevice, L->stream));
-	launch_lun_kernel(L, grid + 1, shared);
+	{
+		uint32_t nv = 0;
+		for (uint32_t q = 0; q < L->num_queues; q++) nv += L->queues[q].vq_size != 0;
+		launch_lun_kernel(L, grid + 1, shared, nv == nd);
+	}
 	if (shared) L->shared_launches++;
 	CU_OK(cudaGetLastError());
 	CU_OK(cudaEventRecord(L->kick_ev[slot], L->stream));

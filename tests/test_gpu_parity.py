@@ -279,6 +279,57 @@ def test_cuda_host_batch_path(gpu, oracles, pin):
         gpu.delete_bdev("hb0")
 
 
+def test_cuda_c2_full_size_sample_matches_oracle(gpu, oracles):
+    """BASELINE config 2 at its real size: an 8 GiB bdev holding the position-keyed pattern, 2^18 READ(10)s of 4 KiB at
+    `8 * (rng mod 2 097 152)` (the C2 trace of SURVEY 8(d)) over 254 queues, replayed through the oracle on an 8 GiB
+    store with the same contents; every completion and every payload byte must agree (per-read digests would hide
+    nothing a byte compare shows)."""
+    import torch
+    nb, seed = 16777216, 0xB2000000
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 12 << 30:
+        pytest.skip("not enough free HBM")
+    nq, per_q = 254, 1024
+    n = nq * per_q
+    t = traces.uniform_trace(n, nb, io_blocks=8, pattern="randread", seed=seed)
+    lbas = np.array([int.from_bytes(bytes(x[2:6]), "big") for x in t.reqs["cdb"]], dtype=np.uint64)
+    # the oracle's store: 8 GiB of zero pages of which only the blocks the trace reads are filled in (the rest is never
+    # looked at; calloc'ed pages stay uncommitted)
+    o = (oracles.RefOracle if oracles.ref_available() else oracles.PortOracle)(nb)     # the compiled reference where it travelled
+    words = (lbas[:, None] * np.uint64(64) + np.arange(512, dtype=np.uint64)[None, :]).reshape(-1)     # word index = byte offset / 8
+    with np.errstate(over="ignore"):
+        pat = traces.mix64((np.uint64(seed) ^ words) * traces.GAMMA + traces.GAMMA)
+    o.store.view(np.uint64)[words] = pat
+    del words
+    oa = np.zeros(t.arena_bytes, dtype=np.uint8)
+    want_cpls = o.submit(t.reqs, t.bind(oa.ctypes.data))
+    o.close()
+    assert (oa.view(np.uint64) == pat).all(), "the oracle itself must return the pattern"
+    gpu.construct_malloc_bdev(nb, 512, name="c2big", device=0)
+    gpu.construct_vhost_scsi_controller("c2big.ctl")
+    gpu.add_vhost_scsi_lun("c2big.ctl", 0, "c2big")
+    try:
+        store_ptr = gpu.get_bdevs("c2big")[0]["device_ptr"]
+        with gpu.Lun("c2big.ctl", 0, num_queues=nq, queue_size=32) as lun:
+            # fill the whole device with the pattern on the GPU (same function as traces.pattern_words)
+            import bench
+            bench.device_pattern_fill(lun, store_ptr, nb * 512, seed, torch)
+            dev = torch.zeros(t.arena_bytes, dtype=torch.uint8, device="cuda:0")
+            d_reqs = torch.from_numpy(t.reqs.view(np.uint8).copy()).cuda()
+            d_iovs = torch.from_numpy(t.bind(dev.data_ptr()).view(np.uint8).copy()).cuda()
+            d_cpls = torch.zeros(n * 48, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            lun.submit_batch(nq, per_q, d_reqs.data_ptr(), d_iovs.data_ptr(), len(t.iovs), d_cpls.data_ptr(), abi.MEM_DEVICE)
+            lun.sync()
+        got = np.frombuffer(d_cpls.cpu().numpy().tobytes(), dtype=abi.cpl_dtype)
+        util.assert_cpls_equal(got, want_cpls, t.reqs)
+        assert (dev.cpu().numpy() == oa).all(), "payload differs from the oracle's at the full device size"
+    finally:
+        gpu.remove_vhost_scsi_target("c2big.ctl", 0)
+        gpu.remove_vhost_controller("c2big.ctl")
+        gpu.delete_bdev("c2big")
+
+
 def test_cuda_full_size_properties(gpu):
     """BASELINE config sizes (8 GiB bdev): size-independent properties instead of a CPU replay.
     write(seeded pattern) -> read back == pattern; random 4 KiB reads return the bytes the position-keyed
