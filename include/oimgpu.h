@@ -219,6 +219,10 @@ int oimgpu_bdev_iostat(const char *name, struct oimgpu_iostat *out);
  * Blocking; run it on a thread of its own.  0 = orderly end, -EINVAL = bad request magic, -ENODEV = no bdev. */
 int oimgpu_nbd_serve(const char *bdev_name, int sock_fd);
 
+/* gather `rows` x `width` bytes that lie `pitch` apart in device memory into host memory with the copy engine (works
+ * next to a resident poller, which a kernel would not): e.g. the used indices of many rings living in HBM */
+int oimgpu_read_strided(int device, void *dst, const void *src, size_t pitch, size_t width, size_t rows);
+int oimgpu_write_strided(int device, void *dst, const void *src, size_t pitch, size_t width, size_t rows);	/* host -> device */
 /* test/digest helpers: raw access to the backing store of replica r (synchronous) */
 int oimgpu_bdev_read_raw(const char *name, int replica, uint64_t offset, void *dst, uint64_t len);
 int oimgpu_bdev_write_raw(const char *name, int replica, uint64_t offset, const void *src, uint64_t len);

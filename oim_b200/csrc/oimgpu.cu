@@ -850,6 +850,38 @@ static int raw_access(const char *name, int replica, uint64_t offset, void *host
 	return 0;
 }
 
+/* `rows` pieces of `width` bytes, `pitch` apart in device memory, gathered into host memory by the COPY ENGINE on the
+ * device's housekeeping stream: how a host thread looks at ring indices in HBM while a resident poller holds every SM
+ * slot (a kernel launched for the same purpose would wait for the poller to leave) */
+extern "C" int oimgpu_read_strided(int device, void *dst, const void *src, size_t pitch, size_t width, size_t rows)
+{
+	if (!dst || !src || !width || !rows) return -EINVAL;
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited || g.control_only) return -ENODEV;
+	const int slot = find_device_slot(device);
+	if (slot < 0) return -EINVAL;
+	CU_OK(cudaSetDevice(device));
+	cudaStream_t st = g.devices[slot].util;
+	CU_OK(cudaMemcpy2DAsync(dst, width, src, pitch, width, rows, cudaMemcpyDeviceToHost, st));
+	CU_OK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+/* the scatter counterpart (host -> device), e.g. a test guest publishing avail->idx on many rings in HBM */
+extern "C" int oimgpu_write_strided(int device, void *dst, const void *src, size_t pitch, size_t width, size_t rows)
+{
+	if (!dst || !src || !width || !rows) return -EINVAL;
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited || g.control_only) return -ENODEV;
+	const int slot = find_device_slot(device);
+	if (slot < 0) return -EINVAL;
+	CU_OK(cudaSetDevice(device));
+	cudaStream_t st = g.devices[slot].util;
+	CU_OK(cudaMemcpy2DAsync(dst, pitch, src, width, width, rows, cudaMemcpyHostToDevice, st));
+	CU_OK(cudaStreamSynchronize(st));
+	return 0;
+}
+
 extern "C" int oimgpu_bdev_read_raw(const char *name, int replica, uint64_t offset, void *dst, uint64_t len)
 {
 	return raw_access(name, replica, offset, dst, len, false);

@@ -69,6 +69,8 @@ SYMBOLS = [
     ("oimgpu_bdev_delete", _I, [C.c_char_p]),
     ("oimgpu_bdev_get", _I, [C.c_char_p, C.POINTER(BdevInfo)]),
     ("oimgpu_bdev_list", _I, [C.POINTER(BdevInfo), _I]),
+    ("oimgpu_read_strided", _I, [_I, _VP, _VP, C.c_size_t, C.c_size_t, C.c_size_t]),
+    ("oimgpu_write_strided", _I, [_I, _VP, _VP, C.c_size_t, C.c_size_t, C.c_size_t]),
     ("oimgpu_bdev_read_raw", _I, [C.c_char_p, _I, _U64, _VP, _U64]),
     ("oimgpu_bdev_write_raw", _I, [C.c_char_p, _I, _U64, _VP, _U64]),
     ("oimgpu_vhost_scsi_ctrlr_create", _I, [C.c_char_p, C.c_char_p]),
@@ -317,6 +319,18 @@ def bdev_read_raw(name: str, offset: int, nbytes: int, replica: int = 0) -> np.n
 def bdev_write_raw(name: str, offset: int, data: np.ndarray, replica: int = 0) -> None:
     data = np.ascontiguousarray(data, dtype=np.uint8)
     _chk(load().oimgpu_bdev_write_raw(_b(name), replica, offset, data.ctypes.data, data.size), "bdev_write_raw")
+
+
+def read_strided(device: int, src: int, pitch: int, width: int, rows: int) -> np.ndarray:
+    """rows x width bytes, pitch apart in device memory -> host, by the copy engine (include/oimgpu.h)"""
+    out = np.empty(rows * width, dtype=np.uint8)
+    _chk(load().oimgpu_read_strided(device, out.ctypes.data, src, pitch, width, rows), "read_strided")
+    return out
+
+
+def write_strided(device: int, dst: int, data: np.ndarray, pitch: int, width: int) -> None:
+    data = np.ascontiguousarray(data).view(np.uint8)
+    _chk(load().oimgpu_write_strided(device, dst, data.ctypes.data, pitch, width, data.size // width), "write_strided")
 
 
 def mem_register(arr: np.ndarray) -> None:

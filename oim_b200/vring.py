@@ -277,19 +277,24 @@ class UniformGuest:
 
 
 def build_uniform_queues(nq: int, per_q: int, num_blocks: int, *, io_blocks: int = 8, ring_size: int = 1024,
-                         seed: int = 1, target: int = 0, gpa_base: int = R2_GPA, ntargets: int = 1) -> UniformGuest:
+                         seed: int = 1, target: int = 0, gpa_base: int = R2_GPA, ntargets: int = 1,
+                         indirect: bool = False) -> UniformGuest:
     """nq virtqueues, each holding per_q READ(10) requests of io_blocks as 3-descriptor direct chains
     [RO req 51 B][WR resp 108 B][WR data], random LBAs over the whole device (reads only: no ordering
     question).  The avail ring is pre-filled with the heads repeated ring_size/per_q times, so bumping
     avail->idx by per_q re-publishes the same chains (what a guest re-using its buffers does)."""
-    assert 3 * per_q <= ring_size and ring_size % per_q == 0
+    # indirect: one ring slot per request (VRING_DESC_F_INDIRECT) pointing at its 3-descriptor table in guest memory - how
+    # a Linux guest submits (virtio_ring uses indirect descriptors whenever the device offers them), and what lets a
+    # 1024-entry ring hold 1024 requests instead of 341
+    assert (per_q if indirect else 3 * per_q) <= ring_size and ring_size % per_q == 0
     io_bytes = io_blocks * 512
     desc_off = 0
     avail_off = 16 * ring_size
     used_off = -(-(avail_off + 6 + 2 * ring_size) // 8) * 8
     hdr_off = -(-(used_off + 6 + 8 * ring_size) // 64) * 64
     resp_off = hdr_off + 64 * per_q
-    q_stride = -(-(resp_off + 128 * per_q) // 4096) * 4096
+    ind_off = resp_off + 128 * per_q                     # indirect tables: 3 x 16 B per request
+    q_stride = -(-(ind_off + (48 * per_q if indirect else 0)) // 4096) * 4096
     data_off = nq * q_stride
     data_bytes = nq * per_q * io_bytes
     arena = np.zeros(data_off, dtype=np.uint8)
@@ -297,7 +302,7 @@ def build_uniform_queues(nq: int, per_q: int, num_blocks: int, *, io_blocks: int
     qbase = (np.arange(nq, dtype=np.uint64) * np.uint64(q_stride))[:, None] + np.uint64(gpa_base)      # [nq,1] GPA of a queue block
     k = np.arange(per_q, dtype=np.uint64)[None, :]
     # descriptors: chain i uses ring slots 3i, 3i+1, 3i+2
-    d = np.zeros((nq, ring_size), dtype=desc_dtype)
+    d = np.zeros((nq, max(ring_size, 3 * per_q)), dtype=desc_dtype)
     d["addr"][:, 0:3 * per_q:3] = qbase + np.uint64(hdr_off) + k * np.uint64(64)
     d["len"][:, 0:3 * per_q:3] = 51
     d["flags"][:, 0:3 * per_q:3] = F_NEXT
@@ -310,9 +315,23 @@ def build_uniform_queues(nq: int, per_q: int, num_blocks: int, *, io_blocks: int
     d["addr"][:, 2:3 * per_q:3] = np.uint64(gpa_base + data_off) + (qi * np.uint64(per_q) + k) * np.uint64(io_bytes)
     d["len"][:, 2:3 * per_q:3] = io_bytes
     d["flags"][:, 2:3 * per_q:3] = F_WRITE
-    meta[:, desc_off:desc_off + 16 * ring_size] = d.view(np.uint8).reshape(nq, -1)
-    # avail ring: heads 0,3,6,... repeated
-    heads = np.tile((3 * np.arange(per_q)).astype("<u2"), ring_size // per_q)
+    if indirect:
+        # the three descriptors move into the request's table (next = 1, 2 inside the table) ...
+        tbl = np.zeros((nq, per_q, 3), dtype=desc_dtype)
+        for j in range(3):
+            for f in ("addr", "len", "flags"):
+                tbl[f][:, :, j] = d[f][:, j:3 * per_q:3]
+        tbl["next"][:, :, 0] = 1
+        tbl["next"][:, :, 1] = 2
+        meta[:, ind_off:ind_off + 48 * per_q] = tbl.view(np.uint8).reshape(nq, -1)
+        # ... and ring slot i is one INDIRECT descriptor covering it
+        d = np.zeros((nq, ring_size), dtype=desc_dtype)
+        d["addr"][:, :per_q] = qbase + np.uint64(ind_off) + k * np.uint64(48)
+        d["len"][:, :per_q] = 48
+        d["flags"][:, :per_q] = F_INDIRECT
+    meta[:, desc_off:desc_off + 16 * ring_size] = np.ascontiguousarray(d[:, :ring_size]).view(np.uint8).reshape(nq, -1)
+    # avail ring: heads 0,3,6,... (indirect: 0,1,2,...) repeated
+    heads = np.tile(((1 if indirect else 3) * np.arange(per_q)).astype("<u2"), ring_size // per_q)
     meta[:, avail_off + 4:avail_off + 4 + 2 * ring_size] = heads.view(np.uint8)[None, :]
     # request headers: virtio_scsi_cmd_req with a READ(10) at a random LBA
     rnd = traces.splitmix64_stream(seed, nq * per_q).reshape(nq, per_q)

@@ -290,6 +290,28 @@ def test_vhost_user_handshake_control_and_event_queues(slaves):
     assert struct.unpack("<I8sI", ev2) == (1, bytes([1, 1, 0, 0, 0, 0, 0, 0]), 2)     # ... REMOVED
 
 
+def test_remove_controller_with_a_master_connected_is_busy(slaves):
+    """spdk_vhost_dev_unregister: "Controller %s has still valid connection" -> -EBUSY (S/lib/vhost/vhost.c:783-788); round 1
+    tore the session down instead.  Same RPC replies from both servers, before and after the master leaves."""
+    ours, ref = slaves("ours", ["--control-only"]), slaves("ref")
+    for s in (ours, ref):
+        for t in range(8):
+            s.call("remove_vhost_scsi_target", {"ctrlr": "scsi0", "scsi_target_num": t})     # whatever provision() attached
+        m = vu.Master(s.sock("scsi0"))
+        m.get_u64(vu.GET_FEATURES)                       # the connection is established and served
+        busy = s.call("remove_vhost_controller", {"ctrlr": "scsi0"})
+        assert b'"code":-32602' in busy and b"Device or resource busy" in busy, (s.kind, busy)
+        m.close()
+        deadline = time.time() + 10
+        while True:                                      # the slave notices the closed socket on its own thread
+            r = s.call("remove_vhost_controller", {"ctrlr": "scsi0"})
+            if b'"result":true' in r or time.time() > deadline:
+                break
+            time.sleep(0.05)
+        assert b'"result":true' in r, (s.kind, r)
+        assert not os.path.exists(s.sock("scsi0"))
+
+
 def test_vhost_user_reconnect_and_odd_masters(slaves):
     """a master that disappears mid-handshake, one that sends an unknown request, and a clean reconnect"""
     ours = slaves("ours", ["--control-only"])

@@ -19,7 +19,7 @@ for label, kw in (("1gpu_1lun", dict()),
                   ("spread_poller", dict(gpus=list(range(n)), mode="poller"))):
     mode = kw.pop("mode", "kick")
     try:
-        r = bench.vhost_user_leg(a, 0, mode, (254,), **kw)
+        r = bench.vhost_user_leg(a, 0, mode, (254,), per_q=int(os.environ.get("VU_PER_Q", 1024)), indirect=True, **kw)
         out[label] = {"miops": round(r["value"] / 1e6, 2), "ms_per_round": round(r["ms_per_round"], 2)}
     except Exception as e:  # noqa: BLE001
         out[label] = {"error": f"{type(e).__name__}: {e}"[:200]}
