@@ -57,6 +57,20 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
 	return ok != 0;
 }
 
+/* ---- TMA: request slots global -> shared memory in one bulk copy per pass ---------------------------- */
+
+/* one thread: expect `bytes` on the barrier (and arrive on it: the barrier's only arrival) */
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+/* one thread: dst (shared), src (global), bytes: 16-byte aligned; completion = `bytes` arriving on the barrier */
+__device__ __forceinline__ void tma_load_bulk(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		     :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 /* ---- shared queues: position counters in device memory, handed from CTA to CTA ------------------- */
 
 __device__ __forceinline__ uint32_t ld_acquire32(const uint32_t *p)
@@ -1144,6 +1158,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			mbar_init(&sh.empty[s], kMovers);
 			mbar_init(&sh.released[s], 1);
 		}
+		mbar_init(&sh.req_bar[0], 1);
+		mbar_init(&sh.req_bar[1], 1);
 		sh.pub_q = nullptr;
 		sh.pub_end = 0;
 		for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) sh.lat_ns[t][0] = sh.lat_ns[t][1] = sh.lat_ns[t][2] = 0;
@@ -1179,6 +1195,28 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				mbar_wait(&sh.empty[sidx_], (f / kStages) & 1);
 				reap_stage(sh.stage[sidx_], lane);
 			}
+		};
+
+		/* request slots of slot rings: staged by the TMA unit into reqbuf[fetch_no & 1]; fetches are consumed in the
+		 * order they were issued, one per pass, so buffer and barrier phase follow from the two counters */
+		uint32_t fetch_no = 0, consume_no = 0;
+		auto issue_fetch = [&](const QueueDesc &qd, uint32_t first_slot, uint32_t nslots) {
+			const uint32_t b_ = fetch_no & 1;
+			if (lane == 0) {
+				mbar_expect_tx(&sh.req_bar[b_], nslots * (uint32_t)sizeof(oimgpu_req));
+				const uint32_t s0 = first_slot & qd.ring_mask;
+				uint32_t n1 = nslots;
+				if (qd.ring_mask != 0xffffffffu && s0 + nslots > qd.ring_mask + 1) n1 = qd.ring_mask + 1 - s0;	/* the ring wraps */
+				tma_load_bulk(&sh.reqbuf[b_][0], &qd.reqs[s0], n1 * (uint32_t)sizeof(oimgpu_req), &sh.req_bar[b_]);
+				if (n1 < nslots) tma_load_bulk(&sh.reqbuf[b_][n1], &qd.reqs[0], (nslots - n1) * (uint32_t)sizeof(oimgpu_req), &sh.req_bar[b_]);
+			}
+			fetch_no++;
+		};
+		auto consume_fetch = [&]() -> oimgpu_req * {
+			const uint32_t b_ = consume_no & 1;
+			mbar_wait(&sh.req_bar[b_], (consume_no >> 1) & 1);
+			consume_no++;
+			return sh.reqbuf[b_];
 		};
 
 		const uint32_t nqueues = hdr->nqueues;
@@ -1317,21 +1355,9 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				if (q.count == 0) continue;
 				progress = true;
 			}
-			/* request slots are prefetched one pass ahead: 4 x 16 B per lane, coalesced
-			 * (vector v = k*32+lane of the pass -> request v/4, quarter v%4).  On a shared queue the next pass
-			 * is not known before it is claimed: there the slots are fetched right after the claim. */
-			int4 pre[4];
-			if (!shared && q.count && q.mode == QMODE_SLOTS) {
-				const uint32_t n0 = min((uint32_t)kPass, q.count);
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const uint32_t v = k * 32 + lane;
-					if ((v >> 2) < n0) {
-						const uint32_t slot = (q.head + (v >> 2)) & q.ring_mask;
-						pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
-					}
-				}
-			}
+			/* request slots are fetched one pass ahead by the TMA unit (issue_fetch).  On a shared queue the next pass
+			 * is not known before it is claimed: there the fetch is issued right after the claim. */
+			if (!shared && q.count && q.mode == QMODE_SLOTS) issue_fetch(q, q.head, min((uint32_t)kPass, q.count));
 			/* virtqueue mode walks guest memory: avail entry -> head descriptor -> chain -> request
 			 * header, each a dependent DRAM access under a saturated memory system.  The first two
 			 * are loaded one pass ahead into registers (an L2 prefetch of the rest does not survive:
@@ -1366,14 +1392,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						chunk_left = 0;
 						streak = 0;
 						if (q.mode == QMODE_SLOTS) {
-#pragma unroll
-							for (int k = 0; k < 4; k++) {
-								const uint32_t v = k * 32 + lane;
-								if ((v >> 2) < next_n) {
-									const uint32_t slot = (q.head + next_done + (v >> 2)) & q.ring_mask;
-									pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
-								}
-							}
+							issue_fetch(q, q.head + next_done, next_n);
 						} else if ((uint32_t)lane < next_n) {
 							vq_head_cur = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(q.head + next_done + lane) & (q.vq_size - 1)];
 							if (vq_tbl_aligned && vq_head_cur < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_cur * 16);
@@ -1387,26 +1406,10 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				const uint32_t slot0 = q.head + done;
 				const uint64_t pass_t0 = globaltimer_ns();	/* the requests are in hand: their latency clock starts */
 				__syncwarp();
-				if (q.mode == QMODE_SLOTS) {
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						const uint32_t v = k * 32 + lane;
-						if ((v >> 2) < n) reinterpret_cast<int4 *>(&sh.req[v >> 2])[v & 3] = pre[k];
-					}
-				}
-				__syncwarp();
+				/* this pass's slots: wait for their bulk copy; virtqueue mode builds its slots in a buffer of its own */
+				oimgpu_req *const rq = q.mode == QMODE_SLOTS ? consume_fetch() : sh.reqbuf[consume_no & 1];
 				const uint32_t ahead = shared ? 0u : (done + kPass < q.count ? q.count - done - kPass : 0u);
-				if (q.mode == QMODE_SLOTS && ahead) {
-					const uint32_t n1 = min((uint32_t)kPass, ahead);
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						const uint32_t v = k * 32 + lane;
-						if ((v >> 2) < n1) {
-							const uint32_t slot = (slot0 + n + (v >> 2)) & q.ring_mask;
-							pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
-						}
-					}
-				}
+				if (q.mode == QMODE_SLOTS && ahead) issue_fetch(q, slot0 + n, min((uint32_t)kPass, ahead));
 
 				const bool active = (uint32_t)lane < n;
 				uint64_t my_resp = 0;
@@ -1419,13 +1422,13 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 					my_head = vq_head_cur;
 					VDesc d0 = {0, 0, 0, 0};
 					if (my_head < q.vq_size) d0 = vq_tbl_aligned ? decode_desc(vq_raw) : load_desc(q.vq_desc + (size_t)my_head * 16);
-					chain_ok = vq_task_data_setup(L, q, my_head, d0, sh.req[lane], const_cast<oimgpu_iov *>(iov_base) + (size_t)lane * kIovRow,
+					chain_ok = vq_task_data_setup(L, q, my_head, d0, rq[lane], const_cast<oimgpu_iov *>(iov_base) + (size_t)lane * kIovRow,
 								      sh.sg[lane], lane * kIovRow, &my_resp);
 					/* from here on this lane's `q.iovs` is its own SG list: on chip when it is short (the
 					 * usual case: one data buffer), else its row of the scratch table in HBM */
-					if (chain_ok && sh.req[lane].iovcnt <= kSmemIovs) {
+					if (chain_ok && rq[lane].iovcnt <= kSmemIovs) {
 						q.iovs = sh.sg[lane];
-						sh.req[lane].iov_start = 0;
+						rq[lane].iov_start = 0;
 					} else {
 						q.iovs = iov_base;
 					}
@@ -1433,13 +1436,13 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				/* next pass's head descriptors: issued now, consumed after the hazard analysis, the
 				 * reap and the segment emission of this pass */
 				if (vq_more && vq_tbl_aligned && vq_head_nxt < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_nxt * 16);
-				if (active && chain_ok) parse_request(L, q, sh.req[lane], s);
+				if (active && chain_ok) parse_request(L, q, rq[lane], s);
 				else if (active) {
 					/* invalid_request(): used element of length 0, response untouched (vhost_scsi.c:347-358) */
 					s.op = OP_NONE; s.nseg = 0; s.units = 0; s.hazard = 0; s.valid = 0; s.store_lo = s.store_hi = 0;
 					s.length = 0; s.data_transferred = 0; s.used_len = 0; s.resp_valid = 0; s.response = 0;
 					s.status = SC_GOOD; s.sk = 0; s.asc = 0;
-					sh.req[lane].tag = 0; sh.req[lane].iovcnt = 0;
+					rq[lane].tag = 0; rq[lane].iovcnt = 0;
 				}
 				else { s.nseg = 0; s.units = 0; s.hazard = 0; s.op = OP_NONE; s.valid = 0; s.store_lo = s.store_hi = 0; }
 				const uint32_t haz = active ? s.hazard : 0;
@@ -1561,7 +1564,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						}
 						__syncwarp();
 					}
-					/* the next pass: claim it and start its fetch now (pre[] / vq_raw / vq_head_nxt are free again) */
+					/* the next pass: claim it and start its fetch now (the other slot buffer / vq_raw / vq_head_nxt are free) */
 					{
 						/* A CTA that has had the queue to itself for a few passes takes four passes' worth per claim
 						 * (one atomic round trip per 128 requests instead of per 32); the moment somebody else's claim
@@ -1580,14 +1583,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 							chunk_left = got - next_n;
 						}
 						if (next_n && q.mode == QMODE_SLOTS) {
-#pragma unroll
-							for (int k = 0; k < 4; k++) {
-								const uint32_t v = k * 32 + lane;
-								if ((v >> 2) < next_n) {
-									const uint32_t slot = (q.head + next_done + (v >> 2)) & q.ring_mask;
-									pre[k] = ld_cg16(reinterpret_cast<const int4 *>(&q.reqs[slot]) + (v & 3));
-								}
-							}
+							issue_fetch(q, q.head + next_done, next_n);
 						} else if (next_n && (uint32_t)lane < next_n) {
 							vq_head_nxt = reinterpret_cast<const volatile uint16_t *>(q.vq_avail + 4)[(q.head + next_done + lane) & (q.vq_size - 1)];
 							if (vq_tbl_aligned && vq_head_nxt < q.vq_size) vq_raw = ld_cg16(q.vq_desc + (size_t)vq_head_nxt * 16);
@@ -1686,9 +1682,9 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						__syncwarp();
 					}
 					if (mine) {
-						if (segs) emit_segments(L, q, sh.req[lane], s, &st.seg[seg_incl - segs], unit_incl - units,
+						if (segs) emit_segments(L, q, rq[lane], s, &st.seg[seg_incl - segs], unit_incl - units,
 									(uint16_t)(wave | (cross ? kSegWaitsForDrain : 0)));
-						build_cpl(sh.req[lane], s, &st.cpl[lane - r0]);
+						build_cpl(rq[lane], s, &st.cpl[lane - r0]);
 						if (q.mode == QMODE_VRING) {
 							st.resp[lane - r0] = my_resp;
 							st.vq_head[lane - r0] = (uint16_t)my_head;

@@ -257,7 +257,11 @@ struct __align__(16) HazPass {
 struct __align__(16) CtaShared {
 	Stage stage[kStages];
 	HazPass hist[kStages];		/* ring: the pass being parsed + the kStages-1 before it */
-	oimgpu_req req[kPass];		/* parser-private: the pass being parsed */
+	/* parser-private: the request slots of the pass being parsed and of the next one.  Slot rings are staged here by
+	 * the TMA unit (cp.async.bulk, one 2 KiB copy per pass, completion on req_bar): the fetch of pass p+1 is in
+	 * flight, outside the register file, while pass p is parsed.  Virtqueue mode builds its slots here itself. */
+	oimgpu_req reqbuf[2][kPass];
+	uint64_t req_bar[2];
 	oimgpu_iov sg[kPass][kSmemIovs];	/* virtqueue mode: the SG list of a request with few elements stays on chip */
 	LaneState lane[kPass];
 	uint64_t full[kStages];		/* mbarriers */
