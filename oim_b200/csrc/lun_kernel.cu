@@ -1181,6 +1181,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		if (lane < kStages) { sh.hist[lane].writers = 0; sh.hist[lane].touching = 0; }
 		__syncwarp();
 		uint32_t st_rd = 0, st_wr = 0, st_um = 0, st_er = 0;
+		uint32_t mix_r = 0, mix_w = 0;		/* good reads / writes + unmaps of ANY target: the session's mix */
 		unsigned long long st_rb = 0, st_wb = 0, st_ub = 0;
 		bool first = true;
 		/* Who publishes a fill's completions.  One CTA per queue: the parser, when it needs the stage again.
@@ -1642,6 +1643,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				st_um += __reduce_add_sync(0xffffffffu, um ? s.nseg : 0u);
 				if (um) st_ub += s.unmap_bytes;
 				st_er += __popc(__ballot_sync(0xffffffffu, active && !good));
+				mix_r += __popc(__ballot_sync(0xffffffffu, good && s.op == OP_READ));
+				mix_w += __popc(__ballot_sync(0xffffffffu, good && (s.op == OP_WRITE || s.op == OP_UNMAP)));
 				if (ok && s.op == OP_READ) st_rb += s.length;
 				if (ok && s.op == OP_WRITE) st_wb += s.length;
 				if (active && s.resp_valid && s.response == OIMGPU_S_OK && s.tgt != L.target &&
@@ -1799,6 +1802,10 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			if (st_wr) { atomicAdd(&lun->stats[1], (unsigned long long)st_wr); atomicAdd(&lun->stats[5], st_wb); }
 			if (st_um) atomicAdd(&lun->stats[2], (unsigned long long)st_um);
 			if (st_er) atomicAdd(&lun->stats[7], (unsigned long long)st_er);
+			if (lun->mix_host) {
+				if (mix_r) atomicAdd_system(&lun->mix_host[0], (unsigned long long)mix_r);
+				if (mix_w) atomicAdd_system(&lun->mix_host[1], (unsigned long long)mix_w);
+			}
 			/* every fill is retired: mover warp 0 is done adding */
 			for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
 				LunCtx *T = (t == lun->target) ? lun : lun->peer[t];

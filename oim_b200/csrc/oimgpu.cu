@@ -161,6 +161,10 @@ struct oimgpu_lun {
 	uint8_t *d_kick = nullptr;
 	QueueDesc *d_desc = nullptr;
 	QShare *d_share = nullptr;		/* [3 x num_queues] coordination blocks of shared queues (lun_kernel.cuh) */
+	/* the session's recent read / write mix, counted by the kernels into mapped host memory (LunCtx::mix_host) */
+	volatile unsigned long long *h_mix = nullptr;
+	unsigned long long mix_seen[2] = {0, 0};
+	bool write_hot = false;
 	uint64_t shared_launches = 0;
 	uint64_t launches = 0;
 	int grid_cap = 0;
@@ -1141,6 +1145,7 @@ static void free_lun_resources(oimgpu_lun *L)
 {
 	cudaSetDevice(L->device);
 	if (L->h_door) cudaFreeHost((void *)L->h_door);
+	if (L->h_mix) cudaFreeHost((void *)L->h_mix);
 	if (L->h_flags) cudaFreeHost((void *)L->h_flags);
 	if (L->slab) cudaFreeHost(L->slab);
 	for (int k = 0; k < oimgpu_lun::kKickSlots; k++) {
@@ -1247,6 +1252,13 @@ static int lun_open_on(const char *ctrlr, int scsi_target_num, int on_device, ui
 	memset(&L->h_ctx, 0, sizeof(L->h_ctx));
 	if (session) L->h_ctx.target = 0xff;
 	else fill_lun_ctx(L->h_ctx, *bp, *it->second, scsi_target_num);
+	{
+		unsigned long long *dm = nullptr;
+		CU_OK(cudaHostAlloc((void **)&L->h_mix, 64, cudaHostAllocMapped));
+		memset((void *)L->h_mix, 0, 64);
+		CU_OK(cudaHostGetDevicePointer((void **)&dm, (void *)L->h_mix, 0));
+		L->h_ctx.mix_host = dm;
+	}
 	L->any_mirror = L->h_ctx.nreplicas > 1;
 	CU_OK(cudaMalloc((void **)&L->d_ctx, sizeof(LunCtx)));
 	CU_OK(h2d_sync(L.get(), L->d_ctx, &L->h_ctx, sizeof(LunCtx)));
@@ -1532,7 +1544,19 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	/* Measured on B200 (tools/queue_sweep.py, 4 KiB random read, 2^21 requests): one CTA per queue reaches 0.68 / 0.80 /
 	 * 0.94 / 0.96 of the HBM peak at 100 / 148 / 200 / 254 queues (a CTA alone moves ~6 M IOPS; 200 of them saturate
 	 * HBM), sharing 0.82 / 0.91 / 0.87 / 0.95: sharing pays below ~160 queues, above that ownership is cheaper. */
-	const bool shared = nd < grid && nd <= share_max_queues(L) && !getenv("OIMGPU_NO_SHARED_QUEUES");
+	/* ... and only for read-dominated sessions: passes of different CTAs are ordered coarsely, a write-hot queue is
+	 * served by its home CTA alone and slower than the one-CTA-per-queue kernel would (16 queues mixed 70/30: 0.061 vs
+	 * 0.095 of the HBM peak).  The kernels count what they served into mapped host memory; once 1024 requests have
+	 * been seen since the last look, more than one write in eight switches sharing off (and back on when they stop). */
+	{
+		const unsigned long long r = L->h_mix[0] - L->mix_seen[0], w = L->h_mix[1] - L->mix_seen[1];
+		if (r + w >= 1024) {
+			L->write_hot = w * 8 > r + w;
+			L->mix_seen[0] += r;
+			L->mix_seen[1] += w;
+		}
+	}
+	const bool shared = nd < grid && nd <= share_max_queues(L) && !L->write_hot && !getenv("OIMGPU_NO_SHARED_QUEUES");
 	if (!shared) grid = std::min(grid, nd);
 	KickHeader *kh = (KickHeader *)L->h_kick[slot];
 	memset(kh, 0, sizeof(*kh));	/* run-to-completion: persistent = 0 (the staging buffer is recycled pinned memory) */

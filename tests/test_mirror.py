@@ -23,6 +23,7 @@ def gpu2():
     lib.init([0, 1])
     yield lib
     lib.fini()
+    lib.init([0])           # what the session-wide `gpu` fixture set up: the modules after this one rely on it
 
 
 def test_mirror_write_fanout_matches_oracle(gpu2, oracles):

@@ -182,3 +182,49 @@ def test_sg_lengths_that_wrap_32_bits_are_an_invalid_request(gpu):
         gpu.remove_vhost_scsi_target("wrap.ctl", 0)
         gpu.remove_vhost_controller("wrap.ctl")
         gpu.delete_bdev(name)
+
+
+def test_sharing_follows_the_sessions_read_write_mix(gpu, oracles):
+    """Sharing pays for read-dominated sessions only (a write-hot queue is left to its home CTA): the kernels count what
+    they served, and the launch shape follows the recent mix - shared, then one CTA per queue once writes dominate,
+    then shared again when they stop.  Results equal the oracle's either way."""
+    import torch
+    nb, nq, per_q = 1 << 16, 4, 2048
+    name = "mix0"
+    gpu.construct_malloc_bdev(nb, 512, name=name, device=0)
+    gpu.construct_vhost_scsi_controller("mix.ctl")
+    gpu.add_vhost_scsi_lun("mix.ctl", 0, name)
+    o = oracles.PortOracle(nb)
+    try:
+        init = traces.pattern_bytes(7, 0, nb * 512)
+        gpu.bdev_write_raw(name, 0, init)
+        o.store[:] = init
+        shapes = []
+        with gpu.Lun("mix.ctl", 0, num_queues=nq, queue_size=32) as lun:
+            for step, pattern in enumerate(["randrw", "randrw", "randread", "randread", "randread"]):
+                t = traces.partitioned_queues(nq, per_q, nb, pattern=pattern, read_pct=50, io_blocks=8, seed=40 + step)
+                host = np.zeros(t.arena_bytes, dtype=np.uint8)
+                traces.fill_arena(host, t, 0x5EED + step)
+                oa = host.copy()
+                want = o.submit(t.reqs, t.bind(oa.ctypes.data))
+                dev = torch.from_numpy(host).to("cuda:0")
+                d_reqs = torch.from_numpy(t.reqs.view(np.uint8).copy()).cuda()
+                d_iovs = torch.from_numpy(t.bind(dev.data_ptr()).view(np.uint8).copy()).cuda()
+                d_cpls = torch.zeros(len(t.reqs) * 48, dtype=torch.uint8, device="cuda")
+                torch.cuda.synchronize()
+                before = lun.shared_launches
+                lun.submit_batch(nq, per_q, d_reqs.data_ptr(), d_iovs.data_ptr(), len(t.iovs), d_cpls.data_ptr(), abi.MEM_DEVICE)
+                lun.sync()
+                shapes.append(lun.shared_launches - before)
+                got = np.frombuffer(d_cpls.cpu().numpy().tobytes(), dtype=abi.cpl_dtype)
+                util.assert_cpls_equal(got, want, t.reqs, f"step {step}")
+                assert (dev.cpu().numpy() == oa).all(), f"step {step}: payload"
+        assert (gpu.bdev_read_raw(name, 0, nb * 512) == o.store).all()
+        # launch 0: no history -> shared; 1: writes seen -> one CTA per queue; 2: still write-hot (its own reads are only
+        # known afterwards); 3, 4: reads dominate the recent window -> shared again
+        assert shapes == [1, 0, 0, 1, 1], shapes
+    finally:
+        o.close()
+        gpu.remove_vhost_scsi_target("mix.ctl", 0)
+        gpu.remove_vhost_controller("mix.ctl")
+        gpu.delete_bdev(name)

@@ -342,9 +342,17 @@ def make_requests(seed, n=96):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["kick", "poller"])
+@pytest.mark.parametrize("mode", ["kick", "poller", "kick-2gpus", "poller-2gpus"])
 def test_cuda_vhost_user_io_matches_reference(slaves, mode):
-    ours, ref = slaves("ours", ["--poller"] if mode == "poller" else []), slaves("ref")
+    extra = ["--poller"] if mode.startswith("poller") else []
+    if mode.endswith("2gpus"):
+        # one controller, two GPUs: bdevs placed on the least-loaded GPU, the session's request queues dealt out over
+        # both (queue r -> GPU r mod 2), every target reached from either GPU (own HBM or the peer's over NVLink)
+        import torch
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+        extra += ["--gpus", "0,1"]
+    ours, ref = slaves("ours", extra), slaves("ref")
     rq = make_requests(11)
     lo, so, img, rings = run_script(ours, rq, data=True)
     lr, sr, _, _ = run_script(ref, rq, data=True)
