@@ -1802,10 +1802,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			if (st_wr) { atomicAdd(&lun->stats[1], (unsigned long long)st_wr); atomicAdd(&lun->stats[5], st_wb); }
 			if (st_um) atomicAdd(&lun->stats[2], (unsigned long long)st_um);
 			if (st_er) atomicAdd(&lun->stats[7], (unsigned long long)st_er);
-			if (lun->mix_host) {
-				if (mix_r) atomicAdd_system(&lun->mix_host[0], (unsigned long long)mix_r);
-				if (mix_w) atomicAdd_system(&lun->mix_host[1], (unsigned long long)mix_w);
-			}
+			if (mix_r) atomicAdd(&lun->mix[0], (unsigned long long)mix_r);
+			if (mix_w) atomicAdd(&lun->mix[1], (unsigned long long)mix_w);
 			/* every fill is retired: mover warp 0 is done adding */
 			for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
 				LunCtx *T = (t == lun->target) ? lun : lun->peer[t];

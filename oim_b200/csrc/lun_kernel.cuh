@@ -84,9 +84,9 @@ struct LunCtx {
 	uint8_t  protocol_id;
 	unsigned long long stats[12];	/* read ops, write ops, unmap ops, other, bytes r/w/unmapped, errors,
 					 * [8..10] summed latency in ns of reads / writes / unmaps (get_bdevs_iostat *_latency_ticks) */
-	/* mapped host memory, [0] reads [1] writes + unmaps the session's kernels have served (any target): the host
-	 * picks the launch shape from the recent mix - queue sharing pays for read-dominated sessions only */
-	unsigned long long *mix_host;
+	/* [0] reads [1] writes + unmaps the session's kernels have served (any target).  Copied to the host behind every
+	 * launch: it picks the launch shape from the recent mix - queue sharing pays for read-dominated sessions only */
+	unsigned long long mix[2];
 	/* the other SCSI devices of the same vhost controller (svdev->scsi_dev[8], vhost_scsi.c:80-94):
 	 * one set of virtqueues serves them all */
 	LunCtx *peer[OIMGPU_CTRLR_MAX_DEVS];

@@ -161,7 +161,7 @@ struct oimgpu_lun {
 	uint8_t *d_kick = nullptr;
 	QueueDesc *d_desc = nullptr;
 	QShare *d_share = nullptr;		/* [3 x num_queues] coordination blocks of shared queues (lun_kernel.cuh) */
-	/* the session's recent read / write mix, counted by the kernels into mapped host memory (LunCtx::mix_host) */
+	/* the session's recent read / write mix: LunCtx::mix, copied here (pinned) behind every launch */
 	volatile unsigned long long *h_mix = nullptr;
 	unsigned long long mix_seen[2] = {0, 0};
 	bool write_hot = false;
@@ -1252,13 +1252,8 @@ static int lun_open_on(const char *ctrlr, int scsi_target_num, int on_device, ui
 	memset(&L->h_ctx, 0, sizeof(L->h_ctx));
 	if (session) L->h_ctx.target = 0xff;
 	else fill_lun_ctx(L->h_ctx, *bp, *it->second, scsi_target_num);
-	{
-		unsigned long long *dm = nullptr;
-		CU_OK(cudaHostAlloc((void **)&L->h_mix, 64, cudaHostAllocMapped));
-		memset((void *)L->h_mix, 0, 64);
-		CU_OK(cudaHostGetDevicePointer((void **)&dm, (void *)L->h_mix, 0));
-		L->h_ctx.mix_host = dm;
-	}
+	CU_OK(cudaHostAlloc((void **)&L->h_mix, 64, cudaHostAllocDefault));
+	memset((void *)L->h_mix, 0, 64);
 	L->any_mirror = L->h_ctx.nreplicas > 1;
 	CU_OK(cudaMalloc((void **)&L->d_ctx, sizeof(LunCtx)));
 	CU_OK(h2d_sync(L.get(), L->d_ctx, &L->h_ctx, sizeof(LunCtx)));
@@ -1546,7 +1541,7 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	 * HBM), sharing 0.82 / 0.91 / 0.87 / 0.95: sharing pays below ~160 queues, above that ownership is cheaper. */
 	/* ... and only for read-dominated sessions: passes of different CTAs are ordered coarsely, a write-hot queue is
 	 * served by its home CTA alone and slower than the one-CTA-per-queue kernel would (16 queues mixed 70/30: 0.061 vs
-	 * 0.095 of the HBM peak).  The kernels count what they served into mapped host memory; once 1024 requests have
+	 * 0.095 of the HBM peak).  The kernels count what they served (LunCtx::mix, copied back behind every launch); once 1024 requests have
 	 * been seen since the last look, more than one write in eight switches sharing off (and back on when they stop). */
 	{
 		const unsigned long long r = L->h_mix[0] - L->mix_seen[0], w = L->h_mix[1] - L->mix_seen[1];
@@ -1573,6 +1568,8 @@ extern "C" int oimgpu_kick(oimgpu_lun *L)
 	L->kicks++;
 	launch_lun_kernel(L, grid, shared, nvring == nd);
 	CU_OK(cudaGetLastError());
+	CU_OK(cudaMemcpyAsync((void *)L->h_mix, (const uint8_t *)L->d_ctx + offsetof(LunCtx, mix), sizeof(unsigned long long) * 2,
+			      cudaMemcpyDeviceToHost, L->stream));
 	CU_OK(cudaEventRecord(L->done, L->stream));
 	L->launches++;
 	return (int)nd;
