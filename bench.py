@@ -665,8 +665,8 @@ def run_ours(args, rank, world, local):
                "device_ms_per_step": dev_ms, "pcie_payload_gbs_device": en * 4096 / (dev_ms / 1e3) / 1e9,
                "note": "host request/SG arrays in pinned memory -> copy-engine upload -> kernel on HBM-resident "
                        "metadata; payload stored by the movers straight into pinned client buffers over PCIe; "
-                       "completion records copied back; PCIe D2H ceiling of the box 57 GB/s (cudaMemcpy), "
-                       "52.7 GB/s for SM-originated stores (tools/pcie_store_bench.cu)"}
+                       "completion records copied back; host_ceiling = what the box's host side takes with every rank storing at "
+                       "once (copy engine / SM stores), measured in this run"}
 
     # ---- virtqueue mode: the kernel walks real virtio split rings itself (a19-a22 on the device) ----
     vq = None

@@ -213,6 +213,12 @@ int oimgpu_bdev_list(struct oimgpu_bdev_info *out, int max);	/* returns count */
 /* get_bdevs_iostat (S/lib/bdev/rpc/bdev_rpc.c:50-205): what the bdev has served over its lifetime, through
  * whichever sessions and targets; -ENODEV if there is no such bdev.  kernel_launches is 0 here. */
 int oimgpu_bdev_iostat(const char *name, struct oimgpu_iostat *out);
+/* enable_bdev_histogram / get_bdev_histogram (S/lib/bdev/rpc/bdev_rpc.c:607-790): the latency histogram of struct
+ * spdk_histogram_data at bucket_shift 7 - OIMGPU_HISTOGRAM_BUCKETS = 58 ranges x 128 counters, datapoints in ns of the
+ * GPU's global timer - tallied per completed request by the mover warps.  get: -EFAULT while disabled and in use. */
+#define OIMGPU_HISTOGRAM_BUCKETS (58 * 128)
+int oimgpu_bdev_histogram_enable(const char *name, int enable);
+int oimgpu_bdev_histogram_get(const char *name, uint64_t *buckets);
 
 /* NBD export (S/lib/nbd/nbd.c:560-806): serve the kernel's NBD transmission protocol for `bdev_name` on a
  * connected socket - the end of the socketpair that did NOT go to /dev/nbdX - until the peer disconnects.

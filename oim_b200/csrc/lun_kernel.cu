@@ -1878,8 +1878,18 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 			if (mw == 0 && lane == 0 && st.lat_ntgt) {
 				const unsigned long long dt = globaltimer_ns() - st.t0;
 				for (uint32_t i = 0; i < st.lat_ntgt; i++) {
-					unsigned long long *acc = sh.lat_ns[st.lat_tgt[i] & (OIMGPU_CTRLR_MAX_DEVS - 1)];
+					const uint32_t t = st.lat_tgt[i] & (OIMGPU_CTRLR_MAX_DEVS - 1);
+					unsigned long long *acc = sh.lat_ns[t];
 					acc[0] += dt * st.lat_n[i][0]; acc[1] += dt * st.lat_n[i][1]; acc[2] += dt * st.lat_n[i][2];
+					/* spdk_histogram_data_tally (histogram_data.h:120-160) of the fill's latency, once per request */
+					const LunCtx *T = (t == lun->target) ? lun : lun->peer[t];
+					unsigned long long *hist = T ? *reinterpret_cast<unsigned long long *const volatile *>(&T->hist) : nullptr;
+					if (hist && dt) {
+						const uint32_t clz = (uint32_t)__clzll((long long)dt);
+						const uint32_t range = clz <= 57u ? 57u - clz : 0u;
+						const uint32_t index = (uint32_t)(dt >> (range ? range - 1 : 0)) & 127u;
+						atomicAdd(&hist[(range << 7) + index], (unsigned long long)(st.lat_n[i][0] + st.lat_n[i][1] + st.lat_n[i][2]));
+					}
 				}
 			}
 			__syncwarp();

@@ -52,6 +52,7 @@ constexpr int kSegCap = 256;			/* SG segments per stage (>= 256 UNMAP descriptor
 constexpr uint32_t kUnitBytes = 4096;		/* bytes one warp moves per step: 8 x 16 B per lane */
 constexpr int kMaxReplicas = 4;
 constexpr int kMaxRegions = 8;			/* VHOST_MEMORY_MAX_NREGIONS */
+constexpr int kHistBuckets = 58 * 128;		/* SPDK_HISTOGRAM_NUM_BUCKETS at bucket_shift 7 (S/include/spdk/histogram_data.h:48-55) */
 constexpr int kIovRow = OIMGPU_IOVS_MAX + 1;	/* scratch SG row per parser lane in virtqueue mode */
 
 enum : uint8_t { OP_NONE = 0, OP_READ = 1, OP_WRITE = 2, OP_UNMAP = 3 };
@@ -87,6 +88,9 @@ struct LunCtx {
 	/* [0] reads [1] writes + unmaps the session's kernels have served (any target).  Copied to the host behind every
 	 * launch: it picks the launch shape from the recent mix - queue sharing pays for read-dominated sessions only */
 	unsigned long long mix[2];
+	/* enable_bdev_histogram: the bdev's latency histogram in HBM (struct spdk_histogram_data's buckets, 58 ranges x 128;
+	 * nullptr while disabled); mover warp 0 tallies every completed request's latency */
+	unsigned long long *hist;
 	/* the other SCSI devices of the same vhost controller (svdev->scsi_dev[8], vhost_scsi.c:80-94):
 	 * one set of virtqueues serves them all */
 	LunCtx *peer[OIMGPU_CTRLR_MAX_DEVS];

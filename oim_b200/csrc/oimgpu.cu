@@ -80,6 +80,7 @@ struct Bdev {
 	std::vector<int> devices;	/* replica r lives on devices[r] (an imported replica: the device it is reached from) */
 	std::vector<uint8_t *> stores;
 	std::vector<char> imported;	/* replica r is another process's store, opened from a CUDA IPC handle */
+	unsigned long long *hist = nullptr;	/* enable_bdev_histogram: kHistBuckets counters on devices[0] */
 	unsigned long long retired[12] = {};	/* counters of sessions that are gone (same layout as LunCtx::stats) */
 };
 
@@ -229,6 +230,7 @@ static void fill_lun_ctx(LunCtx &c, const Bdev &b, const Ctrlr &ctrlr, int targe
 	c.nreplicas = (uint32_t)b.stores.size();
 	c.num_blocks = b.num_blocks;
 	c.block_size = b.block_size;
+	c.hist = b.hist;
 	c.block_shift = (b.block_size & (b.block_size - 1)) ? 0xffffffffu : (uint32_t)__builtin_ctz(b.block_size);
 	c.target = (uint8_t)target;
 	snprintf(c.bdev_name, sizeof(c.bdev_name), "%s", b.name.c_str());
@@ -503,6 +505,7 @@ extern "C" void oimgpu_fini(void)
 	if (!g.inited) return;
 	for (auto &kv : g.bdevs) {
 		for (size_t r = 0; r < kv.second->stores.size() && !g.control_only; r++) release_store(*kv.second, r);
+		if (kv.second->hist && !g.control_only) { cudaSetDevice(kv.second->devices[0]); cudaFree(kv.second->hist); }
 	}
 	g.control_only = false;
 	g.bdevs.clear();
@@ -788,7 +791,84 @@ extern "C" int oimgpu_bdev_delete(const char *name)
 		if (own) g.devices[find_device_slot(it->second->devices[r])].bytes_allocated -=
 			it->second->num_blocks * (uint64_t)it->second->block_size;
 	}
+	if (it->second->hist) { cudaSetDevice(it->second->devices[0]); cudaFree(it->second->hist); }
 	g.bdevs.erase(it);
+	return 0;
+}
+
+/* every open session's device-resident view of the bdev learns where its histogram is (or that it is gone) */
+static int publish_hist_locked(const std::string &name, unsigned long long *hist)
+{
+	for (oimgpu_lun *L : g.handles) {
+		std::lock_guard<std::recursive_mutex> hl(L->mu);
+		CU_OK(cudaSetDevice(L->device));
+		if (L->bdev == name) {
+			L->h_ctx.hist = hist;
+			CU_OK(cudaMemcpyAsync((uint8_t *)L->d_ctx + offsetof(LunCtx, hist), &L->h_ctx.hist, sizeof(hist), cudaMemcpyHostToDevice, L->copy_stream));
+			CU_OK(cudaStreamSynchronize(L->copy_stream));
+		}
+		for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) {
+			if (L->peer_bdev[t] != name || !L->d_peer[t]) continue;
+			CU_OK(cudaMemcpyAsync((uint8_t *)L->d_peer[t] + offsetof(LunCtx, hist), &hist, sizeof(hist), cudaMemcpyHostToDevice, L->copy_stream));
+			CU_OK(cudaStreamSynchronize(L->copy_stream));
+		}
+	}
+	return 0;
+}
+
+/* enable_bdev_histogram (S/lib/bdev/rpc/bdev_rpc.c:607-671, spdk_bdev_histogram_enable bdev.c:4367-4400): enabling starts
+ * from an empty histogram, disabling drops it */
+extern "C" int oimgpu_bdev_histogram_enable(const char *name, int enable)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.bdevs.find(name ? name : "");
+	if (it == g.bdevs.end()) return -ENODEV;
+	Bdev &b = *it->second;
+	if (g.control_only) { b.hist = enable ? (unsigned long long *)1 : nullptr; return 0; }
+	CU_OK(cudaSetDevice(b.devices[0]));
+	cudaStream_t st = g.devices[find_device_slot(b.devices[0])].util;
+	if (enable) {
+		if (!b.hist) {
+			unsigned long long *h = nullptr;
+			CU_OK(cudaMalloc((void **)&h, sizeof(unsigned long long) * kHistBuckets));
+			b.hist = h;
+		}
+		CU_OK(cudaMemsetAsync(b.hist, 0, sizeof(unsigned long long) * kHistBuckets, st));
+		CU_OK(cudaStreamSynchronize(st));
+		return publish_hist_locked(it->first, b.hist);
+	}
+	if (b.hist) {
+		int rc = publish_hist_locked(it->first, nullptr);
+		if (rc) return rc;
+		/* kernels already launched may still tally: everything in flight first, resident pollers parked */
+		auto parked = park_pollers_locked(-1);
+		for (oimgpu_lun *L : g.handles) { cudaSetDevice(L->device); cudaStreamSynchronize(L->stream); }
+		cudaSetDevice(b.devices[0]);
+		cudaFree(b.hist);
+		unpark_pollers_locked(parked);
+		b.hist = nullptr;
+	}
+	return 0;
+}
+
+/* get_bdev_histogram (bdev_rpc.c:675-790): the kHistBuckets bucket counters.  Disabled: -EFAULT while anything has the
+ * bdev open (the reference's per-channel histogram is NULL then), an empty histogram otherwise (no channel to ask) */
+extern "C" int oimgpu_bdev_histogram_get(const char *name, uint64_t *buckets)
+{
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.inited) return -ENODEV;
+	auto it = g.bdevs.find(name ? name : "");
+	if (it == g.bdevs.end()) return -ENODEV;
+	if (!buckets) return -EINVAL;
+	Bdev &b = *it->second;
+	memset(buckets, 0, sizeof(uint64_t) * kHistBuckets);
+	if (!b.hist) return b.open_luns > 0 ? -EFAULT : 0;	/* I/O channels exist while a session runs (spdk_scsi_dev_allocate_io_channels) */
+	if (g.control_only) return 0;
+	CU_OK(cudaSetDevice(b.devices[0]));
+	cudaStream_t st = g.devices[find_device_slot(b.devices[0])].util;
+	CU_OK(cudaMemcpyAsync(buckets, b.hist, sizeof(uint64_t) * kHistBuckets, cudaMemcpyDeviceToHost, st));
+	CU_OK(cudaStreamSynchronize(st));
 	return 0;
 }
 

@@ -419,6 +419,33 @@ static Reply dispatch(const std::string &method, const Json *params, const Json 
 		}
 		return result(id, out + "]");
 	}
+	if (method == "enable_bdev_histogram") {
+		/* S/lib/bdev/rpc/bdev_rpc.c:607-671 */
+		if (!decode(params, {{"name", Json::Str, false, &a}, {"enable", Json::Bool, false, &b}})) return error(id, E_INVALID_PARAMS, strerr(EINVAL));
+		int rc = oimgpu_bdev_histogram_enable(a->raw.c_str(), b->b ? 1 : 0);
+		if (rc == -ENODEV) return error(id, E_INVALID_PARAMS, strerr(ENODEV));
+		return result(id, rc == 0 ? "true" : "false");
+	}
+	if (method == "get_bdev_histogram") {
+		/* bdev_rpc.c:675-790: {"histogram": base64 of the bucket array, "bucket_shift": 7, "tsc_rate": ticks per second} */
+		if (!decode(params, {{"name", Json::Str, false, &a}})) return error(id, E_INVALID_PARAMS, strerr(EINVAL));
+		std::vector<uint64_t> buckets(OIMGPU_HISTOGRAM_BUCKETS);
+		int rc = oimgpu_bdev_histogram_get(a->raw.c_str(), buckets.data());
+		if (rc == -ENODEV) return error(id, E_INVALID_PARAMS, strerr(ENODEV));
+		if (rc < 0) return error(id, E_INTERNAL, strerr(rc));
+		static const char tbl[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+		const uint8_t *p = (const uint8_t *)buckets.data();
+		const size_t n = buckets.size() * sizeof(uint64_t);
+		std::string b64;
+		b64.reserve((n + 2) / 3 * 4);
+		for (size_t i = 0; i < n; i += 3) {
+			const uint32_t v = (uint32_t)p[i] << 16 | (i + 1 < n ? (uint32_t)p[i + 1] << 8 : 0) | (i + 2 < n ? p[i + 2] : 0);
+			b64 += tbl[v >> 18]; b64 += tbl[(v >> 12) & 63];
+			b64 += i + 1 < n ? tbl[(v >> 6) & 63] : '=';
+			b64 += i + 2 < n ? tbl[v & 63] : '=';
+		}
+		return result(id, "{\"histogram\":\"" + b64 + "\",\"bucket_shift\":7,\"tsc_rate\":1000000000}");
+	}
 	if (method == "construct_malloc_bdev") {
 		uint64_t nb = 0, bs = 0;
 		if (!decode(params, {{"name", Json::Str, true, &a}, {"uuid", Json::Str, true, &b},

@@ -98,6 +98,8 @@ SYMBOLS = [
     ("oimgpu_submit_batch", _I, [_VP, _U32, _U32, _VP, _VP, _U32, _VP, _I]),
     ("oimgpu_submit_and_wait", _I, [_VP, _U32, _U32, _VP, _VP, _U32, _VP, _I]),
     ("oimgpu_bdev_iostat", _I, [C.c_char_p, C.POINTER(IoStat)]),
+    ("oimgpu_bdev_histogram_enable", _I, [C.c_char_p, _I]),
+    ("oimgpu_bdev_histogram_get", _I, [C.c_char_p, C.POINTER(C.c_uint64)]),
     ("oimgpu_nbd_serve", _I, [C.c_char_p, _I]),
     ("oimgpu_lun_iostat", _I, [_VP, C.POINTER(IoStat)]),
     ("oimgpu_lun_target_iostat", _I, [_VP, _I, C.POINTER(IoStat)]),
@@ -259,6 +261,17 @@ def get_bdevs_iostat(name: str) -> dict:
     s = IoStat()
     _chk(load().oimgpu_bdev_iostat(_b(name), C.byref(s)), "get_bdevs_iostat")
     return {n: getattr(s, n) for n, _ in IoStat._fields_}
+
+
+def enable_bdev_histogram(name: str, enable: bool = True) -> None:
+    _chk(load().oimgpu_bdev_histogram_enable(_b(name), int(enable)), "enable_bdev_histogram")
+
+
+def get_bdev_histogram(name: str) -> np.ndarray:
+    """[58, 128] uint64: struct spdk_histogram_data buckets (range, index), datapoints in ns"""
+    out = np.zeros(58 * 128, dtype=np.uint64)
+    _chk(load().oimgpu_bdev_histogram_get(_b(name), out.ctypes.data_as(C.POINTER(C.c_uint64))), "get_bdev_histogram")
+    return out.reshape(58, 128)
 
 
 def get_bdevs(name: str | None = None) -> list[dict]:

@@ -279,6 +279,52 @@ def test_cuda_host_batch_path(gpu, oracles, pin):
         gpu.delete_bdev("hb0")
 
 
+def test_cuda_latency_histogram(gpu):
+    """enable_bdev_histogram / get_bdev_histogram (S/lib/bdev/rpc/bdev_rpc.c:607-790): struct spdk_histogram_data's buckets
+    (58 ranges x 128, S/include/spdk/histogram_data.h), one tally per completed request, by the mover warps"""
+    import torch
+    from oim_b200.lib import OimGpuError
+    nb, n = 1 << 16, 4096
+    gpu.construct_malloc_bdev(nb, 512, name="hist0", device=0)
+    gpu.construct_vhost_scsi_controller("hist.ctl")
+    gpu.add_vhost_scsi_lun("hist.ctl", 0, "hist0")
+    try:
+        assert gpu.get_bdev_histogram("hist0").sum() == 0            # disabled, nothing open: the empty histogram
+        t = traces.uniform_trace(n, nb, io_blocks=8, pattern="randrw", read_pct=50, seed=77)
+        dev = torch.zeros(t.arena_bytes, dtype=torch.uint8, device="cuda:0")
+        with gpu.Lun("hist.ctl", 0, num_queues=4, queue_size=1024) as lun:
+            with pytest.raises(OimGpuError) as e:                    # disabled and in use: the reference's channel has no histogram
+                gpu.get_bdev_histogram("hist0")
+            assert e.value.rc == -14                                 # EFAULT
+            gpu.enable_bdev_histogram("hist0", True)
+            parts = t.split_queues(4)
+            for q, p in enumerate(parts):
+                lun.submit(q, p.reqs, p.bind(dev.data_ptr()))
+            lun.kick()
+            cpls = np.concatenate([lun.poll(q, len(p.reqs)) for q, p in enumerate(parts)])
+            assert not cpls["status"].any()
+            h = gpu.get_bdev_histogram("hist0")
+            assert int(h.sum()) == n, "one tally per completed request"
+            # datapoints are nanoseconds: range r (>= 2) holds values in [2^(r+6), 2^(r+7)); a request on an idle GPU takes
+            # between a memory round trip and a few milliseconds
+            rng = np.nonzero(h.sum(axis=1))[0]
+            assert rng.min() >= 3 and rng.max() <= 20, rng           # 512 ns .. 134 ms
+            st = lun.iostat()
+            lo = sum(int(h[r, i]) * ((128 + i) << (r - 1) if r >= 1 else i) for r in rng for i in range(128))
+            total = st["read_latency_ns"] + st["write_latency_ns"]
+            assert lo <= total <= lo * 1.02 + n * 2, "bucket lower bounds vs the summed latencies"
+            gpu.enable_bdev_histogram("hist0", True)                 # enabling again starts over
+            assert gpu.get_bdev_histogram("hist0").sum() == 0
+            gpu.enable_bdev_histogram("hist0", False)
+            with pytest.raises(OimGpuError):
+                gpu.get_bdev_histogram("hist0")
+        assert gpu.get_bdev_histogram("hist0").sum() == 0
+    finally:
+        gpu.remove_vhost_scsi_target("hist.ctl", 0)
+        gpu.remove_vhost_controller("hist.ctl")
+        gpu.delete_bdev("hist0")
+
+
 def test_cuda_c2_full_size_sample_matches_oracle(gpu, oracles):
     """BASELINE config 2 at its real size: an 8 GiB bdev holding the position-keyed pattern, 2^18 READ(10)s of 4 KiB at
     `8 * (rng mod 2 097 152)` (the C2 trace of SURVEY 8(d)) over 254 queues, replayed through the oracle on an 8 GiB

@@ -168,6 +168,20 @@ def test_rpc_transcript_matches_reference_server(servers):
     assert len(both(servers, "get_bdevs_iostat", {"name": "MyVol"})["result"]) == 2
     assert both(servers, "get_bdevs_iostat", {"name": "nope"})["error"]["code"] == -32602
     both(servers, "get_bdevs_iostat", {"nam": "MyVol"})
+    # ---- latency histogram (bdev_rpc.c:607-790): no I/O channel exists on either server here, so get returns the empty
+    # histogram whether enabled or not (the per-channel -EFAULT needs a running session: tests/test_vhost_user.py)
+    def hist(reply):
+        return re.sub(r'"tsc_rate":\d+', '"tsc_rate":"<hz>"', reply)
+    for m, pa in (("get_bdev_histogram", {"name": "MyVol"}), ("enable_bdev_histogram", {"name": "MyVol", "enable": True}),
+                  ("get_bdev_histogram", {"name": "MyVol"}), ("enable_bdev_histogram", {"name": "MyVol", "enable": False}),
+                  ("enable_bdev_histogram", {"name": "nope", "enable": True}), ("get_bdev_histogram", {"name": "nope"}),
+                  ("enable_bdev_histogram", {"name": "MyVol"}), ("get_bdev_histogram", {})):
+        a, b = hist(norm(ours.call(m, pa))), hist(norm(ref.call(m, pa)))
+        assert a == b, f"{m} {pa}\n ours: {a[:300]}\n ref : {b[:300]}"
+    import base64
+    ref.call("get_bdev_histogram", {"name": "MyVol"})                    # (keeps the two clients' request ids in step)
+    h = json.loads(ours.call("get_bdev_histogram", {"name": "MyVol"}))["result"]
+    assert h["bucket_shift"] == 7 and len(base64.b64decode(h["histogram"])) == 58 * 128 * 8
     # ---- NBD export of OIM's local mode (nbd_rpc.c): no /dev/nbd* in the build container, so the error paths
     assert both(servers, "get_nbd_disks")["result"] == []
     assert both(servers, "start_nbd_disk", {"bdev_name": "MyVol", "nbd_device": "/dev/nbd-does-not-exist"})["error"]["code"] == -32602
