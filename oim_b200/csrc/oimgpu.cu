@@ -499,10 +499,13 @@ extern "C" int oimgpu_init_control_only(void)
 	return 0;
 }
 
+static void unpin_all_host_ranges();	/* oimgpu_mem_ensure's registrations (end of this file) */
+
 extern "C" void oimgpu_fini(void)
 {
 	std::lock_guard<std::mutex> lk(g.mu);
 	if (!g.inited) return;
+	if (!g.control_only) unpin_all_host_ranges();
 	for (auto &kv : g.bdevs) {
 		for (size_t r = 0; r < kv.second->stores.size() && !g.control_only; r++) release_store(*kv.second, r);
 		if (kv.second->hist && !g.control_only) { cudaSetDevice(kv.second->devices[0]); cudaFree(kv.second->hist); }
@@ -2359,6 +2362,15 @@ extern "C" int oimgpu_fill_submit(oimgpu_lun *L, void *dst, uint8_t fill, uint64
 namespace {
 std::mutex g_pin_mu;
 std::map<uintptr_t, uintptr_t> g_pinned;	/* [start, end) of host ranges pinned by oimgpu_mem_ensure, disjoint */
+}
+
+static void unpin_all_host_ranges()
+{
+	std::lock_guard<std::mutex> lk(g_pin_mu);
+	for (auto &kv : g_pinned) {
+		if (cudaHostUnregister((void *)kv.first) != cudaSuccess) (void)cudaGetLastError();
+	}
+	g_pinned.clear();
 }
 
 static bool pin_range(uintptr_t a, uintptr_t b)

@@ -73,6 +73,10 @@ def bind_to_gpu_node(index: int) -> dict:
             info["note"] = f"sched_setaffinity: {e}"
     else:
         info["note"] = f"no CPU of node {node} in this process's cpuset ({len(allowed)} CPUs allowed)"
+    import platform
+    if platform.machine() != "x86_64":
+        info["mempolicy"] = "default (set_mempolicy syscall number known for x86_64 only)"
+        return info
     try:
         libc = ctypes.CDLL(None, use_errno=True)
         mask = ctypes.c_ulong(1 << node)
