@@ -211,3 +211,53 @@ def test_poller_guest_reuses_ring_and_buffers(gpu, oracles):
         assert (gpu.bdev_read_raw("pv1", 0, nb * 512) == want_store).all()
     finally:
         _teardown(gpu, "pv1")
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("resident", [False, True])
+def test_slot_ring_passes_that_straddle_the_ring_end(gpu, oracles, resident):
+    """Submissions of uneven size on one 64-slot ring: passes start at slot 16, 48 (-> wraps to 16), ... so a pass's
+    slots lie in two pieces of the ring - the TMA unit fetches them with two bulk copies (lun_kernel.cu issue_fetch).
+    Launch per kick and resident poller; results equal the oracle's sequential execution."""
+    import torch
+    nb = 1 << 15
+    sizes = [16, 32, 32, 7, 32, 25, 32, 32, 1, 31, 32, 32]
+    n = sum(sizes)
+    t = traces.uniform_trace(n, nb, io_blocks=8, pattern="randrw", read_pct=50, seed=91, lba_span=4096)
+    host = np.zeros(t.arena_bytes, dtype=np.uint8)
+    traces.fill_arena(host, t)
+    with oracles.PortOracle(nb) as o:
+        o.store[:] = traces.pattern_bytes(7, 0, o.store.size)
+        oa = host.copy()
+        want = o.submit(t.reqs, t.bind(oa.ctypes.data))
+        want_store = o.store.copy()
+    name = "wrap1" if resident else "wrap0"
+    _setup(gpu, name, nb)
+    try:
+        arena = torch.from_numpy(host.copy()).pin_memory()
+        iovs = t.bind(arena.data_ptr())
+        got = []
+        with gpu.Lun(name + ".ctl", 0, num_queues=1, queue_size=64) as lun:
+            if resident:
+                lun.start_poller(idle_timeout_ms=WATCHDOG_MS)
+            try:
+                lo = 0
+                for k in sizes:
+                    part = t.reqs[lo:lo + k].copy()
+                    i0 = int(part["iov_start"][0])
+                    part["iov_start"] -= np.uint32(i0)
+                    lun.submit(0, part, iovs[i0:i0 + k])
+                    lun.kick()
+                    c = lun.poll(0, k, wait=True)
+                    assert len(c) == k
+                    got.append(c)
+                    lo += k
+            finally:
+                if resident:
+                    lun.stop_poller()
+        util.assert_cpls_equal(np.concatenate(got), want, t.reqs)
+        assert (arena.numpy() == oa).all()
+        assert (gpu.bdev_read_raw(name, 0, nb * 512) == want_store).all()
+    finally:
+        _teardown(gpu, name)

@@ -20,13 +20,14 @@ def main():
             continue
         ns = float(r[vi].replace(",", ""))
         per[r[ki]].append(ns)
-        if "oimgpu::" in r[ki]:
+        if "oim_" in r[ki]:
             ours.append((r[ki].split("(")[0], int(ns), r[h.index("Grid Size")], r[h.index("Block Size")]))
     total = sum(sum(v) for v in per.values())
     print(f"# ncu launch list (gpu__time_duration.sum, --clock-control none) of: {cmd}")
     print("# per-launch times are cold-cache and serialised: compare shares, not absolutes")
-    print("# the at:: kernels are torch filling the synthetic store / client arenas BEFORE the timed regions;")
-    print("# a timed step is exactly one oim_lun_queue_kernel launch (plus copy-engine memcpys in the e2e leg)\n")
+    print("# (at:: kernels, when listed, are torch filling the synthetic store / client arenas BEFORE the timed regions;)")
+    print("# a timed step is exactly one launch of a queue kernel: oim_lun_queue_kernel (one CTA per queue, slot rings),")
+    print("# oim_lun_shared_queue_kernel (CTAs share queues: fewer than ~160 queues), oim_lun_vring_kernel (guest virtqueues)\n")
     print("| kernel | launches | total ms | share |\n|---|---|---|---|")
     for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         print(f"| {k[:90]} | {len(v)} | {sum(v) / 1e6:.3f} | {100 * sum(v) / total:.1f}% |")
