@@ -942,7 +942,9 @@ def run_ours(args, rank, world, local):
                                "workload": f"one oim-gpu-vhost --gpus 0..{world - 1}, one controller, {world} targets (1 GiB Malloc bdev each, placed "
                                            "one per GPU), one vhost-user session with 254 request queues x 256 READ(10) of 4 KiB per round, requests "
                                            "dealt out over the targets; queue r is served by GPU r mod N (any GPU reaches any target: own HBM or "
-                                           "a peer's over NVLink), so payload crosses all N PCIe links; single-process Python master"}
+                                           "a peer's over NVLink), so payload crosses all N PCIe links; single-process Python master; the guest's RAM is one "
+                                           "registered memfd on one NUMA node: its host-side write ceiling (~86 GB/s on this pool's boxes, "
+                                           "reached with 2 GPUs) bounds this leg, see DESIGN.md 6c'"}
             except Exception as e:  # noqa: BLE001
                 vuser_multi = {"error": f"{type(e).__name__}: {e}"[:300]}
             store.set("oim_multi_gpu_leg_done", "1")
