@@ -786,7 +786,7 @@ def run_ours(args, rank, world, local):
     # ---- config 4 shape: mixed 70/30 random read/write, qd=128 per queue (bdevperf -M 70 -q 128) ----
     mixed = None
     if not args.no_mixed:
-        mq, mp = 1024, 1024                      # 2^20 requests per step; queue q stays inside LBA window q
+        mq, mp = 254, 4128                       # ~2^20 requests per step on the 254 queues a controller can carry; queue q stays inside LBA window q
         mt = traces.partitioned_queues(mq, mp, NUM_BLOCKS, pattern="randrw", read_pct=70, io_blocks=8, seed=plan["trace_seed"] + 99)
         marena = torch.empty(mt.arena_bytes, dtype=torch.uint8, device="cuda")
         marena.view(torch.int64)[:] = 0x5A5A5A5A5A5A5A5A
@@ -807,7 +807,7 @@ def run_ours(args, rank, world, local):
         mc = np.frombuffer(m_cpls.cpu().numpy().tobytes(), dtype=abi.cpl_dtype)
         assert not mc["status"].any()
         miops = aggregate(len(mt.reqs), args.steps, world, mms)
-        mixed = {"metric": "4KiB 70/30 rand r/w IOPS (qd=128 per queue: 4 passes of 32 in flight per queue, 1024 queues, "
+        mixed = {"metric": "4KiB 70/30 rand r/w IOPS (qd=128 per queue: 4 passes of 32 in flight per queue, 254 queues, "
                            "queue q confined to LBA window q)", "value": miops, "unit": "IOPS",
                  "hbm_frac": 2 * 4096 * miops / world / 1e9 / peak, "requests_per_step": len(mt.reqs),
                  "reads": mt.meta["reads"]}

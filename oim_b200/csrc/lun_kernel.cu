@@ -924,9 +924,9 @@ __device__ __noinline__ bool vq_task_data_setup(const LunCtx &L, const QueueDesc
 /* hazard signature: which bit a 4 KiB granule of device address space maps to */
 __device__ __forceinline__ uint32_t sig_index(uint64_t granule)
 {
-	return (uint32_t)(((uint32_t)granule ^ (uint32_t)(granule >> 20)) * 0x9E3779B1u) >> (32 - 12);
+	return (uint32_t)(((uint32_t)granule ^ (uint32_t)(granule >> 20)) * 0x9E3779B1u) >> (32 - OIM_SIG_LOG2);
 }
-static_assert(kSigBits == 1 << 12, "sig_index produces 12 bits");
+static_assert(kSigBits == 1 << OIM_SIG_LOG2, "sig_index produces OIM_SIG_LOG2 bits");
 
 /* ---- the kernel ----------------------------------------------------------------------------- */
 

@@ -251,7 +251,12 @@ struct __align__(16) Stage {
  * the pass if one of its granules is set in the signature that matters for it, so the common case (no
  * conflict) costs a handful of shared-memory loads per request instead of a 32-entry range scan. */
 constexpr int kSmemIovs = 4;
-constexpr int kSigBits = 4096, kSigWords = kSigBits / 32, kSigMaxGranules = 32;
+#ifndef OIM_SIG_LOG2
+#define OIM_SIG_LOG2 14		/* 16 384 bits: with 32 writers a pass sets 0.2 % of them.  At 4096 bits (round 1) four passes in ten
+				 * had a false positive, and the lane that has one scans 32 exact ranges while the others wait:
+				 * 14 % of the parser's time in the random-write profile (profiles/r2_randwrite_ncu.md) */
+#endif
+constexpr int kSigBits = 1 << OIM_SIG_LOG2, kSigWords = kSigBits / 32, kSigMaxGranules = 32;
 
 struct __align__(16) HazPass {
 	uint64_t lo[kPass], hi[kPass];
