@@ -866,10 +866,15 @@ def run_ours(args, rank, world, local):
     if not args.no_seq and not args.no_extra:
         seq_sg = {}
         for sg_name, label in (("single", "1 x 131072 B"),
-                               ("unaligned", "33 elements: 100 B + 31 x 4096 B + 3996 B (byte-granular head and tail, client "
-                                             "buffers aligned like the store)"),
+                               ("unaligned", "33 elements: 100 B + 31 x 4096 B + 3996 B, one client buffer split at those "
+                                             "bytes (each element continues its predecessor: the parser joins the run "
+                                             "into one segment; client buffers aligned like the store)"),
                                ("unaligned+3", "the same 33 elements with every client buffer 3 bytes off the store's "
-                                               "16-byte alignment (funnel-shift realignment in the movers)")):
+                                               "16-byte alignment: one segment per request, every unit realigned "
+                                               "(bulk copy into shared memory, funnel shifts on the way out)"),
+                               ("scattered", "the same 33 element lengths, but no element continues its predecessor in "
+                                             "client memory (reverse placement): 33 segments per request with "
+                                             "byte-granular heads and tails, source 8 bytes off the destination")):
             n5, ms5, _, _ = resident_leg(256, "seqwrite", sg_name, args.seq_queues, args.seq_per_queue, args.steps, args.warmup, None, target=1)
             g5 = n5 * args.steps * world * 131072 / (ms5 / 1e3) / 1e9
             seq_sg[sg_name] = {"value": g5, "unit": "GB/s", "hbm_frac": 2 * g5 / world / peak, "sg": label}

@@ -71,6 +71,130 @@ __device__ __forceinline__ void tma_load_bulk(void *dst_smem, const void *src_gm
 		     :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/* ---- byte-granular SG elements: the unit goes through shared memory ---------------------------------
+ *
+ * A unit whose source, destination or length is not a multiple of 16 (SURVEY.md §7 "unaligned SG elements",
+ * the 100 B + 31 x 4096 B + 3996 B list of SURVEY §8(d) C3 when its elements do not continue each other) cannot
+ * take the register path at full depth: realigning in registers needs the neighbour lane's vector (shuffles) and
+ * a ninth vector per lane, which spills at 128 registers, and with half-units in flight the movers are latency
+ * bound (0.66-0.78 of the HBM peak, profiles/r2_bench_n1.json).  Here the TMA unit fetches the aligned bytes
+ * that cover the unit (<= 4112) in ONE bulk copy - no registers held while it flies - and the lanes realign
+ * from shared memory: two aligned 16-byte LDS per output vector, funnel shifts, aligned 16-byte stores.
+ * Over-read: up to 15 bytes on either side, inside aligned vectors that hold a byte of the element (never across
+ * a page), read into shared memory and never stored. */
+__device__ __forceinline__ int4 lds16(const uint8_t *p)
+{
+	int4 r;
+	asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];"
+		     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)) : "memory");
+	return r;
+}
+
+/* output vector = bytes m .. m+15 of the 32 bytes (a, b); Q = m / 4 picks the words at compile time, the byte shift
+ * r = 8 (m % 4) is a funnel-shift operand */
+template <int Q>
+__device__ __forceinline__ void realign_rows(uint8_t *d, const uint8_t *base, uint32_t nv, uint32_t r, int lane)
+{
+#pragma unroll 4
+	for (uint32_t v = lane; v < nv; v += 32) {
+		const int4 a = lds16(base + v * 16), b = lds16(base + v * 16 + 16);
+		const uint32_t w[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+		st_cg16(d + (size_t)v * 16, make_int4(__funnelshift_r(w[Q], w[Q + 1], r), __funnelshift_r(w[Q + 1], w[Q + 2], r),
+						      __funnelshift_r(w[Q + 2], w[Q + 3], r), __funnelshift_r(w[Q + 3], w[Q + 4], r)));
+	}
+}
+
+/* One unit = two pieces, each with its own half of the warp's staging buffer and its own barrier: the first ends
+ * where the destination is 16-byte aligned (head + 127 vectors), the second takes the rest.  While a piece is realigned
+ * out of shared memory the other one is still flying, and when the mover knows its NEXT unit (same fill, no barrier in
+ * between) that unit's pieces are requested as soon as the buffers are free: loads and realignment overlap, which is
+ * what the register path could not do (profiles/r2_unaligned3_ncu.md: before, 44 % of the movers' samples sat on the
+ * arrival of the unit they were about to realign). */
+constexpr uint32_t kPieceBody = 2032;			/* 127 vectors */
+constexpr uint32_t kPieceBuf = (kUnitBytes + 128) / 2;	/* 2112 >= 15 + (kUnitBytes - kPieceBody) + 15 rounded to 16 */
+
+struct UStage {			/* per mover warp, in registers */
+	const uint8_t *pf_src;	/* source of the unit whose pieces are already requested (nullptr: none) */
+	uint32_t phase;		/* bit s: parity of the barrier of piece s */
+};
+
+__device__ __forceinline__ uint32_t piece0_bytes(const uint8_t *dst, uint32_t n)
+{
+	const uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+	return min(n, head + kPieceBody);
+}
+
+/* lane 0: request the aligned bytes that cover [src, src + n) */
+__device__ __forceinline__ void ustage_issue(const uint8_t *src, uint32_t n, uint8_t *buf, uint64_t *bar)
+{
+	const uint32_t so = (uint32_t)((uintptr_t)src & 15);
+	const uint32_t span = (so + n + 15) & ~15u;
+	mbar_expect_tx(bar, span);
+	tma_load_bulk(buf, src - so, span, bar);
+}
+
+/* the warp: wait for the piece, move it out */
+__device__ __forceinline__ void ustage_consume(uint8_t *dst, const uint8_t *src, uint32_t n, int lane,
+					       const uint8_t *buf, uint64_t *bar, uint32_t parity)
+{
+	const uint32_t so = (uint32_t)((uintptr_t)src & 15);
+	uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+	if (head > n) head = n;
+	const uint32_t body = n - head, nv = body >> 4, tail = body & 15;
+	const uint32_t o = so + head;			/* where the body starts in the staged bytes */
+	const uint32_t m = o & 15, r = (m & 3) * 8;
+	const uint8_t *base = buf + (o & ~15u);
+	uint8_t *d = dst + head;
+	mbar_wait(bar, parity);
+	if ((uint32_t)lane < head) dst[lane] = buf[so + lane];
+	if (m == 0) {
+#pragma unroll 4
+		for (uint32_t v = lane; v < nv; v += 32) st_cg16(d + (size_t)v * 16, lds16(base + v * 16));
+	} else {
+		switch (m >> 2) {
+		case 0: realign_rows<0>(d, base, nv, r, lane); break;
+		case 1: realign_rows<1>(d, base, nv, r, lane); break;
+		case 2: realign_rows<2>(d, base, nv, r, lane); break;
+		default: realign_rows<3>(d, base, nv, r, lane); break;
+		}
+	}
+	if ((uint32_t)lane < tail) d[(size_t)nv * 16 + lane] = buf[o + nv * 16 + lane];
+	__syncwarp();		/* every lane has read its bytes: the buffer may be refilled */
+}
+
+/* pfence: a mover of this or another CTA may have written the source bytes earlier in this launch (a read behind
+ * a write, ordered by the stage / drain / wave barriers - generic-proxy events) and the bulk copy reads through the
+ * async proxy: the first staged unit after such a barrier crosses proxies with a fence.  Prefetched units never
+ * follow a barrier (the mover asks for the next unit only when nothing has to be waited for in between).
+ * nsrc != nullptr: the unit this warp moves next, (ndst, nsrc, nn), also takes this path - request it. */
+__device__ OIM_SMEM_PATH_INLINE void move_unit_via_smem(uint8_t *dst, const uint8_t *src, uint32_t n, int lane,
+							  uint8_t *ust, uint64_t *bar, UStage &us, bool &pfence,
+							  uint8_t *ndst, const uint8_t *nsrc, uint32_t nn)
+{
+	const uint32_t n0 = piece0_bytes(dst, n), n1 = n - n0;
+	if (us.pf_src != src) {
+		if (lane == 0) {
+			if (pfence) asm volatile("fence.proxy.async.global;" ::: "memory");
+			ustage_issue(src, n0, ust, &bar[0]);
+			if (n1) ustage_issue(src + n0, n1, ust + kPieceBuf, &bar[1]);
+		}
+		pfence = false;
+	}
+	ustage_consume(dst, src, n0, lane, ust, &bar[0], us.phase & 1);
+	us.phase ^= 1;
+	uint32_t m0 = 0;
+	if (nsrc) {
+		m0 = piece0_bytes(ndst, nn);
+		if (lane == 0) ustage_issue(nsrc, m0, ust, &bar[0]);
+	}
+	if (n1) {
+		ustage_consume(dst + n0, src + n0, n1, lane, ust + kPieceBuf, &bar[1], (us.phase >> 1) & 1);
+		us.phase ^= 2;
+	}
+	if (nsrc && nn > m0 && lane == 0) ustage_issue(nsrc + m0, nn - m0, ust + kPieceBuf, &bar[1]);
+	us.pf_src = nsrc;
+}
+
 /* ---- shared queues: position counters in device memory, handed from CTA to CTA ------------------- */
 
 __device__ __forceinline__ uint32_t ld_acquire32(const uint32_t *p)
@@ -281,7 +405,7 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 	const bool from_dev = (r.dir == OIMGPU_DIR_FROM_DEV) || cnt == 0;
 	const uint32_t dxfer_dir = from_dev ? OIMGPU_DIR_FROM_DEV : OIMGPU_DIR_TO_DEV;
 	uint32_t nonzero = 0, units = 0;
-	uint64_t len64 = 0;
+	uint64_t len64 = 0, run_len = 0, run_end = 0;	/* the run of contiguous elements being summed */
 
 	s.op = OP_NONE; s.nseg = 0; s.valid = 1; s.length = 0; s.off = 0; s.tgt = L.target;
 	s.store_lo = s.store_hi = 0;
@@ -296,8 +420,24 @@ __device__ __forceinline__ void parse_request(const LunCtx &L, const QueueDesc &
 		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
 		if (v.addr == 0) { valid = false; break; }
 		len64 += v.len;
-		if (v.len) { nonzero++; units += units_of(v.len); }
+		if (v.len) {
+			/* elements that continue each other in client memory (a buffer that starts inside a page, split at
+			 * page boundaries, as guests hand them over) move as ONE segment: the store side is contiguous by
+			 * construction, so the per-element memcpys of bdev_malloc.c:180-189 add up to one copy of the run -
+			 * with unit boundaries on the run, not on every element's odd head and tail.  A run that ends on
+			 * a unit boundary is closed: joining the next element would give the same units, and separate
+			 * segments measured 3 % faster on 32 x 4 KiB pages (bench.py seq128k_sg: pages vs single) */
+			if ((run_len & (kUnitBytes - 1)) && v.addr == run_end) {
+				run_len += v.len;
+			} else {
+				units += units_of(run_len);
+				run_len = v.len;
+				nonzero++;
+			}
+			run_end = v.addr + v.len;
+		}
 	}
+	units += units_of(run_len);
 	/* The reference sums the element lengths in 32 bits (vhost_scsi.c:573, 596 `len += desc->len`): two
 	 * elements of 2 GiB + 4 KiB wrap to 4 KiB, every length check passes on the wrapped value, and the copy
 	 * then runs over the full elements.  There that overruns the target's own process; here it would cross
@@ -411,18 +551,25 @@ __device__ __forceinline__ void emit_segments(const LunCtx &L, const QueueDesc &
 	uint8_t *pos = T.store[0] + s.off;
 	const bool rd = s.op == OP_READ;
 	uint32_t k = 0, u = first_unit;
+	uint64_t run_end = 0;
+	Segment *g = nullptr;		/* the open run of contiguous elements (see parse_request: same rule, same counts) */
 	for (uint32_t j = 0; j < r.iovcnt; j++) {
 		const oimgpu_iov v = q.iovs[(r.iov_start + j) & q.iov_mask];
 		if (v.len == 0) continue;
-		Segment &g = out[k++];
-		uint8_t *client = (uint8_t *)(uintptr_t)v.addr;
-		g.src = rd ? pos : client;
-		g.dst = rd ? client : pos;
-		g.mirror = rd ? 0 : mirror_tag;
-		g.len = v.len;
-		g.first_unit = u;
-		g.wave = wave;
-		u += units_of(v.len);
+		if (g && (g->len & (kUnitBytes - 1)) && v.addr == run_end) {
+			g->len += v.len;
+		} else {
+			if (g) u += units_of(g->len);
+			g = &out[k++];
+			uint8_t *client = (uint8_t *)(uintptr_t)v.addr;
+			g->src = rd ? pos : client;
+			g->dst = rd ? client : pos;
+			g->mirror = rd ? 0 : mirror_tag;
+			g->len = v.len;
+			g->first_unit = u;
+			g->wave = wave;
+		}
+		run_end = v.addr + v.len;
 		pos += v.len;
 	}
 }
@@ -1160,6 +1307,7 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 		}
 		mbar_init(&sh.req_bar[0], 1);
 		mbar_init(&sh.req_bar[1], 1);
+		for (int w = 0; w < kMovers; w++) { mbar_init(&sh.ubar[w][0], 1); mbar_init(&sh.ubar[w][1], 1); }
 		sh.pub_q = nullptr;
 		sh.pub_end = 0;
 		for (int t = 0; t < OIMGPU_CTRLR_MAX_DEVS; t++) sh.lat_ns[t][0] = sh.lat_ns[t][1] = sh.lat_ns[t][2] = 0;
@@ -1672,7 +1820,11 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						const uint32_t b = __shfl_up_sync(0xffffffffu, unit_incl, o);
 						if (lane >= o) { seg_incl += a; unit_incl += b; }
 					}
-					const uint32_t fits = __ballot_sync(0xffffffffu, in && seg_incl <= (uint32_t)kSegCap);
+					/* ... and a bounded number of units (the first request of a round always fits): a pass of 32 x
+					 * 128 KiB in ONE fill of 1024 units ran at 0.958 of the HBM peak, in fills of <= 256 units at
+					 * 0.984 (bench.py seq128k_sg "single"; 4 KiB passes are 32 units and never split) */
+					const uint32_t fits = __ballot_sync(0xffffffffu, in && seg_incl <= (uint32_t)kSegCap &&
+									    (unit_incl <= (uint32_t)kFillUnits || (uint32_t)lane == r0));
 					const uint32_t r1 = r0 + __popc(fits);	/* prefix property: seg_incl is monotonic */
 					const bool mine = in && (uint32_t)lane < r1;
 
@@ -1718,11 +1870,16 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 						st.nseg = tot_seg;
 						st.nunits = tot_unit;
 						st.nwaves = nwaves;
+#if OIM_SPLIT_FILLS_STREAM
+						/* later fills of a split pass: with conflicts INSIDE the pass (waves) they wait for the fill
+						 * before them, up front; without, only the requests that conflict with an earlier pass wait,
+						 * for the fill before (which covers every older one; c - drain itself may be more than a
+						 * stage ring behind by now) */
+						st.drain = (r0 > 0) ? ((nwaves > 1 || drain) ? 1 : 0) : drain;
+						st.drain_upfront = r0 > 0 && nwaves > 1;
+#else
 						/* later fills of a split pass simply wait for the fill before them, up front */
 						st.drain = (r0 > 0) ? 1 : drain;
-#ifdef OIM_DRAIN_UPFRONT	/* tuning builds: stall the whole fill, as before the per-unit flag existed */
-						st.drain_upfront = 1;
-#else
 						st.drain_upfront = r0 > 0;
 #endif
 						st.stop = 0;
@@ -1815,11 +1972,14 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 	} else {
 		/* ======================= MOVERS ======================= */
 		const int mw = warp - 1;
+		UStage us = {nullptr, 0};	/* this warp's staging buffer (move_unit_via_smem) */
+		bool upfence = true;		/* the next staged unit follows a barrier another mover's stores may hide behind */
 		for (uint32_t c = 0;; c++) {
 			const uint32_t sidx = c % kStages;
 			Stage &st = sh.stage[sidx];
 			mbar_wait(&sh.full[sidx], (c / kStages) & 1);
 			if (st.stop) break;
+			upfence = true;
 			const uint32_t nseg = st.nseg, nunits = st.nunits, nw = st.nwaves;
 			/* RAW/WAW/WAR against fill c-drain: before touching a flagged unit, wait until every mover has
 			 * left that fill (a mover arrives on `empty` only after finishing its share of all earlier
@@ -1840,40 +2000,67 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 				if (lane == 0) v = atomicAdd(&st.unit_ctr, 1u);
 				return __shfl_sync(0xffffffffu, v, 0);
 			};
+			auto find_seg = [&](uint32_t u) -> uint32_t {
+				uint32_t lo = u, hi = nseg;	/* last segment with first_unit <= u */
+				/* as many units as segments: segment u IS unit u.  Taken for passes of small requests (the
+				 * 4 KiB case, +1.5 %); long SG lists of single pages keep the search - measured 1.5 %
+				 * faster there, the lookup's latency spreads the movers' loads */
+				if (nunits != nseg || nseg > (uint32_t)kPass) {
+					lo = 0;
+					while (hi - lo > 1) {
+						const uint32_t mid = (lo + hi) >> 1;
+						if (st.seg[mid].first_unit <= u) lo = mid; else hi = mid;
+					}
+				}
+				return lo;
+			};
 			for (uint32_t w = 0; w < nw; w++) {
 				for (uint32_t u = dyn ? next_unit(0) : (uint32_t)mw, u_next = 0; u < nunits; u = u_next) {
 					u_next = next_unit(u);	/* drawn before this unit moves: the counter's latency hides behind the loads */
-					uint32_t lo = u, hi = nseg;	/* last segment with first_unit <= u */
-					/* as many units as segments: segment u IS unit u.  Taken for passes of small requests (the
-					 * 4 KiB case, +1.5 %); long SG lists of single pages keep the search - measured 1.5 %
-					 * faster there, the lookup's latency spreads the movers' loads */
-					if (nunits != nseg || nseg > (uint32_t)kPass) {
-						lo = 0;
-						while (hi - lo > 1) {
-							const uint32_t mid = (lo + hi) >> 1;
-							if (st.seg[mid].first_unit <= u) lo = mid; else hi = mid;
-						}
-					}
-					const Segment &g = st.seg[lo];
+					const Segment &g = st.seg[find_seg(u)];
 					if (nw > 1 && (g.wave & kSegWaveMask) != w) continue;
 					if ((g.wave & kSegWaitsForDrain) && !drained) {
 						const uint32_t p = c - drain;
 						mbar_wait(&sh.empty[p % kStages], (p / kStages) & 1);
 						drained = true;
+						upfence = true;
 					}
 					const uint64_t off = (uint64_t)(u - g.first_unit) * kUnitBytes;
 					const uint32_t nbytes = (uint32_t)min((uint64_t)kUnitBytes, g.len - off);
 					const uint8_t *src = g.src;
 					uint8_t *dst = g.dst;
 					if (!kMirrored || !g.mirror) {
-						if (src) move_unit<kMirrored>(dst + off, src + off, nbytes, lane);
-						else zero_unit(dst + off, nbytes, lane);
+						if constexpr (kMirrored) {
+							if (src) move_unit<true>(dst + off, src + off, nbytes, lane);
+							else zero_unit(dst + off, nbytes, lane);
+						} else {
+							if (!src) {
+								zero_unit(dst + off, nbytes, lane);
+							} else if ((((uintptr_t)(dst + off) | (uintptr_t)(src + off) | nbytes) & 15) == 0) {
+								move_unit(dst + off, src + off, nbytes, lane);
+							} else {
+								/* the unit this warp moves next, when it is known and nothing has to be waited for
+								 * before it may be read: its bytes are requested while this one is realigned */
+								uint8_t *ndst = nullptr; const uint8_t *nsrc = nullptr; uint32_t nn = 0;
+#if OIM_USTAGE_PREFETCH
+								if (u_next < nunits) {
+									const Segment &g2 = st.seg[find_seg(u_next)];
+									if (g2.src && (nw == 1 || (g2.wave & kSegWaveMask) == w) && (!(g2.wave & kSegWaitsForDrain) || drained)) {
+										const uint64_t off2 = (uint64_t)(u_next - g2.first_unit) * kUnitBytes;
+										nn = (uint32_t)min((uint64_t)kUnitBytes, g2.len - off2);
+										if ((((uintptr_t)(g2.dst + off2) | (uintptr_t)(g2.src + off2) | nn) & 15) != 0) { ndst = g2.dst + off2; nsrc = g2.src + off2; }
+									}
+								}
+#endif
+								move_unit_via_smem(dst + off, src + off, nbytes, lane, sh.ustage[mw], sh.ubar[mw], us, upfence, ndst, nsrc, nn);
+							}
+						}
 					} else {
 						const LunCtx &T = (g.mirror - 1 == lun->target) ? *lun : *lun->peer[g.mirror - 1];
 						mirror_unit(T, dst, src, off, nbytes, lane, T.nreplicas);
 					}
 				}
-				if (nw > 1) movers_barrier();
+				if (nw > 1) { movers_barrier(); upfence = true; }
 			}
 			if (mw == 0 && lane == 0 && st.lat_ntgt) {
 				const unsigned long long dt = globaltimer_ns() - st.t0;

@@ -48,6 +48,16 @@ constexpr int kPass = OIMGPU_REQS_PER_PASS;	/* 32 = one warp of parser lanes */
 constexpr int kMovers = OIM_MOVERS;		/* mover warps per CTA */
 constexpr int kThreads = (1 + kMovers) * 32;	/* parser warp + movers */
 constexpr int kStages = OIM_STAGES;		/* parser -> mover pipeline depth */
+#ifndef OIM_FILL_UNITS
+#define OIM_FILL_UNITS 256
+#endif
+#ifndef OIM_SPLIT_FILLS_STREAM
+#define OIM_SPLIT_FILLS_STREAM 0	/* tuning builds: 1 = later fills of a hazard-free split pass do not wait for the fill
+					 * before them.  Measured WORSE (128 KiB legs 0.96-0.97 instead of 0.98-0.99,
+					 * tools/exp_fill_variants.sh): the wait re-aligns the seven movers every 256 units,
+					 * and movers that drift apart cost more than the bubble at the fill boundary */
+#endif
+constexpr int kFillUnits = OIM_FILL_UNITS;	/* units per stage fill (a request larger than that has a fill of its own) */
 constexpr int kSegCap = 256;			/* SG segments per stage (>= 256 UNMAP descriptors, >= 129 iovecs) */
 constexpr uint32_t kUnitBytes = 4096;		/* bytes one warp moves per step: 8 x 16 B per lane */
 constexpr int kMaxReplicas = 4;
@@ -279,10 +289,20 @@ struct __align__(16) CtaShared {
 	uint64_t full[kStages];		/* mbarriers */
 	uint64_t empty[kStages];
 	uint64_t released[kStages];	/* shared kernels: the fill's completions are published, the stage may be refilled */
+	uint64_t ubar[kMovers][2];	/* movers: arrival of the two pieces of a byte-granular unit in ustage (move_unit_via_smem) */
 	QShare  *pub_q;			/* shared kernels, mover warp 0: queue and end position of its last publication */
 	uint32_t pub_end;
 	unsigned long long lat_ns[OIMGPU_CTRLR_MAX_DEVS][3];	/* mover warp 0, lane 0: summed latencies of this CTA per target (reads, writes, unmaps) */
+	/* one staging buffer per mover warp for units that are not 16-byte aligned on both sides: the aligned bytes
+	 * covering a unit (<= kUnitBytes + 16) land here by bulk copy and are realigned on the way out */
+	__align__(128) uint8_t ustage[kMovers][kUnitBytes + 128];
 };
+#ifndef OIM_SMEM_PATH_INLINE
+#define OIM_SMEM_PATH_INLINE __forceinline__
+#endif
+#ifndef OIM_USTAGE_PREFETCH
+#define OIM_USTAGE_PREFETCH 1	/* tuning builds: 0 = a staged unit is requested only when its turn has come */
+#endif
 
 /* ------------------------------------------------------------------------------------------ */
 

@@ -171,13 +171,16 @@ def uniform_trace(n: int, num_blocks: int, *, io_blocks: int = 8, block_size: in
     shift = 0
     if sg.endswith("+3"):                    # client buffers 3 bytes off the store's alignment: the realign path
         sg, shift = sg[:-2], 3
-    lens = _sg_layout(n, io_bytes, sg)
+    scattered = sg == "scattered"            # the unaligned elements, but none continues its predecessor in client memory
+    lens = _sg_layout(n, io_bytes, "unaligned" if scattered else sg)
     k = len(lens)
     stride = -(-(io_bytes + shift) // buf_align) * buf_align
     reqs = _finish(n, cdb, np.where(is_read, abi.DIR_FROM_DEV, abi.DIR_TO_DEV).astype(np.uint8),
                    np.full(n, k, dtype=np.uint16), target)
     iovs = np.zeros(n * k, dtype=abi.iov_dtype)
     within = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.uint64)
+    if scattered:                            # element j sits where the reversed list would put it
+        within = (io_bytes - np.cumsum(lens)).astype(np.uint64)
     base = (np.arange(n, dtype=np.uint64) * np.uint64(stride) + np.uint64(shift))[:, None]
     iovs["addr"] = (base + within[None, :]).reshape(-1)
     iovs["len"] = np.tile(np.asarray(lens, dtype=np.uint32), n)
@@ -217,7 +220,10 @@ def partitioned_queues(nq: int, per_q: int, num_blocks: int, **kw) -> Trace:
 
 def fuzz_trace(n: int, num_blocks: int, *, block_size: int = 512, seed: int = 1, target: int = 0,
                max_io_blocks: int = 64, arena_bytes: int = 8 << 20, allow_overlap: bool = True,
-               include_malformed: bool = True) -> Trace:
+               include_malformed: bool = True, contiguous: bool = False) -> Trace:
+    """contiguous: multi-element SG lists are cuts of ONE client buffer (a guest buffer split at arbitrary
+    places: elements continue each other, with zero-length elements and an occasional gap in between) instead
+    of separate allocations."""
     rng = np.random.default_rng(seed)
     b = abi.Batch(target)
     cursor = [0]
@@ -246,6 +252,15 @@ def fuzz_trace(n: int, num_blocks: int, *, block_size: int = 512, seed: int = 1,
             cuts = sorted(set((c // 512) * 512 for c in cuts))
         edges = [0] + [c for c in cuts if 0 < c < nbytes] + [nbytes]
         out = []
+        if contiguous:
+            base = alloc(nbytes + 16, 1) + (int(rng.integers(0, 16)) if style == 5 else 0)
+            for a, z in zip(edges[:-1], edges[1:]):
+                if rng.integers(0, 5) == 0:              # a gap: the rest lives in another buffer
+                    base = alloc(nbytes + 16, 1) + int(rng.integers(0, 16))
+                out.append((base + a, z - a))
+                if rng.integers(0, 4) == 0:
+                    out.append((alloc(0), 0))            # a zero-length element does not break a run
+            return out
         for a, z in zip(edges[:-1], edges[1:]):
             out.append((alloc(z - a + 16, 1) + int(rng.integers(0, 16)) if style == 5
                         else alloc(z - a, 1), z - a))

@@ -87,9 +87,11 @@ class _Alloc:
 
 
 def build_image(requests: list[dict], *, ring_size: int = 256, data_bytes: int = 24 << 20, seed: int = 0,
-                mutate: bool = True, pattern_seed: int = 0x5EED) -> GuestImage:
+                mutate: bool = True, pattern_seed: int = 0x5EED, contiguous: bool = False) -> GuestImage:
     """requests: [{'cdb','dir','lun','tag','sg': [len,...], 'payload': optional bytes for TO_DEV}]
-    One kick's worth: at most ring_size requests."""
+    One kick's worth: at most ring_size requests.
+    contiguous: a request's data elements are cuts of one guest buffer (each continues its predecessor, with an
+    occasional gap) instead of separate buffers."""
     rng = np.random.default_rng(seed)
     r2_size = (4 << 20) + data_bytes
     arena = np.zeros(2 * R01_SIZE + r2_size, dtype=np.uint8)
@@ -138,6 +140,7 @@ def build_image(requests: list[dict], *, ring_size: int = 256, data_bytes: int =
         # data buffers
         bufs = []
         pos = 0
+        run_next = None                                # contiguous: where the next element goes
         for ln in sg_lens:
             cross = mutate and ln >= 8192 and not crossed[0] and rng.integers(0, 6) == 0
             if cross:
@@ -157,7 +160,12 @@ def build_image(requests: list[dict], *, ring_size: int = 256, data_bytes: int =
                     continue
                 except (KeyError, ValueError):
                     pass
-            o = data.take(ln + 16, 1) + int(rng.integers(0, 16)) if ln else data.take(16, 1)
+            if contiguous and ln:
+                if run_next is None or rng.integers(0, 5) == 0:
+                    run_next = data.take(sum(sg_lens) - pos + 16, 1) + int(rng.integers(0, 16))
+                o, run_next = run_next, run_next + ln
+            else:
+                o = data.take(ln + 16, 1) + int(rng.integers(0, 16)) if ln else data.take(16, 1)
             if not from_dev and rq.get("payload") is not None and ln:
                 arena[o:o + ln] = rq["payload"][pos:pos + ln]
             pos += ln

@@ -44,6 +44,22 @@ def test_cuda_matches_oracle_on_fuzz(gpu, oracles, seed):
         assert (got[1] == ref[1]).all() and (got[2] == ref[2]).all()
 
 
+@pytest.mark.parametrize("seed", range(340, 348))
+def test_cuda_sg_elements_that_continue_each_other(gpu, oracles, seed):
+    """SG lists cut from ONE client buffer at arbitrary bytes (with zero-length elements and gaps in between): the
+    kernel moves a run of elements that continue each other in client memory as one segment (lun_kernel.cu
+    parse_request / emit_segments), the reference copies element by element (bdev_malloc.c:180-189) - same bytes"""
+    nb = 32768
+    t = traces.fuzz_trace(400, nb, seed=seed, max_io_blocks=[8, 64, 300, 1024][seed % 4], contiguous=True,
+                          arena_bytes=(8 << 20) if seed % 4 < 3 else (48 << 20))
+    checker = oracles.RefOracle if oracles.ref_available() and seed % 2 else oracles.PortOracle
+    want = util.run_oracle(checker, t, nb)
+    got = util.run_cuda(gpu, t, nb, mem="device" if seed % 2 else "host")
+    util.assert_cpls_equal(got[0], want[0], t.reqs, f"seed {seed}")
+    assert (got[1] == want[1]).all(), f"client arena differs at {np.nonzero(got[1] != want[1])[0][:8]}"
+    assert (got[2] == want[2]).all(), f"store differs at {np.nonzero(got[2] != want[2])[0][:8]}"
+
+
 def test_cuda_hazards_same_lba_chain(gpu, oracles):
     """32 requests of one pass all on the same blocks: W,R,W,R,... must serialise exactly"""
     nb = 4096

@@ -6,21 +6,21 @@ import pytest
 from oim_b200 import traces, vring
 
 
-def make_requests(seed: int, n: int = 96, nb: int = 32768):
-    t = traces.fuzz_trace(n, nb, seed=seed, max_io_blocks=[8, 64, 300][seed % 3], arena_bytes=16 << 20)
+def make_requests(seed: int, n: int = 96, nb: int = 32768, contiguous: bool = False):
+    t = traces.fuzz_trace(n, nb, seed=seed, max_io_blocks=[8, 64, 300][seed % 3], arena_bytes=16 << 20, contiguous=contiguous)
     a0 = np.zeros(t.arena_bytes, dtype=np.uint8)
     traces.fill_arena(a0, t)
     return vring.requests_from_trace(t, a0)
 
 
-def run_kicks_oracle(cls, rq, nb, ring_size, seed, mutate=True):
+def run_kicks_oracle(cls, rq, nb, ring_size, seed, mutate=True, contiguous=False):
     """replay `rq` in as many kicks as the ring needs; -> [(masked image, sorted used entries, cursors)], store"""
     out = []
     with cls(nb) as o:
         o.store[:] = traces.pattern_bytes(7, 0, o.store.size)
         pos = kick = 0
         while pos < len(rq):
-            img = vring.build_image(rq[pos:], ring_size=ring_size, seed=seed * 100 + kick, mutate=mutate)
+            img = vring.build_image(rq[pos:], ring_size=ring_size, seed=seed * 100 + kick, mutate=mutate, contiguous=contiguous)
             n, la, lu = o.vq_process(img)
             idx, ring = img.used_entries()
             out.append((img.masked(img.arena), sorted((int(i), int(l)) for i, l in ring[:idx]), (n, la, lu)))
@@ -57,14 +57,17 @@ def test_vring_broken_avail_index(oracles):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", range(420, 432))
+@pytest.mark.parametrize("seed", list(range(420, 432)) + [1420, 1421, 1422, 1423])
 @pytest.mark.parametrize("mem", ["device", "host"])
 def test_cuda_vring_matches_oracle(gpu, oracles, seed, mem):
+    """seeds >= 1000: every request's data descriptors are cuts of one guest buffer - the kernel moves a run of
+    descriptors that continue each other as one segment, the reference copies them one by one"""
     import torch
-    nb, rq = 32768, make_requests(seed)
+    contiguous = seed >= 1000
+    nb, rq = 32768, make_requests(seed, contiguous=contiguous)
     ring = [64, 256, 1024][seed % 3]
     checker = oracles.RefOracle if oracles.ref_available() and seed % 2 else oracles.PortOracle
-    want, want_store = run_kicks_oracle(checker, rq, nb, ring, seed)
+    want, want_store = run_kicks_oracle(checker, rq, nb, ring, seed, contiguous=contiguous)
 
     gpu.construct_malloc_bdev(nb, 512, name=f"vq{seed}{mem}", device=0)
     gpu.construct_vhost_scsi_controller(f"vq{seed}{mem}.ctl")
@@ -75,7 +78,7 @@ def test_cuda_vring_matches_oracle(gpu, oracles, seed, mem):
             pos = kick = 0
             la = lu = 0
             while pos < len(rq):
-                img = vring.build_image(rq[pos:], ring_size=ring, seed=seed * 100 + kick)
+                img = vring.build_image(rq[pos:], ring_size=ring, seed=seed * 100 + kick, contiguous=contiguous)
                 # each kick is a fresh guest image (cursors restart at 0, as in the oracle replay)
                 if mem == "device":
                     dev = torch.from_numpy(img.arena).to("cuda:0")
