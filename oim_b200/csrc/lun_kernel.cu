@@ -1256,7 +1256,12 @@ __device__ __forceinline__ uint32_t find_shared_work(const KickHeader *hdr, cons
  * buffers, 32 used elements and a fence that waits for every load the parser has in flight - 18 % of the time of the
  * warp the virtqueue mode is bound by (profiles/r2_vq_ncu.md).  The slot-ring kernels keep the parser publishing: they
  * are bound by the movers, and their publication is three coalesced vectors per request without a fence. */
-template <bool kMirrored, bool kShared, bool kMoverReap = kShared>
+/* kStaged: byte-granular units go through this warp's staging buffer (move_unit_via_smem) - the kernel is launched
+ * with the 29 KB the buffers take.  The mirror kernels (NVLink-bound, compact path) and the vring kernel do without:
+ * the virtqueue parser lives on the L1 (descriptor tables, rings, the memory table), and two CTAs with staging
+ * buffers leave it 32 KB per SM instead of 96 - measured 4-6 % on the virtqueue legs (tools/exp_vq_variants.sh:
+ * shared memory that nothing used cost the same), while guests' buffers are sector-aligned as a rule */
+template <bool kMirrored, bool kShared, bool kMoverReap = kShared, bool kStaged = !kMirrored>
 __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -2038,6 +2043,8 @@ __device__ __forceinline__ void lun_queue_body(LunCtx *lun, KickHeader *hdr, con
 								zero_unit(dst + off, nbytes, lane);
 							} else if ((((uintptr_t)(dst + off) | (uintptr_t)(src + off) | nbytes) & 15) == 0) {
 								move_unit(dst + off, src + off, nbytes, lane);
+							} else if constexpr (!kStaged || !OIM_USTAGE) {
+								move_unit(dst + off, src + off, nbytes, lane);
 							} else {
 								/* the unit this warp moves next, when it is known and nothing has to be waited for
 								 * before it may be read: its bytes are requested while this one is realigned */
@@ -2114,7 +2121,7 @@ oim_lun_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queue
 __global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
 oim_lun_vring_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues)
 {
-	lun_queue_body<false, false, true>(lun, hdr, queues);
+	lun_queue_body<false, false, true, false>(lun, hdr, queues);
 }
 
 __global__ void __launch_bounds__(kThreads, OIM_MIN_BLOCKS)
@@ -2181,6 +2188,7 @@ oim_digest_kernel(const uint64_t *p, uint64_t nwords, unsigned long long *out)
 	if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], a); atomicAdd(&out[1], b); }
 }
 
-size_t lun_kernel_smem_bytes() { return sizeof(CtaShared); }
+/* staged: with the movers' staging buffers (the last member), for the kernels instantiated with kStaged */
+size_t lun_kernel_smem_bytes(bool staged) { return staged && OIM_USTAGE ? sizeof(CtaShared) : offsetof(CtaShared, ustage); }
 
 }  // namespace oimgpu

@@ -48,6 +48,9 @@ constexpr int kPass = OIMGPU_REQS_PER_PASS;	/* 32 = one warp of parser lanes */
 constexpr int kMovers = OIM_MOVERS;		/* mover warps per CTA */
 constexpr int kThreads = (1 + kMovers) * 32;	/* parser warp + movers */
 constexpr int kStages = OIM_STAGES;		/* parser -> mover pipeline depth */
+#ifndef OIM_USTAGE
+#define OIM_USTAGE 1		/* tuning builds: 0 = byte-granular units take the register path (move_unit_unaligned) */
+#endif
 #ifndef OIM_FILL_UNITS
 #define OIM_FILL_UNITS 256
 #endif
@@ -295,6 +298,10 @@ struct __align__(16) CtaShared {
 	unsigned long long lat_ns[OIMGPU_CTRLR_MAX_DEVS][3];	/* mover warp 0, lane 0: summed latencies of this CTA per target (reads, writes, unmaps) */
 	/* one staging buffer per mover warp for units that are not 16-byte aligned on both sides: the aligned bytes
 	 * covering a unit (<= kUnitBytes + 16) land here by bulk copy and are realigned on the way out */
+#ifdef OIM_SMEM_PAD	/* tuning builds: shared memory that nothing uses (what does the smaller L1 cost?) */
+	uint8_t pad_[OIM_SMEM_PAD];
+#endif
+	/* LAST member: kernels without the staged path are launched without it (lun_kernel_smem_bytes) */
 	__align__(128) uint8_t ustage[kMovers][kUnitBytes + 128];
 };
 #ifndef OIM_SMEM_PATH_INLINE

@@ -36,7 +36,7 @@ __global__ void oim_lun_vring_kernel(LunCtx *lun, KickHeader *hdr, const QueueDe
 __global__ void oim_lun_shared_queue_mirror_kernel(LunCtx *lun, KickHeader *hdr, const QueueDesc *queues);
 __global__ void oim_copy_kernel(uint8_t *dst, const uint8_t *src, uint64_t nbytes);
 __global__ void oim_fill_kernel(uint8_t *dst, uint8_t fill, uint64_t nbytes);
-size_t lun_kernel_smem_bytes();
+size_t lun_kernel_smem_bytes(bool staged);
 }  // namespace oimgpu
 
 using namespace oimgpu;
@@ -1379,13 +1379,13 @@ static int lun_open_on(const char *ctrlr, int scsi_target_num, int on_device, ui
 	CU_OK(cudaMemsetAsync(L->d_vq_state, 0, sizeof(VqState) * num_queues, L->stream));
 	CU_OK(cudaStreamSynchronize(L->stream));
 	/* more than the 48 KB a kernel gets without asking */
-	CU_OK(cudaFuncSetAttribute(oim_lun_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
-	CU_OK(cudaFuncSetAttribute(oim_lun_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
-	CU_OK(cudaFuncSetAttribute(oim_lun_shared_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
-	CU_OK(cudaFuncSetAttribute(oim_lun_vring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
-	CU_OK(cudaFuncSetAttribute(oim_lun_shared_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes()));
+	CU_OK(cudaFuncSetAttribute(oim_lun_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes(true)));
+	CU_OK(cudaFuncSetAttribute(oim_lun_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes(false)));
+	CU_OK(cudaFuncSetAttribute(oim_lun_shared_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes(true)));
+	CU_OK(cudaFuncSetAttribute(oim_lun_vring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes(false)));
+	CU_OK(cudaFuncSetAttribute(oim_lun_shared_queue_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lun_kernel_smem_bytes(false)));
 	int per_sm = 0;
-	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes()));
+	CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oim_lun_queue_kernel, kThreads, lun_kernel_smem_bytes(true)));
 	if (per_sm < 1) per_sm = 1;
 	L->grid_cap = L->sm_count * per_sm;
 	int rc = refresh_peers_locked(L.get());
@@ -1530,15 +1530,16 @@ static uint32_t share_max_queues(const oimgpu_lun *L)
 
 static void launch_lun_kernel(oimgpu_lun *L, uint32_t grid, bool shared, bool vrings_only = false)
 {
-	const size_t smem = lun_kernel_smem_bytes();
+	/* the kernels with the staged byte-granular path carry the movers' staging buffers; the others keep the L1 */
+	const size_t smem = lun_kernel_smem_bytes(true), lean = lun_kernel_smem_bytes(false);
 	KickHeader *kh = (KickHeader *)L->d_kick;
 	if (!shared && !L->any_mirror && vrings_only && !getenv("OIMGPU_NO_VRING_KERNEL")) {
-		oim_lun_vring_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
+		oim_lun_vring_kernel<<<grid, kThreads, lean, L->stream>>>(L->d_ctx, kh, L->d_desc);
 		return;
 	}
-	if (shared && L->any_mirror) oim_lun_shared_queue_mirror_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
+	if (shared && L->any_mirror) oim_lun_shared_queue_mirror_kernel<<<grid, kThreads, lean, L->stream>>>(L->d_ctx, kh, L->d_desc);
 	else if (shared) oim_lun_shared_queue_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
-	else if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
+	else if (L->any_mirror) oim_lun_queue_mirror_kernel<<<grid, kThreads, lean, L->stream>>>(L->d_ctx, kh, L->d_desc);
 	else oim_lun_queue_kernel<<<grid, kThreads, smem, L->stream>>>(L->d_ctx, kh, L->d_desc);
 }
 
