@@ -30,12 +30,18 @@ CASES = [  # (name, seed, n, kwargs)
     ("fuzz_big", 104, 96, {"max_io_blocks": 1024, "arena_bytes": 24 << 20}),
     ("fuzz_clean", 105, 400, {"include_malformed": False}),
     ("fuzz_removed", 106, 120, {}),
+    # SG lists cut from ONE client buffer: elements continue each other (the CUDA path moves such runs as one segment)
+    ("fuzz_runs", 107, 320, {"contiguous": True}),
+    ("fuzz_runs_big", 108, 96, {"max_io_blocks": 1024, "arena_bytes": 24 << 20, "contiguous": True}),
 ]
 
 
 def main():
     bindings.build()
+    only = set(sys.argv[1:])        # `make_golden.py fuzz_runs ...` regenerates just those
     for name, seed, n, kw in CASES:
+        if only and name not in only:
+            continue
         t = traces.fuzz_trace(n, NUM_BLOCKS, seed=seed, **kw)
         removed = name == "fuzz_removed"
         cpls, arena, store = util.run_oracle(bindings.RefOracle, t, NUM_BLOCKS, removed=removed)
@@ -66,5 +72,6 @@ def primary():
 
 
 if __name__ == "__main__":
-    primary()
+    if len(sys.argv) == 1:
+        primary()
     main()
