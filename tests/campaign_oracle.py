@@ -27,6 +27,18 @@ for seed in range(2000, 2000 + max(1, int(250 * N))):
     except AssertionError as e:
         bad+=1; print("MISMATCH fuzz", seed, str(e)[:300], flush=True)
 print("fuzz done", time.time()-t0, "bad", bad, flush=True)
+# 1b. the same with SG lists cut from ONE client buffer (elements continue each other: the runs the CUDA parser joins)
+for seed in range(2500, 2500 + max(1, int(150 * N))):
+    nb=[32768, 8192, 65536, 16384][seed%4]
+    t=traces.fuzz_trace(400, nb, seed=seed, max_io_blocks=[8,64,300,1024][seed%4], arena_bytes=(48<<20) if seed%4==3 else (16<<20), contiguous=True)
+    a=util.run_oracle(bindings.RefOracle, t, nb)
+    b=util.run_oracle(bindings.PortOracle, t, nb)
+    try:
+        util.assert_cpls_equal(b[0], a[0], t.reqs, f"seed {seed}")
+        assert (a[1]==b[1]).all() and (a[2]==b[2]).all()
+    except AssertionError as e:
+        bad+=1; print("MISMATCH fuzz-runs", seed, str(e)[:300], flush=True)
+print("fuzz-runs done", time.time()-t0, "bad", bad, flush=True)
 # 2. primary commands
 for seed in range(3000, 3000 + max(1, int(100 * N))):
     t=traces.primary_trace(300, seed=seed)
@@ -51,6 +63,14 @@ for seed in range(5000, 5000 + max(1, int(150 * N))):
     ok = len(got)==len(want) and all(g[2]==w[2] and g[1]==w[1] and (g[0]==w[0]).all() for g,w in zip(got,want)) and (gs==ws).all()
     if not ok: bad+=1; print("MISMATCH vring", seed, flush=True)
 print("vring done", time.time()-t0, "bad", bad, flush=True)
+for seed in range(5500, 5500 + max(1, int(80 * N))):     # data descriptors that continue each other in guest memory
+    nb, rq = 32768, TV.make_requests(seed, contiguous=True)
+    ring = [64, 256, 1024][seed % 3]
+    want, ws = TV.run_kicks_oracle(bindings.RefOracle, rq, nb, ring, seed, contiguous=True)
+    got, gs = TV.run_kicks_oracle(bindings.PortOracle, rq, nb, ring, seed, contiguous=True)
+    ok = len(got)==len(want) and all(g[2]==w[2] and g[1]==w[1] and (g[0]==w[0]).all() for g,w in zip(got,want)) and (gs==ws).all()
+    if not ok: bad+=1; print("MISMATCH vring-runs", seed, flush=True)
+print("vring-runs done", time.time()-t0, "bad", bad, flush=True)
 for seed in range(6000, 6000 + max(1, int(60 * N))):
     for kind in ("fuzz","primary"):
         t = TM.multi_trace(seed, kind=kind)
